@@ -1,0 +1,402 @@
+#!/usr/bin/env python
+"""Benchmark of the DyCON loss hot path: fused UnCL + FeCL forward+backward (voxels/s).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path on N B200s
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU
+
+A "step" is one pass of the hot path over one synthetic batch of BASELINE config 2
+(BraTS19 shape: B=4 per GPU, C=2 logits 96^3, embeddings N=1728 x D=256): FeCL forward, UnCL
+forward, then ``(0.5*(f+u)).backward()`` down to the two leaf tensors -- exactly the calls the
+step loop makes (code/train_DyCON_BraTS19.py:346-365).  Under torchrun the batch is sharded
+(weak scaling: B=4 per rank) and the losses all-reduce their 4 partial sums over NCCL.
+Prints ONE JSON line on rank 0 (contract in the task statement / DESIGN.md section "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "voxels/sec fused UnCL+FeCL fwd+bwd"
+U_WEIGHT = 0.5            # args.u_weight, train_DyCON_BraTS19.py:60
+BETA = 1.58               # mid-schedule adaptive_beta (5.0 -> 0.5)
+EPOCH = 100
+CTOR = dict(temperature=0.6, gamma=2.0, use_focal=True, rampup_epochs=1500)   # train_DyCON_BraTS19.py:287-288
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default="brats19")
+    ap.add_argument("--batch", type=int, default=4, help="samples per GPU")
+    ap.add_argument("--dim", type=int, default=256)
+    ap.add_argument("--precision", default=None, help="FeCL similarity arithmetic: fp32 | bf16")
+    ap.add_argument("--sets", type=int, default=4, help="rotating input sets (defeats the 126 MB L2)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm": p["hbm_gbs"], "tensor_burst": p["bf16_tflops"],
+                "tensor": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "source": "fallback"}
+
+
+def workload_name(args, n_gpus):
+    from dycon_paper_replication_b200.synthetic import SHAPES, feature_grid
+    sp = SHAPES[args.shape][0]
+    g = feature_grid(args.shape)
+    return (f"{args.shape}: B={args.batch}/GPU x {n_gpus} GPU, C=2 logits {sp[0]}x{sp[1]}x{sp[2]}, "
+            f"embeddings N={g[0] * g[1] * g[2]} D={args.dim}, structured features, blob mask, focal+teacher")
+
+
+# ----------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, physical_index):
+        self.index = physical_index
+        self.file = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                                          "-lms", "50"], stdout=self.file, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+        self.windows = []
+
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.file.flush()
+        rows = []
+        import datetime
+        for line in open(self.file.name):
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                idx, sm, mx = int(parts[1]), float(parts[2]), float(parts[3])
+            except ValueError:
+                continue
+            if idx == self.index:
+                rows.append((ts, sm, mx, parts[4], parts[5:9]))
+        os.unlink(self.file.name)
+        inside = [r for r in rows if any(a - 0.03 <= r[0] <= b + 0.03 for a, b in self.windows)]
+        note = []
+        if len(inside) < 2:
+            inside, note = rows, ["too few samples inside the timed window; using all samples of the run"]
+        if not inside:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in inside for n, v in zip(names, r[4]) if v.lower().startswith("active")})
+        power = [float(r[3]) for r in inside if r[3].replace(".", "", 1).isdigit()]
+        return {"sm_mhz": statistics.median(r[1] for r in inside), "sm_max_mhz": max(r[2] for r in inside),
+                "reasons": reasons + note, "samples": len(inside), "power_w_max": max(power) if power else None}
+
+
+def physical_gpu_index(local_index):
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    if vis:
+        try:
+            return int(vis.split(",")[local_index])
+        except (ValueError, IndexError):
+            return local_index
+    return local_index
+
+
+# ----------------------------------------------------------------------------------------- CPU arm
+def cpu_time_reference(args, steps, warmup, budget_s=150.0):
+    """Times the oracle port (oracle/torch_port.py: the reference's op chain + autograd) on the host
+    cores.  Returns (voxels_per_s, ms_per_step, sample description, cores)."""
+    import torch
+    from dycon_paper_replication_b200.synthetic import make_inputs
+    from oracle import torch_port
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+
+    def one(inp):
+        s = inp.s_logits.clone().requires_grad_(True)
+        f = inp.feat.clone().requires_grad_(True)
+        fl = torch_port.fecl_loss(f, inp.mask, inp.teacher, None, EPOCH, **CTOR)
+        ul = torch_port.uncl_loss(s, inp.t_logits, BETA)
+        (U_WEIGHT * (fl + ul)).backward()
+        return float((fl + ul).detach())
+
+    batch = args.batch
+    inp = make_inputs(args.shape, batch=batch, dim=args.dim)
+    t0 = time.perf_counter()
+    one(inp)
+    first = time.perf_counter() - t0
+    if first * (steps + warmup) > budget_s and batch > 1:
+        batch = 1                          # bounded sample: one sample of the batch per step
+        inp = make_inputs(args.shape, batch=batch, dim=args.dim)
+        one(inp)
+    for _ in range(max(0, warmup - 1)):
+        one(inp)
+    times = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        one(inp)
+        times.append(time.perf_counter() - t0)
+    med = statistics.median(times)
+    sample = (f"{steps} timed steps (after {warmup} warm-up) of UnCL+FeCL fwd+bwd on B={batch} of the "
+              f"{args.batch}-sample {args.shape} batch, fp32, {torch.get_num_threads()} torch threads, median")
+    return inp.voxels / med, med * 1e3, sample, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vps, ms, sample, cores = cpu_time_reference(args, args.steps, args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": vps, "unit": "voxels/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args, 1), "arm": "host CPU only; GPUs idle"},
+            "cpu_baseline": {"value": vps, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": vps, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from dycon_paper_replication_b200 import FeCLoss, UnCLoss, _lib, dycon_losses, update_ema_variables
+    from dycon_paper_replication_b200.synthetic import make_inputs, unet3d_param_shapes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    group = None
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        group = dist.group.WORLD
+    n_gpus = world
+    precision = args.precision or dycon_losses.default_fecl_precision()
+    gb = args.batch * world
+    fecl = FeCLoss(dev, precision=precision, process_group=group, global_batch=gb if world > 1 else None, **CTOR)
+    uncl = UnCLoss(process_group=group, global_batch=gb if world > 1 else None)
+
+    # rotating input sets, resident in HBM before the timed region (different seeds per rank and set)
+    host_sets = [make_inputs(args.shape, batch=args.batch, dim=args.dim, seed=1337 + 101 * rank + k)
+                 for k in range(args.sets)]
+    sets = []
+    for h in host_sets:
+        d = h.to(dev)
+        sets.append((d.s_logits.requires_grad_(True), d.t_logits, d.feat.requires_grad_(True), d.teacher, d.mask))
+    voxels = host_sets[0].voxels
+    B, N, D = host_sets[0].feat.shape
+    set_bytes = sum(x.numel() * 4 for x in (host_sets[0].s_logits, host_sets[0].t_logits, host_sets[0].feat,
+                                            host_sets[0].teacher)) + 3 * voxels * 4
+
+    def step(k):
+        s, t, f, tf, m = sets[k % len(sets)]
+        s.grad = None
+        f.grad = None
+        loss = U_WEIGHT * (fecl(feat=f, mask=m, teacher_feat=tf, gambling_uncertainty=None, epoch=EPOCH)
+                           + uncl(s, t, BETA))
+        loss.backward()
+        return loss
+
+    def fence():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    sampler = ClockSampler(physical_gpu_index(local)) if rank == 0 else None
+    for k in range(args.warmup):
+        step(k)
+    fence()
+    launches0 = _lib.lib().dycon_launch_count()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    with dycon_losses.kernel_timer() as kt:
+        start.record()
+        for k in range(args.steps):
+            loss = step(args.warmup + k)
+        end.record()
+        fence()
+        calls = kt.ms()
+    w1 = time.time()
+    if sampler:
+        sampler.window(w0, w1)
+    launches = _lib.lib().dycon_launch_count() - launches0
+    ms_total = start.elapsed_time(end)
+    final_loss = float(loss)
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t)
+    ms_step = ms_total / args.steps
+    value = voxels * world / (ms_step * 1e-3)
+
+    # ---- end to end through the public API with HOST (pinned) buffers ----------------------------
+    e2e = None
+    if not args.no_e2e:
+        h = host_sets[0]
+        pin = lambda x: x.contiguous().pin_memory()
+        hs, ht = pin(h.s_logits), pin(h.t_logits)
+        hf, htf = pin(h.feat.transpose(1, 2)), pin(h.teacher.transpose(1, 2))      # (B,D,N) storage order
+        hm = pin(h.mask)
+        ds, dt = torch.empty_like(hs, device=dev), torch.empty_like(ht, device=dev)
+        dfs, dtfs = torch.empty_like(hf, device=dev), torch.empty_like(htf, device=dev)
+        dm = torch.empty_like(hm, device=dev)
+        out_gs = torch.empty_like(hs).pin_memory()
+        out_gf = torch.empty((B, N, D)).pin_memory()
+        out_loss = torch.empty(()).pin_memory()
+        h2d = sum(x.numel() * 4 for x in (hs, ht, hf, htf, hm))
+        d2h = (out_gs.numel() + out_gf.numel() + 1) * 4
+
+        def e2e_step():
+            ds.copy_(hs, non_blocking=True)
+            dt.copy_(ht, non_blocking=True)
+            dfs.copy_(hf, non_blocking=True)
+            dtfs.copy_(htf, non_blocking=True)
+            dm.copy_(hm, non_blocking=True)
+            s = ds.detach().requires_grad_(True)
+            f = dfs.transpose(1, 2).detach().requires_grad_(True)          # caller strides (D*N, 1, N)
+            loss = U_WEIGHT * (fecl(feat=f, mask=dm, teacher_feat=dtfs.transpose(1, 2), gambling_uncertainty=None,
+                                    epoch=EPOCH) + uncl(s, dt, BETA))
+            loss.backward()
+            out_loss.copy_(loss.detach(), non_blocking=True)
+            out_gs.copy_(s.grad, non_blocking=True)
+            out_gf.copy_(f.grad, non_blocking=True)
+
+        for _ in range(max(3, min(args.warmup, 5))):
+            e2e_step()
+        fence()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e0.record()
+        for _ in range(args.steps):
+            e2e_step()
+        e1.record()
+        fence()
+        w1 = time.time()
+        if sampler:
+            sampler.window(w0, w1)
+        ms_e2e = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms_e2e = float(t)
+        e2e = {"value": voxels * world / (ms_e2e / args.steps * 1e-3), "unit": "voxels/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+               "note": "pinned host inputs copied in, loss + both gradients copied out, every step"}
+
+    # ---- EMA (reported beside the metric, not part of it) ----------------------------------------
+    shapes = unet3d_param_shapes()
+    mk = lambda seed: torch.nn.ParameterList([torch.nn.Parameter(torch.randn(*s, device=dev)) for s in shapes])
+    bags = [(mk(0), mk(1)) for _ in range(6)]      # 6 x 49 MB > L2
+    n_params = sum(p.numel() for p in bags[0][0])
+    for i in range(3):
+        update_ema_variables(bags[i % 6][0], bags[i % 6][1], 0.99, 10 + i)
+    fence()
+    with dycon_losses.kernel_timer() as kt:
+        for i in range(24):
+            update_ema_variables(bags[i % 6][0], bags[i % 6][1], 0.99, 100 + i)
+        ema_ms = statistics.median(kt.ms()["ema"])
+
+    clocks = sampler.stop() if sampler else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline ------------------------------------------------------------------------------------
+    pk = peaks()
+    avg = {k: sum(v) / len(v) for k, v in calls.items()}
+    flops_fwd = 4.0 * B * N * N * D            # S (2) + cross (2)         SURVEY.md 8(d)
+    flops_bwd = 6.0 * B * N * N * D            # (G+G^T)F (4) + Gc T (2)
+    of = pk["source"]
+    fam = {
+        "uncl_fwd": {"bound": "hbm", "algorithmic": 16.0 * voxels, "moved": 20.0 * voxels},
+        "uncl_bwd": {"bound": "hbm", "algorithmic": 24.0 * voxels, "moved": 12.0 * voxels},
+        "fecl_fwd": {"bound": "tensor", "algorithmic": flops_fwd},
+        "fecl_bwd": {"bound": "tensor", "algorithmic": flops_bwd},
+    }
+    roof_all = {}
+    for name, spec in fam.items():
+        if name not in avg:
+            continue
+        sec = avg[name] * 1e-3
+        if spec["bound"] == "hbm":
+            ach, peak, unit = spec["algorithmic"] / sec / 1e9, pk["hbm"], "GB/s"
+        else:
+            ach, peak, unit = spec["algorithmic"] / sec / 1e12, pk["tensor"], "TFLOP/s"
+        roof_all[name] = {"bound": spec["bound"], "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
+                          "traffic": None, "avg_ms": avg[name], "peak_source": f"of {of}"}
+        if "moved" in spec:
+            roof_all[name]["moved_gbs"] = spec["moved"] / sec / 1e9
+    if "uncl_fwd" in avg and "uncl_bwd" in avg:
+        sec = (avg["uncl_fwd"] + avg["uncl_bwd"]) * 1e-3
+        roof_all["uncl_pair"] = {"bound": "hbm", "achieved": 40.0 * voxels / sec / 1e9, "peak": pk["hbm"],
+                                 "unit": "GB/s", "frac": 40.0 * voxels / sec / 1e9 / pk["hbm"], "traffic": None,
+                                 "moved_gbs": 32.0 * voxels / sec / 1e9, "avg_ms": sec * 1e3,
+                                 "note": "40 B/voxel algorithmic (SURVEY 8d); the stash design moves 32 B/voxel"}
+    roof_all["ema"] = {"bound": "hbm", "achieved": 12.0 * n_params / (ema_ms * 1e-3) / 1e9, "peak": pk["hbm"],
+                       "unit": "GB/s", "frac": 12.0 * n_params / (ema_ms * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
+                       "avg_ms": ema_ms, "params": n_params}
+    dominant = max((k for k in fam if k in avg), key=lambda k: avg[k])
+    roofline = dict(roof_all[dominant], kernel=dominant,
+                    share_of_step=avg[dominant] / sum(avg[k] for k in fam if k in avg))
+
+    line = {"metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "bf16 MMA operands, f32 accumulate/epilogue",
+            "data": "synthetic",
+            "config": {"workload": workload_name(args, n_gpus), "fecl_precision": precision,
+                       "l2": f"rotating {args.sets} input sets of {set_bytes / 1e6:.0f} MB each (> 126 MB L2), no flush",
+                       "loss_check": final_loss},
+            "roofline": roofline, "roofline_all": roof_all,
+            "gpu_launches": int(launches), "clocks": clocks}
+    if e2e:
+        line["e2e"] = e2e
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        vps, ms, sample, cores = cpu_time_reference(args, steps=3, warmup=1)
+        line["cpu_baseline"] = {"value": vps, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample,
+                                "ms_per_step": ms}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -1,0 +1,74 @@
+// C-ABI entry points of FeCL (include/dycon_b200.h): argument validation + dispatch on the
+// similarity arithmetic (fp32 SIMT tiles / bf16 tcgen05 tiles).
+#include "fecl_internal.h"
+
+using namespace dycon;
+
+namespace {
+
+int check_shape(int B, int N, int D, int precision) {
+  DYCON_REQUIRE(B > 0 && N > 0 && D > 0, DYCON_ERR_ARG, "FeCL: B=%d N=%d D=%d must be positive", B, N, D);
+  DYCON_REQUIRE(precision == DYCON_FECL_FP32 || precision == DYCON_FECL_BF16, DYCON_ERR_ARG,
+                "FeCL: unknown precision %d", precision);
+  DYCON_REQUIRE((long long)N * N < (1LL << 40), DYCON_ERR_UNSUPPORTED, "FeCL: N=%d too large", N);
+  return DYCON_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t dycon_fecl_state_bytes(int B, int N, int D, int has_teacher, int precision) {
+  if (B <= 0 || N <= 0 || D <= 0) return 0;
+  return precision == DYCON_FECL_BF16 ? fecl_tc_state_bytes(B, N, D, has_teacher)
+                                      : fecl_simt_state_bytes(B, N, D, has_teacher);
+}
+
+size_t dycon_fecl_workspace_bytes(int B, int N, int D, int precision) {
+  if (B <= 0 || N <= 0 || D <= 0) return 0;
+  return precision == DYCON_FECL_BF16 ? fecl_tc_workspace_bytes(B, N, D) : fecl_simt_workspace_bytes(B, N, D);
+}
+
+int dycon_fecl_fwd(const float* feat, int64_t f_sb, int64_t f_sn, int64_t f_sd, const float* teacher, int64_t t_sb,
+                   int64_t t_sn, int64_t t_sd, const float* labels, const float* row_weight, int B, int N, int D,
+                   float inv_tau, float gamma, int use_focal, float cross_thresh, float lambda_cross, double inv_rows,
+                   int precision, void* state, size_t state_bytes, double* sums_out, float* loss_out, void* workspace,
+                   size_t workspace_bytes, dycon_stream_t stream) {
+  if (int rc = check_shape(B, N, D, precision)) return rc;
+  DYCON_REQUIRE(feat && labels && state && sums_out && workspace, DYCON_ERR_ARG,
+                "FeCL fwd: NULL feat/labels/state/sums_out/workspace");
+  DYCON_REQUIRE(aligned(feat, 4) && aligned(teacher, 4) && aligned(labels, 4) && aligned(row_weight, 4) &&
+                    aligned(state, 128) && aligned(sums_out, 8) && aligned(workspace, 16),
+                DYCON_ERR_ARG, "FeCL fwd: misaligned pointer");
+  DYCON_REQUIRE(f_sn > 0 && f_sd > 0 && (teacher == nullptr || (t_sn > 0 && t_sd > 0)), DYCON_ERR_ARG,
+                "FeCL fwd: non-positive strides");
+  const int has_teacher = teacher != nullptr;
+  DYCON_REQUIRE(state_bytes >= dycon_fecl_state_bytes(B, N, D, has_teacher, precision), DYCON_ERR_WORKSPACE,
+                "FeCL fwd: state %zu < %zu bytes", state_bytes, dycon_fecl_state_bytes(B, N, D, has_teacher, precision));
+  DYCON_REQUIRE(workspace_bytes >= dycon_fecl_workspace_bytes(B, N, D, precision), DYCON_ERR_WORKSPACE,
+                "FeCL fwd: workspace %zu < %zu bytes", workspace_bytes, dycon_fecl_workspace_bytes(B, N, D, precision));
+  FeclProblem p{B, N, D, has_teacher,
+                FeclScalars{inv_tau, gamma, cross_thresh, lambda_cross, (use_focal && row_weight == nullptr) ? 1 : 0},
+                inv_rows};
+  FeclFwdArgs a{feat, f_sb, f_sn, f_sd, teacher, t_sb, t_sn, t_sd, labels, row_weight, state, sums_out, loss_out, workspace};
+  return precision == DYCON_FECL_BF16 ? fecl_tc_fwd(p, a, as_stream(stream)) : fecl_simt_fwd(p, a, as_stream(stream));
+}
+
+int dycon_fecl_bwd(const void* state, size_t state_bytes, const float* labels, int B, int N, int D, int has_teacher,
+                   float inv_tau, float gamma, int use_focal, int has_row_weight, float cross_thresh,
+                   float lambda_cross, int precision, const double* cross_cnt, const float* grad_out,
+                   float* grad_feat, dycon_stream_t stream) {
+  if (int rc = check_shape(B, N, D, precision)) return rc;
+  DYCON_REQUIRE(state && labels && grad_out && grad_feat, DYCON_ERR_ARG, "FeCL bwd: NULL state/labels/grad_out/grad_feat");
+  DYCON_REQUIRE(!has_teacher || cross_cnt, DYCON_ERR_ARG, "FeCL bwd: the teacher term needs cross_cnt");
+  DYCON_REQUIRE(aligned(state, 128) && aligned(grad_feat, 16) && aligned(cross_cnt, 8), DYCON_ERR_ARG,
+                "FeCL bwd: misaligned pointer");
+  DYCON_REQUIRE(state_bytes >= dycon_fecl_state_bytes(B, N, D, has_teacher, precision), DYCON_ERR_WORKSPACE,
+                "FeCL bwd: state %zu < %zu bytes", state_bytes, dycon_fecl_state_bytes(B, N, D, has_teacher, precision));
+  FeclProblem p{B, N, D, has_teacher ? 1 : 0,
+                FeclScalars{inv_tau, gamma, cross_thresh, lambda_cross, (use_focal && !has_row_weight) ? 1 : 0}, 0.0};
+  FeclBwdArgs a{state, labels, cross_cnt, grad_out, grad_feat};
+  return precision == DYCON_FECL_BF16 ? fecl_tc_bwd(p, a, as_stream(stream)) : fecl_simt_bwd(p, a, as_stream(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,402 @@
+"""Drop-in replacement for the reference's ``code/utils/dycon_losses.py`` on B200.
+
+Same names, signatures, defaults and autograd behaviour as the reference module
+(rogeliorjr/DyCON_Paper_Replication), so ``from utils import dycon_losses`` call sites
+(code/train_DyCON_BraTS19.py:286-288,295,346-351 and the Pancreas / ISLES22 twins) work
+unchanged; the arithmetic runs in hand-written sm_100a CUDA kernels behind the C ABI of
+``include/dycon_b200.h``.  There is no CPU or eager-PyTorch fallback: CPU tensors raise.
+
+  UnCLoss().forward(s_logits, t_logits, beta)                       dycon_losses.py:50-118
+  FeCLoss(device, temperature, gamma, use_focal, rampup_epochs,
+          lambda_cross).forward(feat, mask, teacher_feat,
+          gambling_uncertainty, epoch)                              dycon_losses.py:120-235
+  adaptive_beta / sigmoid_rampup / gambling_softmax                 dycon_losses.py:8-47
+  update_ema_variables(model, ema_model, alpha, global_step)        train_DyCON_BraTS19.py:155-164
+
+Extensions that the reference does not have (all optional, keyword-only):
+  * ``FeCLoss(..., precision="bf16"|"fp32")`` -- similarity arithmetic (tcgen05 bf16 tiles with
+    fp32 accumulation, or exact fp32 SIMT tiles).
+  * ``process_group=`` on both modules -- the batch is sharded over ranks; partial sums and the
+    batch-global hard-negative count are all-reduced (one 4-double message per step, see
+    ``dycon_paper_replication_b200.sharded``).
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+import os
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+__all__ = ["UnCLoss", "FeCLoss", "adaptive_beta", "sigmoid_rampup", "gambling_softmax",
+           "update_ema_variables"]
+
+
+# =========================================================================== host scalars
+def adaptive_beta(epoch, total_epochs, max_beta=5.0, min_beta=0.5):
+    """beta decays geometrically from max_beta (epoch 0) to min_beta (dycon_losses.py:8-12)."""
+    return max_beta * ((min_beta / max_beta) ** (epoch / total_epochs))
+
+
+def sigmoid_rampup(current_epoch, total_rampup_epochs, min_threshold, max_threshold, steepness=5.0):
+    """exp(-steepness*(1-e/E)^2) ramp from min to max threshold (dycon_losses.py:28-47)."""
+    if total_rampup_epochs == 0:
+        return max_threshold
+    e = max(0.0, min(float(current_epoch), total_rampup_epochs))
+    phase = 1.0 - (e / total_rampup_epochs)
+    return min_threshold + (max_threshold - min_threshold) * math.exp(-steepness * (phase ** 2))
+
+
+def gambling_softmax(logits):
+    """Un-stabilised softmax over dim 1 with a 1e-18 guard (dycon_losses.py:14-26).  Only referenced
+    from commented-out code in the reference; kept as a thin PyTorch function for API parity."""
+    ex = torch.exp(logits)
+    return ex / (ex.sum(dim=1, keepdim=True) + 1e-18)
+
+
+# =========================================================================== plumbing
+_workspaces = {}
+_timer = None     # {name: [(start_event, end_event), ...]} while a kernel_timer() is active
+
+
+class kernel_timer:
+    """Measurement aid for bench.py: CUDA events (on the launching stream) around every C-ABI call
+    made while the context is active.  ``ms()`` -> {call name: [milliseconds per call]}."""
+
+    def __enter__(self):
+        global _timer
+        self.records = {}
+        _timer = self.records
+        return self
+
+    def __exit__(self, *exc):
+        global _timer
+        _timer = None
+        return False
+
+    def ms(self):
+        torch.cuda.synchronize()
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in self.records.items()}
+
+
+def _tick():
+    if _timer is None:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _tock(name, start):
+    if start is not None and _timer is not None:
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        _timer.setdefault(name, []).append((start, end))
+
+
+def _stream_ptr(device):
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _workspace(device, kind, nbytes):
+    """Zero-filled reduction workspace, one per (device, stream, kind); kernels leave it zeroed."""
+    key = (device.index, _stream_ptr(device), kind)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.zeros(max(int(nbytes), 16), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def _require_cuda_fp32(name, x):
+    if not torch.is_tensor(x):
+        raise TypeError(f"{name} must be a tensor")
+    if not x.is_cuda:
+        raise RuntimeError(f"{name} is on {x.device}: the DyCON B200 kernels have no CPU fallback")
+    if x.dtype != torch.float32:
+        raise TypeError(f"{name} must be float32 (got {x.dtype}); the reference runs fp32 end to end")
+
+
+def _ptr(x):
+    return ctypes.c_void_p(x.data_ptr()) if x is not None else None
+
+
+def _scalar_grad(go):
+    go = go.reshape(()).to(torch.float32)
+    return go.contiguous()
+
+
+# =========================================================================== UnCL
+class _UnCLFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s_logits, t_logits, beta, process_group, global_batch):
+        _require_cuda_fp32("s_logits", s_logits)
+        _require_cuda_fp32("t_logits", t_logits)
+        if s_logits.shape != t_logits.shape or s_logits.dim() < 3:
+            raise ValueError(f"UnCLoss expects equal (B, C, spatial...) shapes, got {tuple(s_logits.shape)} "
+                             f"and {tuple(t_logits.shape)}")
+        if s_logits.device != t_logits.device:
+            raise RuntimeError("s_logits and t_logits are on different devices")
+        dev = s_logits.device
+        s = s_logits.contiguous()
+        t = t_logits.detach().contiguous()
+        B, Cn = s.shape[0], s.shape[1]
+        V = s[0, 0].numel()
+        gb = int(global_batch) if global_batch is not None else B
+        inv_count = 1.0 / (gb * V)
+        with torch.cuda.device(dev):
+            _lib.require_b200(dev.index)
+            L = _lib.lib()
+            ws = _workspace(dev, "uncl", L.dycon_uncl_workspace_bytes())
+            stash = torch.empty(B * V, dtype=torch.float32, device=dev) if Cn == 2 else None
+            total = torch.empty(1, dtype=torch.float64, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            t0 = _tick()
+            _lib.check(L.dycon_uncl_fwd(_ptr(s), _ptr(t), B, Cn, V, float(beta), inv_count, _ptr(stash),
+                                        _ptr(total), _ptr(loss), _ptr(ws), ws.numel(), _stream_ptr(dev)),
+                       "dycon_uncl_fwd")
+            _tock("uncl_fwd", t0)
+            if process_group is not None:
+                torch.distributed.all_reduce(total, group=process_group)
+                loss = (total[0] * inv_count).to(torch.float32)
+        ctx.dims = (B, Cn, V, float(beta), inv_count)
+        ctx.shape = s_logits.shape
+        if Cn == 2:
+            ctx.save_for_backward(stash)
+        else:
+            ctx.save_for_backward(s, t)
+        return loss
+
+    @staticmethod
+    def backward(ctx, go):
+        B, Cn, V, beta, inv_count = ctx.dims
+        saved = ctx.saved_tensors
+        dev = saved[0].device
+        grad = torch.empty(ctx.shape, dtype=torch.float32, device=dev)
+        go = _scalar_grad(go)
+        with torch.cuda.device(dev):
+            L = _lib.lib()
+            t0 = _tick()
+            if Cn == 2:
+                rc = L.dycon_uncl_bwd(None, None, _ptr(saved[0]), B, Cn, V, beta, inv_count, _ptr(go), _ptr(grad),
+                                      _stream_ptr(dev))
+            else:
+                rc = L.dycon_uncl_bwd(_ptr(saved[0]), _ptr(saved[1]), None, B, Cn, V, beta, inv_count, _ptr(go),
+                                      _ptr(grad), _stream_ptr(dev))
+            _lib.check(rc, "dycon_uncl_bwd")
+            _tock("uncl_bwd", t0)
+        return grad, None, None, None, None
+
+
+class UnCLoss(nn.Module):
+    """Uncertainty-aware student/teacher consistency (reference: dycon_losses.py:50-118).
+
+    ``forward(s_logits, t_logits, beta)`` with logits of shape (B, C, H, W, D) returns the 0-dim
+    fp32 loss.  Only ``s_logits`` receives a gradient: the teacher forward runs under
+    ``torch.no_grad()`` in every reference call site (train_DyCON_BraTS19.py:305-306); a
+    ``t_logits`` that requires grad raises instead of being silently dropped.
+    """
+
+    def __init__(self, process_group=None, global_batch=None):
+        super().__init__()
+        self.process_group = process_group
+        self.global_batch = global_batch
+
+    def forward(self, s_logits, t_logits, beta):
+        if torch.is_tensor(t_logits) and t_logits.requires_grad and torch.is_grad_enabled():
+            raise RuntimeError("UnCLoss: t_logits requires grad; the teacher branch is a constant in DyCON "
+                               "(detach it, as the reference's no_grad teacher forward does)")
+        if torch.is_tensor(beta):
+            beta = float(beta)
+        return _UnCLFunction.apply(s_logits, t_logits, beta, self.process_group, self.global_batch)
+
+
+# =========================================================================== FeCL
+_PRECISIONS = {"fp32": _lib.FECL_FP32, "bf16": _lib.FECL_BF16}
+
+
+def default_fecl_precision():
+    return os.environ.get("DYCON_FECL_PRECISION", "fp32")
+
+
+class _FeCLFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, feat, labels, teacher, row_weight, inv_tau, gamma, use_focal, cross_thresh,
+                lambda_cross, precision, process_group, global_batch):
+        dev = feat.device
+        B, N, D = feat.shape
+        gb = int(global_batch) if global_batch is not None else B
+        inv_rows = 1.0 / (gb * N)
+        has_teacher = teacher is not None
+        with torch.cuda.device(dev):
+            _lib.require_b200(dev.index)
+            L = _lib.lib()
+            sbytes = L.dycon_fecl_state_bytes(B, N, D, int(has_teacher), precision)
+            wbytes = L.dycon_fecl_workspace_bytes(B, N, D, precision)
+            state = torch.empty(max(sbytes, 16), dtype=torch.uint8, device=dev)
+            ws = _workspace(dev, f"fecl{precision}", wbytes)
+            sums = torch.empty(3, dtype=torch.float64, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            ts = teacher.stride() if has_teacher else (0, 0, 0)
+            t0 = _tick()
+            _lib.check(L.dycon_fecl_fwd(_ptr(feat), *feat.stride(), _ptr(teacher), *ts, _ptr(labels),
+                                        _ptr(row_weight), B, N, D, inv_tau, gamma, int(use_focal), cross_thresh,
+                                        lambda_cross, inv_rows, precision, _ptr(state), state.numel(), _ptr(sums),
+                                        _ptr(loss), _ptr(ws), ws.numel(), _stream_ptr(dev)),
+                       "dycon_fecl_fwd")
+            _tock("fecl_fwd", t0)
+            if process_group is not None:
+                torch.distributed.all_reduce(sums, group=process_group)
+                cross = sums[1] / (sums[2] + 1e-18) if has_teacher else 0.0
+                loss = (sums[0] * inv_rows + lambda_cross * cross).to(torch.float32)
+        ctx.save_for_backward(state, labels, sums)
+        ctx.cfg = (B, N, D, has_teacher, inv_tau, gamma, int(use_focal), row_weight is not None, cross_thresh,
+                   lambda_cross, precision)
+        return loss
+
+    @staticmethod
+    def backward(ctx, go):
+        state, labels, sums = ctx.saved_tensors
+        B, N, D, has_teacher, inv_tau, gamma, use_focal, has_rw, cross_thresh, lambda_cross, precision = ctx.cfg
+        dev = state.device
+        grad = torch.empty((B, N, D), dtype=torch.float32, device=dev)
+        go = _scalar_grad(go)
+        with torch.cuda.device(dev):
+            t0 = _tick()
+            _lib.check(_lib.lib().dycon_fecl_bwd(_ptr(state), state.numel(), _ptr(labels), B, N, D, int(has_teacher),
+                                                 inv_tau, gamma, use_focal, int(has_rw), cross_thresh, lambda_cross,
+                                                 precision, ctypes.c_void_p(sums.data_ptr() + 16), _ptr(go),
+                                                 _ptr(grad), _stream_ptr(dev)),
+                       "dycon_fecl_bwd")
+            _tock("fecl_bwd", t0)
+        return (grad,) + (None,) * 11
+
+
+class FeCLoss(nn.Module):
+    """Feature contrastive loss with focal positives and the teacher hard-negative branch
+    (reference: dycon_losses.py:120-235; constructor :141-148, forward :150-235).
+
+    feat (B,N,D) student embeddings (any strides), mask (B,1,N) labels, teacher_feat (B,N,D) or
+    None, gambling_uncertainty (B,N) or None (a per-row weight that also disables the focal
+    weights, :209-211), epoch -> the sigmoid_rampup thresholds.  Returns the 0-dim fp32 loss;
+    the gradient flows to ``feat`` only.
+    """
+
+    def __init__(self, device, temperature=0.6, gamma=2.0, use_focal=False, rampup_epochs=2000,
+                 lambda_cross=1.0, *, precision=None, process_group=None, global_batch=None):
+        super().__init__()
+        self.device = device
+        self.temperature = temperature
+        self.gamma = gamma
+        self.use_focal = use_focal
+        self.rampup_epochs = rampup_epochs
+        self.lambda_cross = lambda_cross
+        self.precision = precision or default_fecl_precision()
+        if self.precision not in _PRECISIONS:
+            raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
+        self.process_group = process_group
+        self.global_batch = global_batch
+
+    def forward(self, feat, mask, teacher_feat=None, gambling_uncertainty=None, epoch=0):
+        _require_cuda_fp32("feat", feat)
+        if feat.dim() != 3:
+            raise ValueError(f"feat must be (B, N, D), got {tuple(feat.shape)}")
+        B, N, D = feat.shape
+        grad_on = torch.is_grad_enabled()
+        if teacher_feat is not None:
+            _require_cuda_fp32("teacher_feat", teacher_feat)
+            if teacher_feat.shape != feat.shape:
+                raise ValueError("teacher_feat must have the shape of feat")
+            if teacher_feat.requires_grad and grad_on:
+                raise RuntimeError("FeCLoss: teacher_feat requires grad; the teacher is a constant in DyCON")
+            teacher_feat = teacher_feat.detach()
+        if not torch.is_tensor(mask) or not mask.is_cuda:
+            raise RuntimeError("mask must be a CUDA tensor (no CPU fallback)")
+        if mask.is_floating_point() and mask.requires_grad and grad_on:
+            raise RuntimeError("FeCLoss: mask requires grad; labels are constants")
+        if mask.numel() != B * N:
+            raise ValueError(f"mask must be (B, 1, N) = ({B}, 1, {N}), got {tuple(mask.shape)}")
+        labels = mask.detach().reshape(B, N).to(torch.float32).contiguous()
+        rw = None
+        if gambling_uncertainty is not None:
+            if gambling_uncertainty.requires_grad and grad_on:
+                raise RuntimeError("FeCLoss: gambling_uncertainty requires grad; it is a constant weight")
+            if gambling_uncertainty.numel() != B * N:
+                raise ValueError("gambling_uncertainty must be (B, N)")
+            rw = gambling_uncertainty.detach().reshape(B, N).to(device=feat.device, dtype=torch.float32).contiguous()
+        # host scalars, recomputed every call like the reference (:199-200, :222)
+        cross_thresh = sigmoid_rampup(epoch, self.rampup_epochs, min_threshold=0.3, max_threshold=0.5)
+        return _FeCLFunction.apply(feat, labels, teacher_feat, rw, 1.0 / float(self.temperature), float(self.gamma),
+                                   bool(self.use_focal), float(cross_thresh), float(self.lambda_cross),
+                                   _PRECISIONS[self.precision], self.process_group, self.global_batch)
+
+
+# =========================================================================== EMA
+class _EmaPlan:
+    """ctypes pointer tables for one (student, teacher) parameter set, rebuilt only if a pointer moves."""
+
+    def __init__(self):
+        self.key = None
+        self.arrays = None
+
+    def tables(self, ema_params, params):
+        key = tuple(p.data_ptr() for p in ema_params) + tuple(p.data_ptr() for p in params)
+        if key != self.key:
+            n = len(params)
+            e = (ctypes.c_void_p * n)(*[p.data_ptr() for p in ema_params])
+            s = (ctypes.c_void_p * n)(*[p.data_ptr() for p in params])
+            c = (ctypes.c_int64 * n)(*[p.numel() for p in params])
+            self.key, self.arrays = key, (e, s, c, n)
+        return self.arrays
+
+
+_ema_plans = {}
+
+
+def _dense_like(a, b):
+    """Same shape and strides, and dense in memory (contiguous or channels-last)."""
+    if a.shape != b.shape or a.stride() != b.stride():
+        return False
+    if a.is_contiguous():
+        return True
+    if a.dim() == 4:
+        return a.is_contiguous(memory_format=torch.channels_last)
+    if a.dim() == 5:
+        return a.is_contiguous(memory_format=torch.channels_last_3d)
+    return False
+
+
+def update_ema_variables(model, ema_model, alpha, global_step):
+    """Mean-teacher update, one multi-tensor launch (reference: train_DyCON_BraTS19.py:155-164).
+
+    alpha = min(1 - 1/(global_step+1), alpha); ema = ema*alpha + (1-alpha)*param over
+    ``parameters()`` only (buffers are not averaged), unwrapping ``.module`` like the reference.
+    """
+    alpha = min(1 - 1 / (global_step + 1), alpha)
+    src = model.module if hasattr(model, "module") else model
+    dst = ema_model.module if hasattr(ema_model, "module") else ema_model
+    params = [p.data for p in src.parameters()]
+    ema_params = [p.data for p in dst.parameters()]
+    n = min(len(params), len(ema_params))          # zip() semantics of the reference loop
+    params, ema_params = params[:n], ema_params[:n]
+    if n == 0:
+        return
+    dev = ema_params[0].device
+    for e, p in zip(ema_params, params):
+        _require_cuda_fp32("ema parameter", e)
+        _require_cuda_fp32("parameter", p)
+        if e.device != dev or p.device != dev:
+            raise RuntimeError("update_ema_variables: parameters span several devices")
+        if not _dense_like(e, p):
+            raise RuntimeError("update_ema_variables: student/teacher parameters must be dense with equal strides")
+    plan = _ema_plans.setdefault((id(src), id(dst)), _EmaPlan())
+    e_arr, p_arr, c_arr, n = plan.tables(ema_params, params)
+    with torch.cuda.device(dev):
+        _lib.require_b200(dev.index)
+        t0 = _tick()
+        _lib.check(_lib.lib().dycon_ema_multi(e_arr, p_arr, c_arr, n, float(alpha), float(1 - alpha),
+                                              _stream_ptr(dev)), "dycon_ema_multi")
+        _tock("ema", t0)

@@ -1,0 +1,137 @@
+/*
+ * dycon_b200.h -- C ABI of the B200-native DyCON loss hot path.
+ *
+ * One shared library (dycon_paper_replication_b200/_dycon_b200.so, built by
+ * dycon_paper_replication_b200/csrc/build.py for sm_100a) exports exactly these
+ * entry points.  Every pointer is a plain device pointer unless stated
+ * otherwise; the library allocates no device memory, keeps no device state
+ * between calls, never synchronises the host with the device and only enqueues
+ * work on the stream it is given (all launches are CUDA-graph capturable).
+ *
+ * Reference interfaces replaced (rogeliorjr/DyCON_Paper_Replication):
+ *   dycon_uncl_*   UnCLoss.forward + its autograd backward    code/utils/dycon_losses.py:94-118
+ *   dycon_fecl_*   FeCLoss.forward + its autograd backward    code/utils/dycon_losses.py:150-235
+ *                  (also legacy losses.FeCLoss                code/utils/losses.py:221-250)
+ *   dycon_ema_*    update_ema_variables                       code/train_DyCON_BraTS19.py:155-164
+ *
+ * Return value: 0 on success, a negative DYCON_ERR_* code for a rejected call
+ * (nothing was enqueued), or a positive cudaError_t if a launch failed.
+ * dycon_last_error() returns a thread-local, human readable description.
+ * Floating-point inputs are IEEE fp32; NaN/Inf in the inputs propagate to the
+ * outputs (the caller's isnan/isinf guard, train_DyCON_BraTS19.py:360, keeps
+ * working).
+ */
+#ifndef DYCON_B200_H
+#define DYCON_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
+#endif
+
+#define DYCON_ABI_VERSION 1
+
+#define DYCON_OK 0
+#define DYCON_ERR_ARG (-1)         /* NULL / misaligned / out-of-range argument          */
+#define DYCON_ERR_UNSUPPORTED (-2) /* shape or option outside what the kernels implement */
+#define DYCON_ERR_DEVICE (-3)      /* current device is not sm_100 (B200)                */
+#define DYCON_ERR_WORKSPACE (-4)   /* workspace / state buffer too small                 */
+
+/* FeCL similarity arithmetic */
+#define DYCON_FECL_FP32 0 /* SIMT fp32 tiles (exact mode, parity 1e-5)                      */
+#define DYCON_FECL_BF16 1 /* TMA + tcgen05/TMEM tiles, bf16 operands, fp32 accumulate (2e-3) */
+
+typedef void* dycon_stream_t; /* a cudaStream_t (NULL = legacy default stream) */
+
+int dycon_abi_version(void);
+const char* dycon_last_error(void);
+/* 0 if the *current* CUDA device can run this library (compute capability 10.x). */
+int dycon_device_check(void);
+/* Number of CUDA kernels this library has launched in this process (all threads, monotonic). */
+uint64_t dycon_launch_count(void);
+
+/* ------------------------------------------------------------------ UnCL
+ * s_logits, t_logits: (B, C, V) fp32 contiguous (V = H*W*D voxels of one sample).
+ * Per voxel: L_v = sum_c (ps-pt)^2 / (exp(beta*Hs) + exp(beta*Ht)) + beta*(Hs+Ht)
+ * (dycon_losses.py:98-116).  inv_count is 1/(B_global*V): the mean denominator of
+ * dycon_losses.py:116, passed explicitly so a batch shard produces correctly
+ * scaled partial results.
+ *
+ * workspace: dycon_uncl_workspace_bytes() bytes, 16-byte aligned, ZERO-FILLED once
+ * by the caller after allocation; each call leaves it zeroed again.  It must not be
+ * shared by calls that may run concurrently (one workspace per stream).
+ * stash (C == 2 only, else NULL): B*V floats; receives the unit gradient
+ * dL_v/ds[:,1,v] so the backward is a 4-byte read instead of a recompute.
+ * sum_out: 1 double, sum of L_v over the local voxels (the quantity to all-reduce).
+ * loss_out: 1 float, sum * inv_count (may be NULL).
+ */
+size_t dycon_uncl_workspace_bytes(void);
+int dycon_uncl_fwd(const float* s_logits, const float* t_logits, int64_t B, int C, int64_t V,
+                   float beta, double inv_count, float* stash, double* sum_out, float* loss_out,
+                   void* workspace, size_t workspace_bytes, dycon_stream_t stream);
+/* grad_out: 1 float on the device (upstream gradient of the scalar loss).
+ * grad_s: (B, C, V) fp32 contiguous, fully overwritten.
+ * C == 2: reads only `stash` (s_logits/t_logits may be NULL).  C != 2: recomputes from
+ * s_logits/t_logits (stash ignored). */
+int dycon_uncl_bwd(const float* s_logits, const float* t_logits, const float* stash, int64_t B, int C,
+                   int64_t V, float beta, double inv_count, const float* grad_out, float* grad_s,
+                   dycon_stream_t stream);
+
+/* ------------------------------------------------------------------ FeCL
+ * feat / teacher: (B, N, D) fp32 with arbitrary ELEMENT strides (the caller's
+ * normalize(transpose(view)) result has strides (D*N, 1, N), train_DyCON_BraTS19.py:316-323).
+ * teacher may be NULL (no cross term).  labels: B*N fp32 contiguous (the (B,1,N) mask);
+ * pairs are positive iff labels are equal (dycon_losses.py:172).  row_weight: B*N fp32 or
+ * NULL -- the reference's gambling_uncertainty; when given, focal weighting is off
+ * (dycon_losses.py:209-211).  cross_thresh = sigmoid_rampup(epoch, rampup, 0.3, 0.5)
+ * computed by the host (dycon_losses.py:222).  inv_rows = 1/(B_global*N).
+ *
+ * state: dycon_fecl_state_bytes() bytes, 128-byte aligned; written by fwd, read by bwd
+ * (operand copies in kernel layout + per-row statistics m, n, A, kappa).
+ * workspace: dycon_fecl_workspace_bytes() bytes, ZERO-FILLED once by the caller, left
+ * zeroed by each call, one per stream.
+ * sums_out: 3 doubles {student_sum, cross_sum, cross_cnt} over the local samples
+ *   (student_sum = sum_rows r_i*c_i*sum_j loss_ij; the loss is
+ *    student_sum*inv_rows + lambda_cross*cross_sum/(cross_cnt + 1e-18)).
+ * loss_out: 1 float, that expression evaluated on the local sums (may be NULL).
+ */
+size_t dycon_fecl_state_bytes(int B, int N, int D, int has_teacher, int precision);
+size_t dycon_fecl_workspace_bytes(int B, int N, int D, int precision);
+int dycon_fecl_fwd(const float* feat, int64_t f_sb, int64_t f_sn, int64_t f_sd,
+                   const float* teacher, int64_t t_sb, int64_t t_sn, int64_t t_sd,
+                   const float* labels, const float* row_weight, int B, int N, int D,
+                   float inv_tau, float gamma, int use_focal, float cross_thresh, float lambda_cross,
+                   double inv_rows, int precision, void* state, size_t state_bytes,
+                   double* sums_out, float* loss_out, void* workspace, size_t workspace_bytes,
+                   dycon_stream_t stream);
+/* cross_cnt: 1 double on the device -- the BATCH-GLOBAL hard-negative count
+ * (dycon_losses.py:229; the all-reduced sums_out[2] when the batch is sharded).
+ * grad_out: 1 float on the device.  grad_feat: (B, N, D) fp32 contiguous, overwritten. */
+int dycon_fecl_bwd(const void* state, size_t state_bytes, const float* labels, int B, int N, int D,
+                   int has_teacher, float inv_tau, float gamma, int use_focal, int has_row_weight,
+                   float cross_thresh, float lambda_cross, int precision, const double* cross_cnt,
+                   const float* grad_out, float* grad_feat, dycon_stream_t stream);
+
+/* ------------------------------------------------------------------ EMA
+ * For every tensor k:  ema[k] = fma(one_minus_alpha, param[k], rn(ema[k]*alpha))  -- the
+ * rounding order of ema.mul_(alpha).add_(param, alpha=1-alpha)
+ * (train_DyCON_BraTS19.py:164).  alpha / one_minus_alpha are the fp32 roundings of the
+ * host doubles alpha and 1-alpha with alpha = min(1 - 1/(step+1), ema_decay).
+ * ema_ptrs / param_ptrs / numels are HOST arrays of n_tensors entries (copied into the
+ * kernel's parameter space: no host->device copy, graph capturable).
+ */
+int dycon_ema_multi(float* const* ema_ptrs, const float* const* param_ptrs, const int64_t* numels,
+                    int n_tensors, float alpha, float one_minus_alpha, dycon_stream_t stream);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* DYCON_B200_H */

@@ -1,0 +1,87 @@
+"""Host-side mirror of the reference interface: names, signatures, defaults, scalar schedules."""
+import inspect
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN
+
+
+def test_scalar_schedules_match_reference_values():
+    from dycon_paper_replication_b200 import dycon_losses as dl
+    z = np.load(GOLDEN + "/scalars.npz")
+    for name, args, val in zip(z["names"], z["args"], z["values"]):
+        fn = dl.adaptive_beta if name == "adaptive_beta" else dl.sigmoid_rampup
+        assert fn(*args.tolist()) == float(val), (name, args)
+    got = dl.gambling_softmax(torch.from_numpy(z["gs_in"])).numpy()
+    assert np.array_equal(got, z["gs_out"])
+
+
+def test_signatures_mirror_the_reference():
+    """Reference: code/utils/dycon_losses.py:8,14,28,91,94,141,150 and train_DyCON_BraTS19.py:155."""
+    from dycon_paper_replication_b200 import dycon_losses as dl
+    sig = lambda f: str(inspect.signature(f))
+    assert sig(dl.adaptive_beta) == "(epoch, total_epochs, max_beta=5.0, min_beta=0.5)"
+    assert sig(dl.sigmoid_rampup) == ("(current_epoch, total_rampup_epochs, min_threshold, max_threshold, "
+                                      "steepness=5.0)")
+    assert sig(dl.gambling_softmax) == "(logits)"
+    assert sig(dl.update_ema_variables) == "(model, ema_model, alpha, global_step)"
+    assert sig(dl.UnCLoss.forward) == "(self, s_logits, t_logits, beta)"
+    assert sig(dl.FeCLoss.forward) == "(self, feat, mask, teacher_feat=None, gambling_uncertainty=None, epoch=0)"
+    init = inspect.signature(dl.FeCLoss.__init__)
+    positional = [p for p in init.parameters.values() if p.kind == p.POSITIONAL_OR_KEYWORD][1:]
+    assert [(p.name, p.default) for p in positional] == [
+        ("device", inspect.Parameter.empty), ("temperature", 0.6), ("gamma", 2.0), ("use_focal", False),
+        ("rampup_epochs", 2000), ("lambda_cross", 1.0)]
+    # extensions are keyword-only, so positional reference calls keep their meaning
+    assert all(p.kind == p.KEYWORD_ONLY for p in init.parameters.values()
+               if p.name in ("precision", "process_group", "global_batch"))
+
+
+def test_modules_are_stateless_like_the_reference():
+    from dycon_paper_replication_b200 import FeCLoss, UnCLoss
+    crit = FeCLoss(device="cuda:0", temperature=0.5, gamma=2.0, use_focal=True, rampup_epochs=1500)
+    assert (crit.device, crit.temperature, crit.gamma, crit.use_focal, crit.rampup_epochs, crit.lambda_cross) == \
+        ("cuda:0", 0.5, 2.0, True, 1500, 1.0)
+    assert len(crit.state_dict()) == 0 and len(UnCLoss().state_dict()) == 0
+    assert list(crit.parameters()) == [] and list(crit.buffers()) == []
+
+
+def test_cpu_tensors_raise_no_fallback():
+    from dycon_paper_replication_b200 import FeCLoss, UnCLoss, update_ema_variables
+    x = torch.randn(1, 2, 4, 4, 4)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        UnCLoss()(x, x, 1.0)
+    f = torch.nn.functional.normalize(torch.randn(1, 8, 4), dim=-1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        FeCLoss("cpu")(f, torch.zeros(1, 1, 8))
+    lin = torch.nn.Linear(3, 3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        update_ema_variables(lin, torch.nn.Linear(3, 3), 0.99, 5)
+
+
+def test_product_package_never_imports_the_oracle():
+    import os
+    import re
+    from conftest import ROOT
+    pkg = os.path.join(ROOT, "dycon_paper_replication_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_synthetic_inputs_have_the_callers_layout():
+    from dycon_paper_replication_b200.synthetic import make_inputs, unet3d_param_shapes
+    inp = make_inputs("tiny", dim=32)
+    b, n, d = inp.feat.shape
+    assert inp.feat.stride() == (d * n, 1, n)                 # train_DyCON_BraTS19.py:316-323
+    assert inp.mask.shape == (b, 1, n) and set(inp.mask.unique().tolist()) <= {0.0, 1.0}
+    assert torch.allclose(inp.feat.norm(dim=-1), torch.ones(b, n), atol=1e-5)
+    again = make_inputs("tiny", dim=32)
+    assert torch.equal(inp.feat, again.feat) and torch.equal(inp.s_logits, again.s_logits)
+    shapes = unet3d_param_shapes()
+    assert len(shapes) == 48 and sum(math.prod(s) for s in shapes) == 6148532
