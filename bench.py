@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--shape", default="brats19")
     ap.add_argument("--batch", type=int, default=4, help="samples per GPU")
     ap.add_argument("--dim", type=int, default=256)
-    ap.add_argument("--precision", default=None, help="FeCL similarity arithmetic: fp32 | bf16")
+    ap.add_argument("--precision", default=None, help="FeCL similarity arithmetic: fp16 (default) | bf16 | fp32")
     ap.add_argument("--sets", type=int, default=4, help="rotating input sets (defeats the 126 MB L2)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -376,7 +376,7 @@ def run_ours(args):
 
     line = {"metric": METRIC, "value": value, "unit": "voxels/s", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32" if precision == "fp32" else "bf16 MMA operands, f32 accumulate/epilogue",
+            "vs_baseline": None, "dtype": "f32" if precision == "fp32" else f"{precision} MMA operands, f32 accumulate/epilogue",
             "data": "synthetic",
             "config": {"workload": workload_name(args, n_gpus), "fecl_precision": precision,
                        "l2": f"rotating {args.sets} input sets of {set_bytes / 1e6:.0f} MB each (> 126 MB L2), no flush",

@@ -14,6 +14,7 @@ SO_PATH = os.path.join(_HERE, "_dycon_b200.so")
 
 FECL_FP32 = 0
 FECL_BF16 = 1
+FECL_FP16 = 2
 
 _lock = threading.Lock()
 _lib = None

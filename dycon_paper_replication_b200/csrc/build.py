@@ -19,8 +19,8 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 SO = os.path.join(PKG, "_dycon_b200.so")
 STAMP = SO + ".hash"
-SOURCES = ["api.cu", "uncl.cu", "ema.cu", "fecl_api.cu", "fecl_simt.cu", "fecl_tc.cu"]
-HEADERS = ["common.cuh", "fecl_math.cuh", "fecl_internal.h", os.path.join(ROOT, "include", "dycon_b200.h")]
+SOURCES = ["api.cu", "uncl.cu", "ema.cu", "fecl_api.cu", "fecl_simt.cu", "fecl_tc.cu", "tc_host.cu"]
+HEADERS = ["common.cuh", "fecl_math.cuh", "fecl_internal.h", "tc_common.cuh", os.path.join(ROOT, "include", "dycon_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--use_fast_math" if False else "-DDYCON_NO_GLOBAL_FAST_MATH",   # fast intrinsics are chosen per call site
@@ -75,5 +75,21 @@ def build(force=False, verbose=False):
     return SO
 
 
+def build_probe():
+    """tests/native/tc_probe.cu -> build/tc_probe (stand-alone tcgen05 / TMA encoding check)."""
+    out = os.path.join(ROOT, "build", "tc_probe")
+    src = [os.path.join(ROOT, "tests", "native", "tc_probe.cu"), os.path.join(HERE, "tc_host.cu"),
+           os.path.join(HERE, "api.cu")]
+    newest = max(os.path.getmtime(f) for f in src + [os.path.join(HERE, "tc_common.cuh")])
+    if os.path.exists(out) and os.path.getmtime(out) >= newest:
+        return out
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-lineinfo", "-std=c++17",
+           "-I", os.path.join(ROOT, "include"), "-I", HERE] + src + ["-o", out]
+    subprocess.run(cmd, check=True)
+    return out
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_probe())

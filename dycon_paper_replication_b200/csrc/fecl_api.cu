@@ -8,7 +8,7 @@ namespace {
 
 int check_shape(int B, int N, int D, int precision) {
   DYCON_REQUIRE(B > 0 && N > 0 && D > 0, DYCON_ERR_ARG, "FeCL: B=%d N=%d D=%d must be positive", B, N, D);
-  DYCON_REQUIRE(precision == DYCON_FECL_FP32 || precision == DYCON_FECL_BF16, DYCON_ERR_ARG,
+  DYCON_REQUIRE(precision == DYCON_FECL_FP32 || precision == DYCON_FECL_BF16 || precision == DYCON_FECL_FP16, DYCON_ERR_ARG,
                 "FeCL: unknown precision %d", precision);
   DYCON_REQUIRE((long long)N * N < (1LL << 40), DYCON_ERR_UNSUPPORTED, "FeCL: N=%d too large", N);
   return DYCON_OK;
@@ -20,13 +20,13 @@ extern "C" {
 
 size_t dycon_fecl_state_bytes(int B, int N, int D, int has_teacher, int precision) {
   if (B <= 0 || N <= 0 || D <= 0) return 0;
-  return precision == DYCON_FECL_BF16 ? fecl_tc_state_bytes(B, N, D, has_teacher)
+  return precision != DYCON_FECL_FP32 ? fecl_tc_state_bytes(B, N, D, has_teacher)
                                       : fecl_simt_state_bytes(B, N, D, has_teacher);
 }
 
 size_t dycon_fecl_workspace_bytes(int B, int N, int D, int precision) {
   if (B <= 0 || N <= 0 || D <= 0) return 0;
-  return precision == DYCON_FECL_BF16 ? fecl_tc_workspace_bytes(B, N, D) : fecl_simt_workspace_bytes(B, N, D);
+  return precision != DYCON_FECL_FP32 ? fecl_tc_workspace_bytes(B, N, D) : fecl_simt_workspace_bytes(B, N, D);
 }
 
 int dycon_fecl_fwd(const float* feat, int64_t f_sb, int64_t f_sn, int64_t f_sd, const float* teacher, int64_t t_sb,
@@ -49,9 +49,9 @@ int dycon_fecl_fwd(const float* feat, int64_t f_sb, int64_t f_sn, int64_t f_sd, 
                 "FeCL fwd: workspace %zu < %zu bytes", workspace_bytes, dycon_fecl_workspace_bytes(B, N, D, precision));
   FeclProblem p{B, N, D, has_teacher,
                 FeclScalars{inv_tau, gamma, cross_thresh, lambda_cross, (use_focal && row_weight == nullptr) ? 1 : 0},
-                inv_rows};
+                inv_rows, precision};
   FeclFwdArgs a{feat, f_sb, f_sn, f_sd, teacher, t_sb, t_sn, t_sd, labels, row_weight, state, sums_out, loss_out, workspace};
-  return precision == DYCON_FECL_BF16 ? fecl_tc_fwd(p, a, as_stream(stream)) : fecl_simt_fwd(p, a, as_stream(stream));
+  return precision != DYCON_FECL_FP32 ? fecl_tc_fwd(p, a, as_stream(stream)) : fecl_simt_fwd(p, a, as_stream(stream));
 }
 
 int dycon_fecl_bwd(const void* state, size_t state_bytes, const float* labels, int B, int N, int D, int has_teacher,
@@ -66,9 +66,9 @@ int dycon_fecl_bwd(const void* state, size_t state_bytes, const float* labels, i
   DYCON_REQUIRE(state_bytes >= dycon_fecl_state_bytes(B, N, D, has_teacher, precision), DYCON_ERR_WORKSPACE,
                 "FeCL bwd: state %zu < %zu bytes", state_bytes, dycon_fecl_state_bytes(B, N, D, has_teacher, precision));
   FeclProblem p{B, N, D, has_teacher ? 1 : 0,
-                FeclScalars{inv_tau, gamma, cross_thresh, lambda_cross, (use_focal && !has_row_weight) ? 1 : 0}, 0.0};
+                FeclScalars{inv_tau, gamma, cross_thresh, lambda_cross, (use_focal && !has_row_weight) ? 1 : 0}, 0.0, precision};
   FeclBwdArgs a{state, labels, cross_cnt, grad_out, grad_feat};
-  return precision == DYCON_FECL_BF16 ? fecl_tc_bwd(p, a, as_stream(stream)) : fecl_simt_bwd(p, a, as_stream(stream));
+  return precision != DYCON_FECL_FP32 ? fecl_tc_bwd(p, a, as_stream(stream)) : fecl_simt_bwd(p, a, as_stream(stream));
 }
 
 }  // extern "C"

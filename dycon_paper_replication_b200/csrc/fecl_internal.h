@@ -11,6 +11,7 @@ struct FeclProblem {
   int has_teacher;
   FeclScalars sc;
   double inv_rows;
+  int precision;
 };
 
 struct FeclFwdArgs {

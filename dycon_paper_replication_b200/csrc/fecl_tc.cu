@@ -1,13 +1,765 @@
-// K2 (bf16 tensor-core mode) -- placeholder until the tcgen05 kernels land.
+// K2 (16-bit tensor-core modes) -- FeCL forward / backward on tcgen05 + TMEM + TMA (sm_100a).
+// Operands are bf16 or fp16 (template parameter; same kind::f16 MMA, same rate, fp32 accumulation).
+// fp16's 10-bit mantissa is what keeps the gradient inside the 2e-3 budget on every input.
+// Reference: code/utils/dycon_losses.py:150-235; per-pair algebra in fecl_math.cuh / SURVEY.md 0.2.
+//
+// Data layout in HBM (the `state` buffer, written by the forward, read by the backward):
+//   hdr    : 128 bytes; hdr[0] = power-of-two scale applied to H / Gc before the 16-bit conversion
+//   Fb, Tb : 16-bit [B][Npad][Dpad], row-major (K-major for the MMAs), Npad = ceil128(N),
+//            Dpad = ceil64(D); padding rows / columns are zero.
+//   stats  : 4 planes of B*N floats: m (column == row max), n (negative sum), A, kappa.
+// No (N,N) tensor is ever written: every similarity tile lives in TMEM and is consumed in place.
+//
+// Kernels (a CTA owns 128 rows of one sample; 10 warps: TMA producer, MMA issuer, 8 epilogue):
+//   fecl_tc_sweep_kernel<0>  P0: S = F_I F_J^T tiles -> row max m_i, positive count -> kappa_i
+//   fecl_tc_sweep_kernel<1>  P1: S tiles -> n_i ;  P2: S tiles -> row loss, A_i ; F_I T_J^T tiles -> cross sum/count
+//   fecl_tc_bwd_kernel       per 64-column tile: S, CS -> H = G + G^T, Gc (bf16, written to smem in the
+//                            UMMA K-major swizzle) -> dF_I += H F_J + Gc T_J with F_J / T_J read as
+//                            MN-major operands from the very tiles that produced S / CS.
+// Pipelines: smem ring (TMA -> MMA) and TMEM ring (MMA -> epilogue), all mbarrier based.
 #include "fecl_internal.h"
+#include "tc_common.cuh"
 
 namespace dycon {
-size_t fecl_tc_state_bytes(int, int, int, int) { return 0; }
-size_t fecl_tc_workspace_bytes(int, int, int) { return 0; }
-int fecl_tc_fwd(const FeclProblem&, const FeclFwdArgs&, cudaStream_t) {
-  return fail(DYCON_ERR_UNSUPPORTED, "FeCL bf16 (tcgen05) path not built yet");
+namespace {
+
+using namespace tc;
+
+constexpr int kTM = 128;               // rows per CTA (UMMA M)
+constexpr int kThreads = 320;          // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
+constexpr int kEpiThreads = 256;
+constexpr uint32_t kChunk128 = 128 * 128;   // bytes of a [128 rows][64 bf16] swizzle chunk
+constexpr uint32_t kChunk64 = 64 * 128;     // bytes of a [ 64 rows][64 bf16] swizzle chunk
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ float pow_gm1(float x, float g) {   // x^(g-1), x in [0,1]
+  if (g == 2.f) return x;
+  if (g == 1.f) return 1.f;
+  if (g == 3.f) return x * x;
+  return ex2_approx((g - 1.f) * lg2_approx(x));
 }
-int fecl_tc_bwd(const FeclProblem&, const FeclBwdArgs&, cudaStream_t) {
-  return fail(DYCON_ERR_UNSUPPORTED, "FeCL bf16 (tcgen05) path not built yet");
+
+// Positive pair with exponent argument t = log2(e_ij) and row negative-sum n:
+//   forward : phi(d) and the A-summand phi'(d) d / T;   backward: phi'(d) d (1-d).
+__device__ __forceinline__ void pos_fwd(float t, float e, float n, const FeclScalars& sc, float& phi, float& a_term) {
+  const float T = e + n;
+  const float rT = rcp_approx(T);
+  const float d = e * rT;
+  const float logd = kLn2 * (t - lg2_approx(T));
+  if (sc.focal) {
+    const float omd = 1.f - d, w1 = pow_gm1(omd, sc.gamma), w = w1 * omd;
+    phi = -logd * w;
+    a_term = (sc.gamma * w1 * d * logd - w) * rT;
+  } else {
+    phi = -logd;
+    a_term = -rT;
+  }
 }
+__device__ __forceinline__ float pos_bwd(float t, float e, float n, const FeclScalars& sc) {
+  const float T = e + n;
+  const float d = e * rcp_approx(T);
+  const float omd = 1.f - d;
+  if (sc.focal) {
+    const float logd = kLn2 * (t - lg2_approx(T));
+    return pow_gm1(omd, sc.gamma) * omd * (sc.gamma * d * logd - omd);
+  }
+  return -omd;
+}
+
+// ---- pack: fp32 (B,N,D) with element strides -> bf16 [B][Npad][Dpad], zero padded ---------------
+template <bool kBf16> struct Cvt;
+template <> struct Cvt<true> {
+  using type = __nv_bfloat16;
+  static __device__ __forceinline__ type one(float x) { return __float2bfloat16(x); }
+  static __device__ __forceinline__ uint32_t two(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+};
+template <> struct Cvt<false> {
+  using type = __half;
+  static __device__ __forceinline__ type one(float x) { return __float2half_rn(x); }
+  static __device__ __forceinline__ uint32_t two(float a, float b) {   // saturate: fp16 overflows at 65504
+    __half2 v = __floats2half2_rn(fminf(fmaxf(a, -60000.f), 60000.f), fminf(fmaxf(b, -60000.f), 60000.f));
+    return *reinterpret_cast<uint32_t*>(&v);
+  }
+};
+
+template <bool kBf16>
+__global__ void __launch_bounds__(256)
+pack16_kernel(const float* __restrict__ src, int64_t sb, int64_t sn, int64_t sd, int N, int D, int Npad, int Dpad,
+              typename Cvt<kBf16>::type* __restrict__ dst) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, n0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const float* s = src + (int64_t)b * sb;
+  if (sn <= sd) {
+    for (int k = ty; k < 32; k += 8) {
+      const int n = n0 + tx, d = d0 + k;
+      tile[k][tx] = (n < N && d < D) ? s[(int64_t)n * sn + (int64_t)d * sd] : 0.f;
+    }
+    __syncthreads();
+    for (int k = ty; k < 32; k += 8) {
+      const int n = n0 + k, d = d0 + tx;
+      if (n < Npad && d < Dpad) dst[((size_t)b * Npad + n) * Dpad + d] = Cvt<kBf16>::one(tile[tx][k]);
+    }
+  } else {
+    for (int k = ty; k < 32; k += 8) {
+      const int n = n0 + k, d = d0 + tx;
+      if (n < Npad && d < Dpad) {
+        const float v = (n < N && d < D) ? s[(int64_t)n * sn + (int64_t)d * sd] : 0.f;
+        dst[((size_t)b * Npad + n) * Dpad + d] = Cvt<kBf16>::one(v);
+      }
+    }
+  }
+}
+
+// =================================================================================================
+//  Forward sweeps
+// =================================================================================================
+struct SweepParams {
+  int N, Npad, KC, has_teacher;
+  FeclScalars sc;
+  float c1;            // inv_tau * log2(e)
+  float inv_rows;
+  double inv_rows_d;
+  float hscale;
+  float* hdr;
+  const float* labels;
+  const float* row_weight;
+  float* stat_m;
+  float* stat_n;
+  float* stat_a;
+  float* stat_kappa;
+  unsigned int* ticket;
+  double* partials;
+  double* sums_out;
+  float* loss_out;
+};
+
+struct SweepMisc {
+  uint64_t a_full;
+  uint64_t b_full[2], b_empty[2];
+  uint64_t acc_full[4], acc_empty[4];
+  uint32_t tmem_slot;
+  uint32_t pad_;
+  float col[2][2][128];    // [slot][stat: y, m2][column]
+  float xch[3][128];       // half-1 -> half-0 exchange of per-row partials
+  double scratch[3 * 32];
+};
+
+template <int kMode, bool kBf16>  // kMode 0: row max + kappa,  1: n / loss / A / cross
+__global__ void __launch_bounds__(kThreads, 1)
+fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapT,
+                     const SweepParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KC = p.KC;
+  const uint32_t tile_bytes = (uint32_t)KC * kChunk128;
+  uint8_t* sA = smem;
+  uint8_t* sB[2] = {smem + tile_bytes, smem + 2 * tile_bytes};
+  SweepMisc& ms = *reinterpret_cast<SweepMisc*>(smem + 3 * tile_bytes);
+  const int b = blockIdx.y, i0 = blockIdx.x * kTM;
+  const int nt = p.Npad / 128;
+  const int per_j = 1 + (kMode == 1 ? p.has_teacher : 0);
+  const int total = kMode == 0 ? nt : nt + nt * per_j;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(&ms.a_full, 1);
+    for (int s = 0; s < 2; ++s) mbar_init(&ms.b_full[s], 1), mbar_init(&ms.b_empty[s], 1);
+    for (int a = 0; a < 4; ++a) mbar_init(&ms.acc_full[a], 1), mbar_init(&ms.acc_empty[a], 8);
+    fence_mbar_init();
+    prefetch_tmap(&mapF);
+    if (kMode == 1 && p.has_teacher) prefetch_tmap(&mapT);
+    if (kMode == 0 && blockIdx.x == 0 && blockIdx.y == 0) p.hdr[0] = p.hscale;
+  }
+  if (warp == 1) tmem_alloc(&ms.tmem_slot, 512);
+  tcgen05_before_sync();
+  __syncthreads();
+  tcgen05_after_sync();
+  const uint32_t tmem = ms.tmem_slot;
+
+  // tile t -> (column tile, operand)
+  auto tile_of = [&](int t, int& jt, bool& teacher) {
+    if (kMode == 0 || t < nt) { jt = t; teacher = false; return; }
+    const int u = t - nt;
+    jt = u / per_j;
+    teacher = (u % per_j) == 1;
+  };
+
+  double red[3] = {0.0, 0.0, 0.0};
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      mbar_expect_tx(&ms.a_full, tile_bytes);
+      for (int c = 0; c < KC; ++c) tma_load_2d(sA + c * kChunk128, &mapF, c * 64, b * p.Npad + i0, &ms.a_full);
+      for (int t = 0; t < total; ++t) {
+        const int s = t & 1;
+        int jt; bool teacher;
+        tile_of(t, jt, teacher);
+        mbar_wait(&ms.b_empty[s], ((t >> 1) & 1) ^ 1);
+        mbar_expect_tx(&ms.b_full[s], tile_bytes);
+        for (int c = 0; c < KC; ++c)
+          tma_load_2d(sB[s] + c * kChunk128, teacher ? &mapT : &mapF, c * 64, b * p.Npad + jt * 128, &ms.b_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_16(128, 128, false, false, kBf16);
+      mbar_wait(&ms.a_full, 0);
+      for (int t = 0; t < total; ++t) {
+        const int s = t & 1, a = t & 3;
+        mbar_wait(&ms.b_full[s], (t >> 1) & 1);
+        mbar_wait(&ms.acc_empty[a], ((t >> 2) & 1) ^ 1);
+        tcgen05_after_sync();
+        const uint32_t d_tmem = tmem + a * 128;
+        for (int c = 0; c < KC; ++c) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(d_tmem, umma_desc_kmajor(smem_u32(sA + c * kChunk128) + k * 32),
+                      umma_desc_kmajor(smem_u32(sB[s] + c * kChunk128) + k * 32), idesc, (c | k) != 0);
+        }
+        umma_commit(&ms.b_empty[s]);
+        umma_commit(&ms.acc_full[a]);
+      }
+    }
+  } else {
+    // ================================ epilogue (8 warps) ==========================
+    const int et = threadIdx.x - 64;              // 0..255
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane, i = i0 + r;
+    const bool row_ok = i < p.N;
+    const float* yb = p.labels + (size_t)b * p.N;
+    const float yi = row_ok ? __ldg(yb + i) : __int_as_float(0x7fc00000);
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // mode 0: max, count; mode 1: n | loss, A | cross sum, count
+    float n_row = 0.f;
+
+    for (int t = 0; t < total; ++t) {
+      const int a = t & 3, slot = t & 1;
+      int jt; bool teacher;
+      tile_of(t, jt, teacher);
+      const int j0 = jt * 128;
+      // ---- stage the column statistics of this tile ----
+      {
+        const int cidx = et & 127, j = j0 + cidx;
+        if (et < 128) {
+          ms.col[slot][0][cidx] = j < p.N ? __ldg(yb + j) : __int_as_float(0x7fc00000);
+        } else if (kMode == 1) {
+          ms.col[slot][1][cidx] = j < p.N ? __ldg(p.stat_m + (size_t)b * p.N + j) * kLog2e : INFINITY;
+        }
+      }
+      if (kMode == 1 && t == nt) {
+        // P1 -> P2: publish the other half's partial n_i and total them
+        if (half == 1) ms.xch[0][r] = acc0;
+        epi_barrier();
+        if (half == 0) ms.xch[1][r] = acc0;
+        epi_barrier();
+        n_row = ms.xch[0][r] + ms.xch[1][r];
+        acc0 = 0.f;
+      } else {
+        epi_barrier();
+      }
+      mbar_wait(&ms.acc_full[a], (t >> 2) & 1);
+      tcgen05_after_sync();
+      const bool diag = (jt == (int)blockIdx.x) && !teacher;
+#pragma unroll
+      for (int ch = 0; ch < 2; ++ch) {
+        const int cbase = half * 64 + ch * 32;
+        float v[32];
+        tmem_ld32(tmem + lane_base + a * 128 + cbase, v);
+        tmem_ld_wait();
+        const float4* y4 = reinterpret_cast<const float4*>(&ms.col[slot][0][cbase]);
+        const float4* m4 = reinterpret_cast<const float4*>(&ms.col[slot][1][cbase]);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 yy = y4[q];
+          float4 mm = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (kMode == 1) mm = m4[q];
+          const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int lc = cbase + q * 4 + k;
+            const float x = v[q * 4 + k];
+            const bool same = ys[k] == yi;
+            const bool offd = !(diag && lc == r);
+            if (kMode == 0) {
+              if (offd) acc0 = fmaxf(acc0, x);
+              acc1 += same ? 1.f : 0.f;
+            } else if (t < nt) {
+              const float e = ex2_approx(fmaf(x, p.c1, -m2[k]));
+              acc0 += (ys[k] != yi) ? e : 0.f;               // padded columns: m2 = +inf -> e = 0
+            } else if (!teacher) {
+              const float targ = fmaf(x, p.c1, -m2[k]);
+              const float e = ex2_approx(targ);
+              float phi, at;
+              pos_fwd(targ, e, n_row, p.sc, phi, at);
+              const bool pos = same && offd;
+              acc0 += pos ? phi : 0.f;
+              acc1 += pos ? at : 0.f;
+            } else {
+              const bool hard = (ys[k] != yi) && (ys[k] == ys[k]) && row_ok && (x > p.sc.cross_thresh);
+              if (hard) {
+                acc2 += -kLn2 * lg2_approx(1.f - x + kTiny);
+                acc3 += 1.f;
+              }
+            }
+          }
+        }
+      }
+      tcgen05_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ms.acc_empty[a]);
+    }
+
+    // ---- combine the two column halves, write per-row statistics ----
+    epi_barrier();
+    if (half == 1) { ms.xch[0][r] = acc0; ms.xch[1][r] = acc1; }
+    epi_barrier();
+    if (half == 0 && row_ok) {
+      const size_t g = (size_t)b * p.N + i;
+      if (kMode == 0) {
+        const float mx = fmaxf(acc0, ms.xch[0][r]) * p.sc.inv_tau;      // >= 0: the zeroed diagonal takes part
+        const float P = acc1 + ms.xch[1][r];
+        const float rw = p.row_weight ? __ldg(p.row_weight + g) : 1.f;
+        p.stat_m[g] = mx;
+        p.stat_kappa[g] = rw / ((P - 1.f) + kTiny) * p.inv_rows;
+      } else {
+        const float ls = acc0 + ms.xch[0][r], as = acc1 + ms.xch[1][r];
+        p.stat_n[g] = n_row;
+        p.stat_a[g] = as;
+        red[0] = (double)(__ldg(p.stat_kappa + g) * ls);
+      }
+    }
+    if (kMode == 1) { red[1] = (double)acc2; red[2] = (double)acc3; }
+  }
+
+  // ---- block / grid reduction of {student, cross_sum, cross_cnt} (mode 1) ----
+  if (kMode == 1) {
+    double total_[3];
+    const unsigned int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+    if (grid_sum_last_block<3>(red, total_, p.ticket, p.partials, nblocks, bid, ms.scratch) && threadIdx.x == 0) {
+      const double student = total_[0] / p.inv_rows_d;
+      p.sums_out[0] = student;
+      p.sums_out[1] = total_[1];
+      p.sums_out[2] = total_[2];
+      if (p.loss_out) {
+        const double cross = p.has_teacher ? total_[1] / (total_[2] + 1e-18) : 0.0;
+        *p.loss_out = (float)(student * p.inv_rows_d + (double)p.sc.lambda_cross * cross);
+      }
+    }
+  }
+  tcgen05_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// =================================================================================================
+//  Backward
+// =================================================================================================
+struct BwdParams {
+  int N, Npad, KC, D, has_teacher;
+  FeclScalars sc;
+  float c1;
+  const float* labels;
+  const float* stat_m;
+  const float* stat_n;
+  const float* stat_a;
+  const float* stat_kappa;
+  const float* hdr;
+  const double* cross_cnt;
+  const float* grad_out;
+  float* grad_feat;
+};
+
+struct BwdMisc {
+  uint64_t a_full;
+  uint64_t b_full[2], b_empty[2];
+  uint64_t sc_full[2], sc_empty[2];
+  uint64_t h_full, h_free, df_full;
+  uint32_t tmem_slot;
+  uint32_t pad_;
+  float col[2][5][64];   // [slot][y, m2, n, A, kappa][column]
+};
+
+template <bool kBf16>
+__global__ void __launch_bounds__(kThreads, 1)
+fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapF,
+                   const __grid_constant__ CUtensorMap mapT, const BwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KC = p.KC, Dpad = KC * 64;
+  const uint32_t a_bytes = (uint32_t)KC * kChunk128, j_bytes = (uint32_t)KC * kChunk64;
+  const uint32_t stage_bytes = j_bytes * 2;       // F_J tile + T_J tile
+  uint8_t* sA = smem;
+  uint8_t* sStage[2] = {smem + a_bytes, smem + a_bytes + stage_bytes};
+  uint8_t* sH = smem + a_bytes + 2 * stage_bytes;     // [128 i][64 j] bf16, K-major SW128
+  uint8_t* sG = sH + kChunk128;
+  BwdMisc& ms = *reinterpret_cast<BwdMisc*>(sG + kChunk128);
+  const int b = blockIdx.y, i0 = blockIdx.x * kTM;
+  const int nt = p.Npad / 64;
+  const bool teacher = p.has_teacher != 0;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    mbar_init(&ms.a_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&ms.b_full[s], 1);
+      mbar_init(&ms.b_empty[s], 1);
+      mbar_init(&ms.sc_full[s], 1);
+      mbar_init(&ms.sc_empty[s], 8);
+    }
+    mbar_init(&ms.h_full, 8);
+    mbar_init(&ms.h_free, 1);
+    mbar_init(&ms.df_full, 1);
+    fence_mbar_init();
+    prefetch_tmap(&mapA);
+    prefetch_tmap(&mapF);
+    if (teacher) prefetch_tmap(&mapT);
+  }
+  if (warp == 1) tmem_alloc(&ms.tmem_slot, 512);
+  tcgen05_before_sync();
+  __syncthreads();
+  tcgen05_after_sync();
+  const uint32_t tmem = ms.tmem_slot;
+  // TMEM columns: S[s] at s*64, CS[s] at 128 + s*64, dF at 256 (Dpad columns)
+  const uint32_t tm_s = tmem, tm_cs = tmem + 128, tm_df = tmem + 256;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(&ms.a_full, a_bytes);
+      for (int c = 0; c < KC; ++c) tma_load_2d(sA + c * kChunk128, &mapA, c * 64, b * p.Npad + i0, &ms.a_full);
+      for (int t = 0; t < nt; ++t) {
+        const int s = t & 1;
+        mbar_wait(&ms.b_empty[s], ((t >> 1) & 1) ^ 1);
+        mbar_expect_tx(&ms.b_full[s], teacher ? stage_bytes : j_bytes);
+        for (int c = 0; c < KC; ++c) {
+          tma_load_2d(sStage[s] + c * kChunk64, &mapF, c * 64, b * p.Npad + t * 64, &ms.b_full[s]);
+          if (teacher) tma_load_2d(sStage[s] + j_bytes + c * kChunk64, &mapT, c * 64, b * p.Npad + t * 64, &ms.b_full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc_s = umma_idesc_16(128, 64, false, false, kBf16);
+      const uint32_t idesc_d = umma_idesc_16(128, Dpad, false, true, kBf16);   // B = F_J / T_J read MN-major
+      auto issue_sc = [&](int t) {
+        const int s = t & 1;
+        mbar_wait(&ms.b_full[s], (t >> 1) & 1);
+        mbar_wait(&ms.sc_empty[s], ((t >> 1) & 1) ^ 1);
+        tcgen05_after_sync();
+        for (int c = 0; c < KC; ++c) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tm_s + s * 64, umma_desc_kmajor(smem_u32(sA + c * kChunk128) + k * 32),
+                      umma_desc_kmajor(smem_u32(sStage[s] + c * kChunk64) + k * 32), idesc_s, (c | k) != 0);
+        }
+        if (teacher) {
+          for (int c = 0; c < KC; ++c) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tm_cs + s * 64, umma_desc_kmajor(smem_u32(sA + c * kChunk128) + k * 32),
+                        umma_desc_kmajor(smem_u32(sStage[s] + j_bytes + c * kChunk64) + k * 32), idesc_s, (c | k) != 0);
+          }
+        }
+        umma_commit(&ms.sc_full[s]);
+      };
+      mbar_wait(&ms.a_full, 0);
+      issue_sc(0);
+      for (int t = 0; t < nt; ++t) {
+        if (t + 1 < nt) issue_sc(t + 1);
+        const int s = t & 1;
+        mbar_wait(&ms.h_full, t & 1);
+        tcgen05_after_sync();
+        // dF += H * F_J (+ Gc * T_J): K = 64 columns of the tile = 4 steps of 16 rows (2048 B) of the B tile
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tm_df, umma_desc_kmajor(smem_u32(sH) + k * 32),
+                    umma_desc(smem_u32(sStage[s]) + k * 2048, kChunk64, 1024), idesc_d, (t | k) != 0);
+        if (teacher) {
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tm_df, umma_desc_kmajor(smem_u32(sG) + k * 32),
+                      umma_desc(smem_u32(sStage[s] + j_bytes) + k * 2048, kChunk64, 1024), idesc_d, true);
+        }
+        umma_commit(&ms.b_empty[s]);
+        umma_commit(&ms.h_free);
+      }
+      umma_commit(&ms.df_full);
+    }
+  } else {
+    const int et = threadIdx.x - 64;
+    const int quarter = warp & 3, half = (warp - 2) >> 2;
+    const int r = quarter * 32 + lane, i = i0 + r;
+    const bool row_ok = i < p.N;
+    const size_t off = (size_t)b * p.N;
+    const int ic = row_ok ? i : p.N - 1;
+    const float yi = row_ok ? __ldg(p.labels + off + ic) : __int_as_float(0x7fc00000);
+    const float m2i = __ldg(p.stat_m + off + ic) * kLog2e;
+    const float ni = __ldg(p.stat_n + off + ic), ai = __ldg(p.stat_a + off + ic);
+    const float ki = row_ok ? __ldg(p.stat_kappa + off + ic) : 0.f;
+    // H and Gc are scaled by a power of two (~ B N tau / 8, so |H| stays O(1)) before the 16-bit
+    // conversion: exact, and it keeps fp16 out of its subnormal range.  Undone when dF is read out.
+    const float hscale = __ldg(p.hdr);
+    const float gc_scale = teacher ? hscale * p.sc.lambda_cross / ((float)(*p.cross_cnt) + kTiny) : 0.f;
+    const float h_mul = p.sc.inv_tau * hscale;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    const int cbase = half * 32;                  // this thread's 32 columns of the 64-column tile
+
+    for (int t = 0; t < nt; ++t) {
+      const int s = t & 1, j0 = t * 64;
+      // stage column statistics (5 x 64 floats) -- 256 threads cover 320 values in two rounds
+      for (int q = et; q < 320; q += kEpiThreads) {
+        const int st = q >> 6, cidx = q & 63, j = j0 + cidx;
+        float val;
+        if (j < p.N) {
+          const float* src = st == 0 ? p.labels : st == 1 ? p.stat_m : st == 2 ? p.stat_n : st == 3 ? p.stat_a : p.stat_kappa;
+          val = __ldg(src + off + j);
+          if (st == 1) val *= kLog2e;
+        } else {
+          val = st == 0 ? __int_as_float(0x7fc00000) : st == 1 ? INFINITY : 0.f;
+        }
+        ms.col[s][st][cidx] = val;
+      }
+      epi_barrier();
+      mbar_wait(&ms.sc_full[s], (t >> 1) & 1);
+      tcgen05_after_sync();
+      const bool diag_tile = (j0 >= i0) && (j0 < i0 + kTM);
+      float sv[32], cv[32];
+      tmem_ld32(tm_s + lane_base + s * 64 + cbase, sv);
+      if (teacher) tmem_ld32(tm_cs + lane_base + s * 64 + cbase, cv);
+      tmem_ld_wait();
+      tcgen05_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ms.sc_empty[s]);
+
+      uint32_t hp[16], gp[16];
+#pragma unroll
+      for (int q = 0; q < 16; ++q) {
+        float hv[2], gv[2];
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int lc = cbase + q * 2 + k;
+          const float yj = ms.col[s][0][lc], m2j = ms.col[s][1][lc], nj = ms.col[s][2][lc];
+          const float aj = ms.col[s][3][lc], kj = ms.col[s][4][lc];
+          const float x = sv[q * 2 + k];
+          const float tij = fmaf(x, p.c1, -m2j), tji = fmaf(x, p.c1, -m2i);
+          const float eij = ex2_approx(tij), eji = ex2_approx(tji);
+          float g;
+          if (yj == yi) {
+            g = ki * pos_bwd(tij, eij, ni, p.sc) + kj * pos_bwd(tji, eji, nj, p.sc);
+          } else {
+            g = -(ki * eij * ai + kj * eji * aj);
+          }
+          const bool offd = !(diag_tile && (j0 + lc == i));
+          hv[k] = (offd && (yj == yj)) ? g * h_mul : 0.f;
+          if (teacher) {
+            const float cs = cv[q * 2 + k];
+            const bool hard = (yj != yi) && (yj == yj) && row_ok && (cs > p.sc.cross_thresh);
+            gv[k] = hard ? gc_scale * rcp_approx(1.f - cs + kTiny) : 0.f;
+          } else {
+            gv[k] = 0.f;
+          }
+        }
+        hp[q] = Cvt<kBf16>::two(hv[0], hv[1]);
+        gp[q] = Cvt<kBf16>::two(gv[0], gv[1]);
+      }
+      // the previous tile's second GEMMs must have finished reading sH / sG
+      if (t > 0) mbar_wait(&ms.h_free, (t - 1) & 1);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {     // four 16-byte units = 32 bf16 columns
+        const uint32_t o = sw128_offset(r, cbase + u * 8);
+        *reinterpret_cast<uint4*>(sH + o) = make_uint4(hp[u * 4], hp[u * 4 + 1], hp[u * 4 + 2], hp[u * 4 + 3]);
+        if (teacher) *reinterpret_cast<uint4*>(sG + o) = make_uint4(gp[u * 4], gp[u * 4 + 1], gp[u * 4 + 2], gp[u * 4 + 3]);
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ms.h_full);
+    }
+
+    // ---- dF (TMEM) * go -> grad_feat ----
+    mbar_wait(&ms.df_full, 0);
+    tcgen05_after_sync();
+    const float go = __ldg(p.grad_out) / hscale;
+    const int dhalf = Dpad / 2;                      // columns per half (multiple of 32)
+    for (int c0 = half * dhalf; c0 < (half + 1) * dhalf; c0 += 32) {
+      float v[32];
+      tmem_ld32(tm_df + lane_base + c0, v);
+      tmem_ld_wait();
+      if (row_ok) {
+        float* dst = p.grad_feat + (off + i) * p.D + c0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          if (c0 + q * 4 + 3 < p.D) {
+            *reinterpret_cast<float4*>(dst + q * 4) =
+                make_float4(go * v[q * 4], go * v[q * 4 + 1], go * v[q * 4 + 2], go * v[q * 4 + 3]);
+          } else {
+            for (int k = 0; k < 4; ++k)
+              if (c0 + q * 4 + k < p.D) dst[q * 4 + k] = go * v[q * 4 + k];
+          }
+        }
+      }
+    }
+  }
+  tcgen05_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+struct TcState {
+  float* hdr;
+  void* F;
+  void* T;
+  float* stats;
+};
+constexpr size_t kHdrBytes = 1024;   // keeps the operand arrays 1024-B aligned relative to the state base
+inline int npad_of(int N) { return (N + 127) / 128 * 128; }
+inline int dpad_of(int D) { return (D + 63) / 64 * 64; }
+size_t operand_bytes(int B, int N, int D) { return align_up((size_t)B * npad_of(N) * dpad_of(D) * 2, 1024); }
+size_t stats_bytes(int B, int N) { return align_up((size_t)kNumStats * B * N * sizeof(float), 128); }
+TcState carve(void* state, int B, int N, int D, int has_teacher) {
+  char* p = reinterpret_cast<char*>(state);
+  TcState s;
+  s.hdr = reinterpret_cast<float*>(p);
+  p += kHdrBytes;
+  s.F = p;
+  p += operand_bytes(B, N, D);
+  s.T = has_teacher ? p : nullptr;
+  if (has_teacher) p += operand_bytes(B, N, D);
+  s.stats = reinterpret_cast<float*>(p);
+  return s;
+}
+
+int check_tc_shape(int B, int N, int D) {
+  DYCON_REQUIRE(D % 4 == 0 && D <= 256, DYCON_ERR_UNSUPPORTED,
+                "FeCL bf16: D=%d must be a multiple of 4 and <= 256 (the reference projection head has D=256)", D);
+  DYCON_REQUIRE((long long)(npad_of(N) / 128) * B <= kMaxPartials && B <= 65535, DYCON_ERR_UNSUPPORTED,
+                "FeCL bf16: %d row blocks x B=%d exceeds %d CTAs", npad_of(N) / 128, B, kMaxPartials);
+  return DYCON_OK;
+}
+
+// Opt the kernel into the full 227 KB of shared memory per CTA (minus its static part).
+template <typename K>
+int set_smem(K kernel) {
+  cudaFuncAttributes attr;
+  DYCON_CUDA(cudaFuncGetAttributes(&attr, kernel));
+  DYCON_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  227 * 1024 - (int)attr.sharedSizeBytes));
+  return DYCON_OK;
+}
+
+}  // namespace
+
+size_t fecl_tc_state_bytes(int B, int N, int D, int has_teacher) {
+  if (D % 4 != 0 || D > 256) return 0;
+  return kHdrBytes + operand_bytes(B, N, D) * (has_teacher ? 2 : 1) + stats_bytes(B, N);
+}
+size_t fecl_tc_workspace_bytes(int, int, int) { return 16 + sizeof(double) * 3 * kMaxPartials; }
+
+namespace {
+
+// Power of two ~ B_global N tau / 8: |H| <= 2 (1 + gamma/e) r_max / (B N tau), so scaled entries are O(1).
+float pick_hscale(double inv_rows, float inv_tau) {
+  const double x = 1.0 / (inv_rows * (double)inv_tau * 8.0);
+  int e = 0;
+  if (x > 1.0) {
+    double y = x;
+    while (y >= 2.0 && e < 40) { y *= 0.5; ++e; }
+  }
+  return (float)(1ull << e);
+}
+
+template <bool kBf16>
+int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
+  using T16 = typename Cvt<kBf16>::type;
+  const int B = p.B, N = p.N, D = p.D;
+  const int Npad = npad_of(N), Dpad = dpad_of(D), KC = Dpad / 64;
+  TcState s = carve(a.state, B, N, D, p.has_teacher);
+  const size_t plane = (size_t)B * N;
+  dim3 pgrid(Npad / 32, Dpad / 32, B);
+  pack16_kernel<kBf16><<<pgrid, 256, 0, st>>>(a.feat, a.f_sb, a.f_sn, a.f_sd, N, D, Npad, Dpad,
+                                               reinterpret_cast<T16*>(s.F));
+  if (p.has_teacher)
+    pack16_kernel<kBf16><<<pgrid, 256, 0, st>>>(a.teacher, a.t_sb, a.t_sn, a.t_sd, N, D, Npad, Dpad,
+                                                 reinterpret_cast<T16*>(s.T));
+  CUtensorMap mapF, mapT;
+  if (int rc = make_tmap_16_2d(&mapF, s.F, (uint64_t)B * Npad, Dpad, 128, kBf16)) return rc;
+  if (int rc = make_tmap_16_2d(&mapT, p.has_teacher ? s.T : s.F, (uint64_t)B * Npad, Dpad, 128, kBf16)) return rc;
+  ReduceWorkspace ws = carve_reduce_workspace(a.workspace);
+  SweepParams sp;
+  sp.N = N; sp.Npad = Npad; sp.KC = KC; sp.has_teacher = p.has_teacher;
+  sp.sc = p.sc;
+  sp.c1 = p.sc.inv_tau * kLog2e;
+  sp.inv_rows = (float)p.inv_rows;
+  sp.inv_rows_d = p.inv_rows;
+  sp.hscale = pick_hscale(p.inv_rows, p.sc.inv_tau);
+  sp.hdr = s.hdr;
+  sp.labels = a.labels; sp.row_weight = a.row_weight;
+  sp.stat_m = s.stats + kStatM * plane; sp.stat_n = s.stats + kStatN * plane;
+  sp.stat_a = s.stats + kStatA * plane; sp.stat_kappa = s.stats + kStatKappa * plane;
+  sp.ticket = ws.ticket; sp.partials = ws.partials; sp.sums_out = a.sums_out; sp.loss_out = a.loss_out;
+  // >= 120 KB of dynamic smem also pins one CTA per SM, so the 512-column TMEM allocation never contends
+  size_t smem = (size_t)3 * KC * kChunk128 + sizeof(SweepMisc);
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  static const int once = set_smem(fecl_tc_sweep_kernel<0, kBf16>) | set_smem(fecl_tc_sweep_kernel<1, kBf16>);
+  if (once) return once;
+  dim3 grid(Npad / 128, B);
+  fecl_tc_sweep_kernel<0, kBf16><<<grid, kThreads, smem, st>>>(mapF, mapT, sp);
+  fecl_tc_sweep_kernel<1, kBf16><<<grid, kThreads, smem, st>>>(mapF, mapT, sp);
+  DYCON_CUDA(cudaGetLastError());
+  count_launches(p.has_teacher ? 4 : 3);
+  return DYCON_OK;
+}
+
+template <bool kBf16>
+int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
+  const int B = p.B, N = p.N, D = p.D;
+  const int Npad = npad_of(N), Dpad = dpad_of(D), KC = Dpad / 64;
+  TcState s = carve(const_cast<void*>(a.state), B, N, D, p.has_teacher);
+  const size_t plane = (size_t)B * N;
+  CUtensorMap mapA, mapF, mapT;
+  if (int rc = make_tmap_16_2d(&mapA, s.F, (uint64_t)B * Npad, Dpad, 128, kBf16)) return rc;
+  if (int rc = make_tmap_16_2d(&mapF, s.F, (uint64_t)B * Npad, Dpad, 64, kBf16)) return rc;
+  if (int rc = make_tmap_16_2d(&mapT, p.has_teacher ? s.T : s.F, (uint64_t)B * Npad, Dpad, 64, kBf16)) return rc;
+  BwdParams bp;
+  bp.N = N; bp.Npad = Npad; bp.KC = KC; bp.D = D; bp.has_teacher = p.has_teacher;
+  bp.sc = p.sc;
+  bp.c1 = p.sc.inv_tau * kLog2e;
+  bp.labels = a.labels;
+  bp.stat_m = s.stats + kStatM * plane; bp.stat_n = s.stats + kStatN * plane;
+  bp.stat_a = s.stats + kStatA * plane; bp.stat_kappa = s.stats + kStatKappa * plane;
+  bp.hdr = s.hdr;
+  bp.cross_cnt = a.cross_cnt; bp.grad_out = a.grad_out; bp.grad_feat = a.grad_feat;
+  size_t smem = (size_t)KC * kChunk128 + 4 * (size_t)KC * kChunk64 + 2 * kChunk128 + sizeof(BwdMisc);
+  if (smem < 120 * 1024) smem = 120 * 1024;
+  static const int once = set_smem(fecl_tc_bwd_kernel<kBf16>);
+  if (once) return once;
+  DYCON_REQUIRE(smem <= 227 * 1024, DYCON_ERR_UNSUPPORTED, "FeCL tensor-core bwd: %zu bytes of shared memory needed", smem);
+  dim3 grid(Npad / 128, B);
+  fecl_tc_bwd_kernel<kBf16><<<grid, kThreads, smem, st>>>(mapA, mapF, mapT, bp);
+  DYCON_CUDA(cudaGetLastError());
+  count_launches(1);
+  return DYCON_OK;
+}
+
+}  // namespace
+
+int fecl_tc_fwd(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
+  if (int rc = check_tc_shape(p.B, p.N, p.D)) return rc;
+  return p.precision == DYCON_FECL_BF16 ? tc_fwd_impl<true>(p, a, st) : tc_fwd_impl<false>(p, a, st);
+}
+
+int fecl_tc_bwd(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
+  if (int rc = check_tc_shape(p.B, p.N, p.D)) return rc;
+  return p.precision == DYCON_FECL_BF16 ? tc_bwd_impl<true>(p, a, st) : tc_bwd_impl<false>(p, a, st);
+}
+
 }  // namespace dycon

@@ -19,34 +19,60 @@ constexpr float kEps = 1e-6f;  // dycon_losses.py:95 -- NOT a numerical no-op, k
 constexpr int kThreads = 256;
 
 // ---- C == 2 fast path ------------------------------------------------------------------------
-__device__ __forceinline__ void softmax2(float x0, float x1, float& p0, float& p1) {
-  const float d = x1 - x0;
-  const float e = __expf(-fabsf(d));            // (0, 1]
-  const float hi = __fdividef(1.f, 1.f + e);    // probability of the larger logit
-  const float lo = e * hi;
-  p1 = d >= 0.f ? hi : lo;
-  p0 = d >= 0.f ? lo : hi;
+// MUFU budget (the XU pipe issues 16 lanes/clk/SM, so it -- not HBM -- bounds this kernel unless
+// kept to ~12 ops/voxel): flush-to-zero approximations straight from PTX (no denormal fix-up
+// code), and the two-class algebra below instead of a generic softmax/log chain.
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
+
+// Two-class softmax + entropy terms of one voxel.  With a = |x1-x0|, e = exp(-a), y = eps(1+e):
+//   p_hi = 1/(1+e), p_lo = e p_hi,
+//   ln(p_hi+eps) = log1p(y) - ln(1+e)      (log1p(y) = y - y^2/2 exactly in fp32, y <= 2e-6)
+//   ln(p_lo+eps) = ln(e + y) - ln(1+e)
+struct TwoClass {
+  float p_hi, p_lo, ln_hi, ln_lo, e, x;   // x = e + y (reused by the gradient: p_lo/(p_lo+eps) = e/x)
+  float H;
+  bool hi_is_1;
+};
+__device__ __forceinline__ TwoClass two_class(float x0, float x1) {
+  TwoClass o;
+  const float d = x1 - x0, a = fabsf(d);
+  o.hi_is_1 = d >= 0.f;
+  o.e = ex2_approx(-a * kLog2e) + (a - a);          // (a - a): +-inf logits become NaN like torch.softmax
+  const float ope = 1.f + o.e;
+  o.p_hi = rcp_approx(ope);
+  o.p_lo = o.e * o.p_hi;
+  const float y = kEps * ope;
+  const float l1 = kLn2 * lg2_approx(ope);
+  o.ln_hi = fmaf(y, fmaf(-0.5f, y, 1.f), -l1);
+  o.x = o.e + y;
+  o.ln_lo = fmaf(kLn2, lg2_approx(o.x), -l1);
+  o.H = -(o.p_hi * o.ln_hi + o.p_lo * o.ln_lo);
+  return o;
 }
 
 // Returns L_v and the unit gradient dL_v/ds1 (SURVEY.md section 0.1 closed form).
+//   u = ps0 ps1 (g1 - g0),  g_c = 2 (ps_c - pt_c) W - dL/dHs (ln(ps_c+eps) + ps_c/(ps_c+eps))
 __device__ __forceinline__ void voxel2(float s0, float s1, float t0, float t1, float beta, float& L,
                                        float& u) {
-  float ps0, ps1, pt0, pt1;
-  softmax2(s0, s1, ps0, ps1);
-  softmax2(t0, t1, pt0, pt1);
-  const float ls0 = __logf(ps0 + kEps), ls1 = __logf(ps1 + kEps);
-  const float lt0 = __logf(pt0 + kEps), lt1 = __logf(pt1 + kEps);
-  const float hs = -(ps0 * ls0 + ps1 * ls1);
-  const float ht = -(pt0 * lt0 + pt1 * lt1);
-  const float es = __expf(beta * hs), et = __expf(beta * ht);
-  const float w = __fdividef(1.f, es + et);
+  const TwoClass S = two_class(s0, s1), T = two_class(t0, t1);
+  const float es = ex2_approx(beta * kLog2e * S.H), et = ex2_approx(beta * kLog2e * T.H);
+  const float w = rcp_approx(es + et);
+  const float ps1 = S.hi_is_1 ? S.p_hi : S.p_lo, ps0 = S.hi_is_1 ? S.p_lo : S.p_hi;
+  const float pt1 = T.hi_is_1 ? T.p_hi : T.p_lo, pt0 = T.hi_is_1 ? T.p_lo : T.p_hi;
   const float d0 = ps0 - pt0, d1 = ps1 - pt1;
   const float q = d0 * d0 + d1 * d1;
-  L = fmaf(q, w, beta * (hs + ht));
+  L = fmaf(q, w, beta * (S.H + T.H));
   const float dl_dh = beta - q * beta * es * w * w;
-  const float g0 = 2.f * d0 * w - dl_dh * (ls0 + __fdividef(ps0, ps0 + kEps));
-  const float g1 = 2.f * d1 * w - dl_dh * (ls1 + __fdividef(ps1, ps1 + kEps));
-  u = ps0 * ps1 * (g1 - g0);  // ps1*(g1 - ps0*g0 - ps1*g1) with ps0 + ps1 = 1
+  // (ln_hi - ln_lo) + (r_hi - r_lo),  r_hi = 1 - y(1-y),  r_lo = e / (e + y)
+  const float y = S.x - S.e;
+  const float r_hi = fmaf(-y, 1.f - y, 1.f), r_lo = S.e * rcp_approx(S.x);
+  const float hi_minus_lo = (S.ln_hi - S.ln_lo) + (r_hi - r_lo);
+  const float g1_minus_g0 = 2.f * (d1 - d0) * w - dl_dh * (S.hi_is_1 ? hi_minus_lo : -hi_minus_lo);
+  u = S.p_hi * S.p_lo * g1_minus_g0;
 }
 
 template <int kVec>
@@ -206,12 +232,20 @@ uncl_bwd_generic_kernel(const float* __restrict__ s, const float* __restrict__ t
   }
 }
 
-// grid.x blocks per sample, grid.y sample lanes; ~8 resident CTAs per SM, at most kMaxPartials blocks.
-dim3 pick_grid(int64_t B, int64_t work_items_per_sample) {
-  const int64_t target = (int64_t)sm_count() * 8;
+// One resident wave: grid.x blocks per sample x grid.y sample lanes = SMs x (CTAs that fit per SM), so
+// the grid-stride loops see no second wave and no tail; at most kMaxPartials blocks.
+template <typename Kernel>
+int resident_ctas(Kernel kernel) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0) != cudaSuccess || per_sm < 1)
+    per_sm = 4;
+  return per_sm * sm_count();
+}
+
+dim3 pick_grid(int64_t B, int64_t work_items_per_sample, int resident) {
   int64_t gy = B < 1024 ? B : 1024;
   int64_t gx = (work_items_per_sample + kThreads - 1) / kThreads;
-  int64_t cap = target / gy;
+  int64_t cap = resident / gy;
   if (cap < 1) cap = 1;
   if (gx > cap) gx = cap;
   if (gx < 1) gx = 1;
@@ -251,16 +285,19 @@ int dycon_uncl_fwd(const float* s, const float* t, int64_t B, int C, int64_t V, 
     DYCON_REQUIRE(stash && aligned(stash, 4), DYCON_ERR_ARG, "UnCL fwd: C == 2 needs a stash of B*V floats");
     const bool vec = (V % 4 == 0) && aligned(s, 16) && aligned(t, 16) && aligned(stash, 16);
     if (vec) {
-      dim3 grid = pick_grid(B, V / 4);
+      static const int res = resident_ctas(uncl_fwd_c2_kernel<4>);
+      dim3 grid = pick_grid(B, V / 4, res);
       uncl_fwd_c2_kernel<4><<<grid, kThreads, 0, st>>>(s, t, B, V, beta, inv_count, stash, ws.ticket, ws.partials,
                                                         sum_out, loss_out);
     } else {
-      dim3 grid = pick_grid(B, V);
+      static const int res = resident_ctas(uncl_fwd_c2_kernel<1>);
+      dim3 grid = pick_grid(B, V, res);
       uncl_fwd_c2_kernel<1><<<grid, kThreads, 0, st>>>(s, t, B, V, beta, inv_count, stash, ws.ticket, ws.partials,
                                                         sum_out, loss_out);
     }
   } else {
-    dim3 grid = pick_grid(B, V);
+    static const int res = resident_ctas(uncl_fwd_generic_kernel);
+    dim3 grid = pick_grid(B, V, res);
     uncl_fwd_generic_kernel<<<grid, kThreads, 0, st>>>(s, t, B, C, V, beta, inv_count, ws.ticket, ws.partials,
                                                        sum_out, loss_out);
   }
@@ -278,13 +315,16 @@ int dycon_uncl_bwd(const float* s, const float* t, const float* stash, int64_t B
     DYCON_REQUIRE(stash, DYCON_ERR_ARG, "UnCL bwd: C == 2 needs the stash written by the forward");
     const bool vec = (V % 4 == 0) && aligned(stash, 16) && aligned(grad_s, 16);
     if (vec) {
-      uncl_bwd_c2_kernel<4><<<pick_grid(B, V / 4), kThreads, 0, st>>>(stash, B, V, (float)inv_count, grad_out, grad_s);
+      static const int res = resident_ctas(uncl_bwd_c2_kernel<4>);
+      uncl_bwd_c2_kernel<4><<<pick_grid(B, V / 4, res), kThreads, 0, st>>>(stash, B, V, (float)inv_count, grad_out, grad_s);
     } else {
-      uncl_bwd_c2_kernel<1><<<pick_grid(B, V), kThreads, 0, st>>>(stash, B, V, (float)inv_count, grad_out, grad_s);
+      static const int res = resident_ctas(uncl_bwd_c2_kernel<1>);
+      uncl_bwd_c2_kernel<1><<<pick_grid(B, V, res), kThreads, 0, st>>>(stash, B, V, (float)inv_count, grad_out, grad_s);
     }
   } else {
     DYCON_REQUIRE(s && t, DYCON_ERR_ARG, "UnCL bwd: C != 2 recomputes from s/t (NULL given)");
-    uncl_bwd_generic_kernel<<<pick_grid(B, V), kThreads, 0, st>>>(s, t, B, C, V, beta, (float)inv_count, grad_out,
+    static const int res = resident_ctas(uncl_bwd_generic_kernel);
+    uncl_bwd_generic_kernel<<<pick_grid(B, V, res), kThreads, 0, st>>>(s, t, B, C, V, beta, (float)inv_count, grad_out,
                                                                   grad_s);
   }
   DYCON_CUDA(cudaGetLastError());

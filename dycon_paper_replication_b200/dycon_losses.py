@@ -14,8 +14,8 @@ unchanged; the arithmetic runs in hand-written sm_100a CUDA kernels behind the C
   update_ema_variables(model, ema_model, alpha, global_step)        train_DyCON_BraTS19.py:155-164
 
 Extensions that the reference does not have (all optional, keyword-only):
-  * ``FeCLoss(..., precision="bf16"|"fp32")`` -- similarity arithmetic (tcgen05 bf16 tiles with
-    fp32 accumulation, or exact fp32 SIMT tiles).
+  * ``FeCLoss(..., precision="fp16"|"bf16"|"fp32")`` -- similarity arithmetic: tcgen05 tiles with
+    fp16 (default) or bf16 operands and fp32 accumulation, or exact fp32 SIMT tiles.
   * ``process_group=`` on both modules -- the batch is sharded over ranks; partial sums and the
     batch-global hard-negative count are all-reduced (one 4-double message per step, see
     ``dycon_paper_replication_b200.sharded``).
@@ -215,11 +215,11 @@ class UnCLoss(nn.Module):
 
 
 # =========================================================================== FeCL
-_PRECISIONS = {"fp32": _lib.FECL_FP32, "bf16": _lib.FECL_BF16}
+_PRECISIONS = {"fp32": _lib.FECL_FP32, "bf16": _lib.FECL_BF16, "fp16": _lib.FECL_FP16}
 
 
 def default_fecl_precision():
-    return os.environ.get("DYCON_FECL_PRECISION", "fp32")
+    return os.environ.get("DYCON_FECL_PRECISION", "fp16")
 
 
 class _FeCLFunction(torch.autograd.Function):

@@ -43,8 +43,9 @@ extern "C" {
 #define DYCON_ERR_WORKSPACE (-4)   /* workspace / state buffer too small                 */
 
 /* FeCL similarity arithmetic */
-#define DYCON_FECL_FP32 0 /* SIMT fp32 tiles (exact mode, parity 1e-5)                      */
-#define DYCON_FECL_BF16 1 /* TMA + tcgen05/TMEM tiles, bf16 operands, fp32 accumulate (2e-3) */
+#define DYCON_FECL_FP32 0 /* SIMT fp32 tiles (exact mode, parity 1e-5)                              */
+#define DYCON_FECL_BF16 1 /* TMA + tcgen05/TMEM tiles, bf16 operands, fp32 accumulate                  */
+#define DYCON_FECL_FP16 2 /* same kernels with fp16 operands (10-bit mantissa): meets 2e-3 on all inputs */
 
 typedef void* dycon_stream_t; /* a cudaStream_t (NULL = legacy default stream) */
 

@@ -50,7 +50,7 @@ def uncl(s, t, beta, go=1.0, count=None):
 
 # --------------------------------------------------------------------------- FeCL
 def fecl(feat, mask, teacher=None, row_weight=None, *, inv_tau, gamma=2.0, use_focal=False,
-         cross_thresh=0.5, lambda_cross=1.0, go=1.0, rows_global=None, cnt_global=None):
+         cross_thresh=0.5, lambda_cross=1.0, go=1.0, rows_global=None, cnt_global=None, ambiguity=0.0):
     """FeCL value, gradient and the per-row statistics the kernels keep.
 
     feat/teacher (B,N,D), mask (B,N) labels, row_weight (B,N)|None (the reference's
@@ -60,6 +60,11 @@ def fecl(feat, mask, teacher=None, row_weight=None, *, inv_tau, gamma=2.0, use_f
     ``rows_global`` / ``cnt_global`` override the two batch-global normalisers
     (B*N of the mean at :193/:206/:211 and the hard-negative count at :229) for
     the sharded path.
+
+    ``ambiguity`` > 0 additionally reports the negative pairs whose cross similarity lies within
+    that distance of ``cross_thresh``: membership of the hard set is a step function of ``cs``
+    (dycon_losses.py:223), so an implementation that rounds ``cs`` differently may legitimately
+    flip exactly those pairs (see ``fecl_grad_error``).
     """
     f = np.asarray(feat, np.float64)
     b, n, _ = f.shape
@@ -96,6 +101,8 @@ def fecl(feat, mask, teacher=None, row_weight=None, *, inv_tau, gamma=2.0, use_f
     dl = kappa[:, :, None] * (dphi * d * (1.0 - d) - neg * e * a[:, :, None])
     g = np.where(offd, dl, 0.0) * inv_tau
     grad = np.einsum("bij,bjd->bid", g + g.transpose(0, 2, 1), f)
+    grad_student = grad
+    cross_unnorm, ambiguous = None, []
 
     cross_sum, cnt = 0.0, 0.0
     if teacher is not None:
@@ -109,12 +116,59 @@ def fecl(feat, mask, teacher=None, row_weight=None, *, inv_tau, gamma=2.0, use_f
         with np.errstate(divide="ignore", invalid="ignore"):
             gc = np.where(hard, 1.0 / ((1.0 - cs + EPS_FECL) * (cg + EPS_FECL)), 0.0)
         grad = grad + lambda_cross * np.einsum("bij,bjd->bid", gc, tf)
+        if ambiguity > 0:
+            with np.errstate(divide="ignore", invalid="ignore"):
+                cross_unnorm = np.einsum("bij,bjd->bid", np.where(hard, 1.0 / (1.0 - cs + EPS_FECL), 0.0), tf)
+            for bb, ii, jj in zip(*np.nonzero(neg & (np.abs(cs - cross_thresh) <= ambiguity))):
+                ambiguous.append((int(bb), int(ii), int(jj), float(cs[bb, ii, jj]), bool(hard[bb, ii, jj])))
     else:
         cg = 0.0
 
     loss = student_sum / rows + lambda_cross * (cross_sum / (cg + EPS_FECL) if teacher is not None else 0.0)
     return {"loss": loss, "grad": go * grad, "m": m, "n": nsum, "A": a, "kappa": kappa,
-            "student_sum": student_sum, "cross_sum": cross_sum, "cnt": cnt}
+            "student_sum": student_sum, "cross_sum": cross_sum, "cnt": cnt,
+            "grad_student": go * grad_student, "cross_unnorm": cross_unnorm, "ambiguous": ambiguous,
+            "go": go, "lambda_cross": lambda_cross}
+
+
+def fecl_grad_error(grad, ref, teacher, max_per_row=14):
+    """max|grad - oracle| / max|oracle|, minimised over the admissible states of the threshold-boundary
+    pairs listed in ``ref["ambiguous"]`` (needs ``fecl(..., ambiguity=delta)``).
+
+    The cross gradient is (lambda/(cnt+1e-18)) * sum_hard t_j/(1-cs_ij): a boundary pair (i,j) only moves
+    row i (plus the global count), so the admissible state is chosen row by row from the cached
+    un-normalised sum (all 2^k states of the k boundary pairs of a row are evaluated at once); the
+    oracle is not re-run.
+    """
+    g = np.asarray(grad, np.float64)
+    scale = np.abs(ref["grad"]).max()
+
+    def err(x):
+        return float(np.abs(g - x).max() / scale)
+
+    amb = ref["ambiguous"]
+    plain = err(ref["grad"])
+    if not amb or ref["cross_unnorm"] is None:
+        return plain
+    tf = np.asarray(teacher, np.float64)
+    k = ref["go"] * ref["lambda_cross"]
+    rows = {}
+    for b, i, j, cs, hard in amb:
+        rows.setdefault((b, i), []).append((j, cs, hard))
+    u = ref["cross_unnorm"].copy()
+    cnt = ref["cnt"]
+    net = 0.0
+    for (b, i), pairs in rows.items():
+        if len(pairs) > max_per_row:
+            raise ValueError(f"{len(pairs)} threshold-boundary pairs in one row: shrink `ambiguity`")
+        signs = np.array([-1.0 if hard else 1.0 for _, _, hard in pairs])
+        contrib = np.stack([sg * tf[b, j] / (1.0 - cs + EPS_FECL) for sg, (j, cs, _) in zip(signs, pairs)])
+        bits = ((np.arange(1 << len(pairs))[:, None] >> np.arange(len(pairs))[None, :]) & 1).astype(np.float64)
+        cand = ref["grad_student"][b, i][None, :] + k * (u[b, i][None, :] + bits @ contrib) / (cnt + EPS_FECL)
+        best = int(np.abs(cand - g[b, i][None, :]).max(axis=1).argmin())
+        u[b, i] = u[b, i] + bits[best] @ contrib
+        net += float(bits[best] @ signs)
+    return min(plain, err(ref["grad_student"] + k * u / (cnt + net + EPS_FECL)))
 
 
 # --------------------------------------------------------------------------- EMA
