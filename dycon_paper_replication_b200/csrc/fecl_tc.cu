@@ -11,8 +11,8 @@
 // No (N,N) tensor is ever written: every similarity tile lives in TMEM and is consumed in place.
 //
 // Kernels (a CTA owns 128 rows of one sample; 10 warps: TMA producer, MMA issuer, 8 epilogue):
-//   fecl_tc_sweep_kernel<0>  P0: S = F_I F_J^T tiles -> row max m_i, positive count -> kappa_i
-//   fecl_tc_sweep_kernel<1>  P1: S tiles -> n_i ;  P2: S tiles -> row loss, A_i ; F_I T_J^T tiles -> cross sum/count
+//   fecl_tc_sweep_kernel<0,..>  P0: S = F_I F_J^T tiles -> row max m_i, positive count -> kappa_i
+//   fecl_tc_sweep_kernel<1,..>  P1: S tiles -> n_i ;  P2: S tiles -> row loss, A_i ; F_I T_J^T tiles -> cross sum/count
 //   fecl_tc_bwd_kernel       per 64-column tile: S, CS -> H = G + G^T, Gc (bf16, written to smem in the
 //                            UMMA K-major swizzle) -> dF_I += H F_J + Gc T_J with F_J / T_J read as
 //                            MN-major operands from the very tiles that produced S / CS.
@@ -36,38 +36,38 @@ __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
-__device__ __forceinline__ float pow_gm1(float x, float g) {   // x^(g-1), x in [0,1]
-  if (g == 2.f) return x;
-  if (g == 1.f) return 1.f;
-  if (g == 3.f) return x * x;
-  return ex2_approx((g - 1.f) * lg2_approx(x));
-}
+// Focal variants are compile-time (a runtime `if (focal)` / gamma test per pair costs branches in the
+// hottest loop): 0 = no focal weight, 1 = gamma == 2 (the scripts' value), 2 = any gamma.
+enum { kNoFocal = 0, kFocalG2 = 1, kFocalAny = 2 };
 
-// Positive pair with exponent argument t = log2(e_ij) and row negative-sum n:
-//   forward : phi(d) and the A-summand phi'(d) d / T;   backward: phi'(d) d (1-d).
-__device__ __forceinline__ void pos_fwd(float t, float e, float n, const FeclScalars& sc, float& phi, float& a_term) {
+// Positive pair, with t = log2(e_ij) (the exponent argument), e = 2^t and the row's negative sum n:
+//   T = e + n, d = e/T, log2 d = t - log2 T.
+// fwd returns phi2 with phi(d) = -ln2 * phi2 (the -ln2 is applied once per row) and the A-summand
+// phi'(d) d / T;  bwd returns phi'(d) d (1-d).
+template <int kFocal>
+__device__ __forceinline__ void pos_fwd(float t, float e, float n, float gamma, float& phi2, float& a_term) {
   const float T = e + n;
   const float rT = rcp_approx(T);
-  const float d = e * rT;
-  const float logd = kLn2 * (t - lg2_approx(T));
-  if (sc.focal) {
-    const float omd = 1.f - d, w1 = pow_gm1(omd, sc.gamma), w = w1 * omd;
-    phi = -logd * w;
-    a_term = (sc.gamma * w1 * d * logd - w) * rT;
-  } else {
-    phi = -logd;
+  const float tL = t - lg2_approx(T);
+  if (kFocal == kNoFocal) {
+    phi2 = tL;
     a_term = -rT;
+  } else {
+    const float d = e * rT, omd = 1.f - d;
+    const float w1 = kFocal == kFocalG2 ? omd : ex2_approx((gamma - 1.f) * lg2_approx(omd));
+    const float w = w1 * omd;
+    phi2 = tL * w;
+    a_term = fmaf(gamma * kLn2 * w1 * d, tL, -w) * rT;
   }
 }
-__device__ __forceinline__ float pos_bwd(float t, float e, float n, const FeclScalars& sc) {
+template <int kFocal>
+__device__ __forceinline__ float pos_bwd(float t, float e, float n, float gamma) {
   const float T = e + n;
-  const float d = e * rcp_approx(T);
-  const float omd = 1.f - d;
-  if (sc.focal) {
-    const float logd = kLn2 * (t - lg2_approx(T));
-    return pow_gm1(omd, sc.gamma) * omd * (sc.gamma * d * logd - omd);
-  }
-  return -omd;
+  const float d = e * rcp_approx(T), omd = 1.f - d;
+  if (kFocal == kNoFocal) return -omd;
+  const float tL = t - lg2_approx(T);
+  const float w1 = kFocal == kFocalG2 ? omd : ex2_approx((gamma - 1.f) * lg2_approx(omd));
+  return w1 * omd * fmaf(gamma * kLn2 * d, tL, -omd);
 }
 
 // ---- pack: fp32 (B,N,D) with element strides -> bf16 [B][Npad][Dpad], zero padded ---------------
@@ -147,12 +147,81 @@ struct SweepMisc {
   uint64_t acc_full[4], acc_empty[4];
   uint32_t tmem_slot;
   uint32_t pad_;
-  float col[2][2][128];    // [slot][stat: y, m2][column]
-  float xch[3][128];       // half-1 -> half-0 exchange of per-row partials
+  alignas(16) float col[2][2][128];    // [slot][stat: y, m2][column]; padded columns carry y = NaN, m2 = +inf
+  float xch[2][128];       // column-half 1 -> column-half 0 exchange of per-row partials
   double scratch[3 * 32];
 };
 
-template <int kMode, bool kBf16>  // kMode 0: row max + kappa,  1: n / loss / A / cross
+// Epilogue bodies: one 32-column chunk of one accumulator row per thread.  `cy` / `cm` point at this
+// chunk's staged column labels / scaled column maxima in shared memory (read as broadcast float4).
+// rdiag = the chunk-local index of the diagonal element of this row, or -1.
+__device__ __forceinline__ void body_rowmax(const float (&v)[32], const float* cy, float yi, int rdiag, float& mx,
+                                            float& cnt) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
+    const float ys[4] = {yy.x, yy.y, yy.z, yy.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = q * 4 + k;
+      mx = fmaxf(mx, c == rdiag ? 0.f : v[c]);     // padded columns hold S = 0 <= mx
+      cnt += ys[k] == yi ? 1.f : 0.f;
+    }
+  }
+}
+__device__ __forceinline__ void body_negsum(const float (&v)[32], const float* cy, const float* cm, float yi, float c1,
+                                            float& nsum) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
+    const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
+    const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float e = ex2_approx(fmaf(v[q * 4 + k], c1, -m2[k]));   // padded: m2 = +inf -> e = 0
+      nsum += ys[k] != yi ? e : 0.f;
+    }
+  }
+}
+template <int kFocal>
+__device__ __forceinline__ void body_pos(const float (&v)[32], const float* cy, const float* cm, float yi, int rdiag,
+                                         float c1, float n_row, float gamma, float& lsum, float& asum) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
+    const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
+    const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = q * 4 + k;
+      const float t = fmaf(v[c], c1, -m2[k]);
+      float phi2, at;
+      pos_fwd<kFocal>(t, ex2_approx(t), n_row, gamma, phi2, at);
+      const bool pos = (ys[k] == yi) && (c != rdiag);    // select, never multiply: the unused lane may be NaN
+      lsum += pos ? phi2 : 0.f;
+      asum += pos ? at : 0.f;
+    }
+  }
+}
+__device__ __forceinline__ void body_cross(const float (&v)[32], const float* cy, const float* cm, float yi,
+                                           float thresh, float& csum, float& ccnt) {
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
+    const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
+    const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float cs = v[q * 4 + k];
+      const bool hard = (ys[k] != yi) && (cs > thresh) && (m2[k] != INFINITY);   // m2 = +inf marks padding
+      const float term = lg2_approx(1.f - cs + kTiny);       // NaN for cs > 1, like the reference's log
+      csum += hard ? term : 0.f;
+      ccnt += hard ? 1.f : 0.f;
+    }
+  }
+}
+
+template <int kMode, bool kBf16, int kFocal>  // kMode 0: row max + kappa,  1: n / loss / A / cross
 __global__ void __launch_bounds__(kThreads, 1)
 fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapT,
                      const SweepParams p) {
@@ -160,13 +229,14 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KC = p.KC;
   const uint32_t tile_bytes = (uint32_t)KC * kChunk128;
-  uint8_t* sA = smem;
-  uint8_t* sB[2] = {smem + tile_bytes, smem + 2 * tile_bytes};
+  uint8_t* const sA = smem;
+  uint8_t* const sB0 = smem + tile_bytes;
   SweepMisc& ms = *reinterpret_cast<SweepMisc*>(smem + 3 * tile_bytes);
   const int b = blockIdx.y, i0 = blockIdx.x * kTM;
   const int nt = p.Npad / 128;
-  const int per_j = 1 + (kMode == 1 ? p.has_teacher : 0);
-  const int total = kMode == 0 ? nt : nt + nt * per_j;
+  const bool teacher_on = kMode == 1 && p.has_teacher;
+  const int per_j = teacher_on ? 2 : 1;
+  const int total = kMode == 0 ? nt : nt + nt * per_j;   // P1 tiles, then per column tile: S [, CS]
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
@@ -175,7 +245,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
     for (int a = 0; a < 4; ++a) mbar_init(&ms.acc_full[a], 1), mbar_init(&ms.acc_empty[a], 8);
     fence_mbar_init();
     prefetch_tmap(&mapF);
-    if (kMode == 1 && p.has_teacher) prefetch_tmap(&mapT);
+    if (teacher_on) prefetch_tmap(&mapT);
     if (kMode == 0 && blockIdx.x == 0 && blockIdx.y == 0) p.hdr[0] = p.hscale;
   }
   if (warp == 1) tmem_alloc(&ms.tmem_slot, 512);
@@ -183,14 +253,6 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
   __syncthreads();
   tcgen05_after_sync();
   const uint32_t tmem = ms.tmem_slot;
-
-  // tile t -> (column tile, operand)
-  auto tile_of = [&](int t, int& jt, bool& teacher) {
-    if (kMode == 0 || t < nt) { jt = t; teacher = false; return; }
-    const int u = t - nt;
-    jt = u / per_j;
-    teacher = (u % per_j) == 1;
-  };
 
   double red[3] = {0.0, 0.0, 0.0};
 
@@ -201,18 +263,25 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
       for (int c = 0; c < KC; ++c) tma_load_2d(sA + c * kChunk128, &mapF, c * 64, b * p.Npad + i0, &ms.a_full);
       for (int t = 0; t < total; ++t) {
         const int s = t & 1;
-        int jt; bool teacher;
-        tile_of(t, jt, teacher);
+        int jt = t;
+        bool teacher = false;
+        if (kMode == 1 && t >= nt) {
+          const int u = t - nt;
+          jt = u / per_j;
+          teacher = (u % per_j) == 1;
+        }
+        uint8_t* dst = sB0 + s * tile_bytes;
         mbar_wait(&ms.b_empty[s], ((t >> 1) & 1) ^ 1);
         mbar_expect_tx(&ms.b_full[s], tile_bytes);
         for (int c = 0; c < KC; ++c)
-          tma_load_2d(sB[s] + c * kChunk128, teacher ? &mapT : &mapF, c * 64, b * p.Npad + jt * 128, &ms.b_full[s]);
+          tma_load_2d(dst + c * kChunk128, teacher ? &mapT : &mapF, c * 64, b * p.Npad + jt * 128, &ms.b_full[s]);
       }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
     if (lane == 0) {
       const uint32_t idesc = umma_idesc_16(128, 128, false, false, kBf16);
+      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB0);
       mbar_wait(&ms.a_full, 0);
       for (int t = 0; t < total; ++t) {
         const int s = t & 1, a = t & 3;
@@ -223,8 +292,8 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
         for (int c = 0; c < KC; ++c) {
 #pragma unroll
           for (int k = 0; k < 4; ++k)
-            umma_bf16(d_tmem, umma_desc_kmajor(smem_u32(sA + c * kChunk128) + k * 32),
-                      umma_desc_kmajor(smem_u32(sB[s] + c * kChunk128) + k * 32), idesc, (c | k) != 0);
+            umma_bf16(d_tmem, umma_desc_kmajor(a_addr + c * kChunk128 + k * 32),
+                      umma_desc_kmajor(b_addr + s * tile_bytes + c * kChunk128 + k * 32), idesc, (c | k) != 0);
         }
         umma_commit(&ms.b_empty[s]);
         umma_commit(&ms.acc_full[a]);
@@ -237,108 +306,106 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
     const int r = quarter * 32 + lane, i = i0 + r;
     const bool row_ok = i < p.N;
     const float* yb = p.labels + (size_t)b * p.N;
-    const float yi = row_ok ? __ldg(yb + i) : __int_as_float(0x7fc00000);
+    const float* mb = p.stat_m + (size_t)b * p.N;
+    const float qnan = __int_as_float(0x7fc00000);
+    const float yi = row_ok ? __ldg(yb + i) : qnan;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;   // mode 0: max, count; mode 1: n | loss, A | cross sum, count
-    float n_row = 0.f;
+    const int cidx = et & 127;
 
-    for (int t = 0; t < total; ++t) {
-      const int a = t & 3, slot = t & 1;
-      int jt; bool teacher;
-      tile_of(t, jt, teacher);
-      const int j0 = jt * 128;
-      // ---- stage the column statistics of this tile ----
-      {
-        const int cidx = et & 127, j = j0 + cidx;
-        if (et < 128) {
-          ms.col[slot][0][cidx] = j < p.N ? __ldg(yb + j) : __int_as_float(0x7fc00000);
-        } else if (kMode == 1) {
-          ms.col[slot][1][cidx] = j < p.N ? __ldg(p.stat_m + (size_t)b * p.N + j) * kLog2e : INFINITY;
-        }
-      }
-      if (kMode == 1 && t == nt) {
-        // P1 -> P2: publish the other half's partial n_i and total them
-        if (half == 1) ms.xch[0][r] = acc0;
-        epi_barrier();
-        if (half == 0) ms.xch[1][r] = acc0;
-        epi_barrier();
-        n_row = ms.xch[0][r] + ms.xch[1][r];
-        acc0 = 0.f;
-      } else {
-        epi_barrier();
-      }
+    // column statistics of tile jt: threads 0..127 fetch the label, 128..255 the (scaled) column max
+    auto fetch = [&](int jt) -> float {
+      const int j = jt * 128 + cidx;
+      if (et < 128) return j < p.N ? __ldg(yb + j) : qnan;
+      if (kMode == 0) return 0.f;
+      return j < p.N ? __ldg(mb + j) * kLog2e : INFINITY;
+    };
+    auto publish = [&](int slot, float val) { ms.col[slot][et >> 7][cidx] = val; };
+    // wait for accumulator `t`, hand each 32-column chunk of this thread's half to `body`, release it
+    auto consume = [&](int t, auto&& body) {
+      const int a = t & 3;
       mbar_wait(&ms.acc_full[a], (t >> 2) & 1);
       tcgen05_after_sync();
-      const bool diag = (jt == (int)blockIdx.x) && !teacher;
-#pragma unroll
+#pragma unroll 1
       for (int ch = 0; ch < 2; ++ch) {
         const int cbase = half * 64 + ch * 32;
         float v[32];
         tmem_ld32(tmem + lane_base + a * 128 + cbase, v);
         tmem_ld_wait();
-        const float4* y4 = reinterpret_cast<const float4*>(&ms.col[slot][0][cbase]);
-        const float4* m4 = reinterpret_cast<const float4*>(&ms.col[slot][1][cbase]);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 yy = y4[q];
-          float4 mm = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (kMode == 1) mm = m4[q];
-          const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int lc = cbase + q * 4 + k;
-            const float x = v[q * 4 + k];
-            const bool same = ys[k] == yi;
-            const bool offd = !(diag && lc == r);
-            if (kMode == 0) {
-              if (offd) acc0 = fmaxf(acc0, x);
-              acc1 += same ? 1.f : 0.f;
-            } else if (t < nt) {
-              const float e = ex2_approx(fmaf(x, p.c1, -m2[k]));
-              acc0 += (ys[k] != yi) ? e : 0.f;               // padded columns: m2 = +inf -> e = 0
-            } else if (!teacher) {
-              const float targ = fmaf(x, p.c1, -m2[k]);
-              const float e = ex2_approx(targ);
-              float phi, at;
-              pos_fwd(targ, e, n_row, p.sc, phi, at);
-              const bool pos = same && offd;
-              acc0 += pos ? phi : 0.f;
-              acc1 += pos ? at : 0.f;
-            } else {
-              const bool hard = (ys[k] != yi) && (ys[k] == ys[k]) && row_ok && (x > p.sc.cross_thresh);
-              if (hard) {
-                acc2 += -kLn2 * lg2_approx(1.f - x + kTiny);
-                acc3 += 1.f;
-              }
-            }
-          }
-        }
+        body(v, cbase);
       }
       tcgen05_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ms.acc_empty[a]);
-    }
+    };
 
-    // ---- combine the two column halves, write per-row statistics ----
+    publish(0, fetch(0));
     epi_barrier();
-    if (half == 1) { ms.xch[0][r] = acc0; ms.xch[1][r] = acc1; }
-    epi_barrier();
-    if (half == 0 && row_ok) {
-      const size_t g = (size_t)b * p.N + i;
-      if (kMode == 0) {
-        const float mx = fmaxf(acc0, ms.xch[0][r]) * p.sc.inv_tau;      // >= 0: the zeroed diagonal takes part
-        const float P = acc1 + ms.xch[1][r];
+    int t = 0;
+    if (kMode == 0) {
+      float mx = 0.f, cnt = 0.f;    // the zeroed diagonal always takes part in the max (dycon_losses.py:178-180)
+      for (int jt = 0; jt < nt; ++jt, ++t) {
+        const int slot = jt & 1;
+        const float nxt = fetch(jt + 1 < nt ? jt + 1 : jt);
+        const int dloc = jt == (int)blockIdx.x ? r : -1;
+        consume(t, [&](const float (&v)[32], int cbase) {
+          body_rowmax(v, &ms.col[slot][0][cbase], yi, dloc - cbase, mx, cnt);
+        });
+        publish(slot ^ 1, nxt);
+        epi_barrier();
+      }
+      if (half == 1) { ms.xch[0][r] = mx; ms.xch[1][r] = cnt; }
+      epi_barrier();
+      if (half == 0 && row_ok) {
+        const size_t g = (size_t)b * p.N + i;
+        const float m = fmaxf(mx, ms.xch[0][r]) * p.sc.inv_tau;
+        const float P = cnt + ms.xch[1][r];
         const float rw = p.row_weight ? __ldg(p.row_weight + g) : 1.f;
-        p.stat_m[g] = mx;
+        p.stat_m[g] = m;
         p.stat_kappa[g] = rw / ((P - 1.f) + kTiny) * p.inv_rows;
-      } else {
-        const float ls = acc0 + ms.xch[0][r], as = acc1 + ms.xch[1][r];
+      }
+    } else {
+      // ---- P1: n_i = sum_k neg_ik exp(l_ik - m_k)              (dycon_losses.py:183-184)
+      float nsum = 0.f;
+      for (int jt = 0; jt < nt; ++jt, ++t) {
+        const int slot = jt & 1;
+        const float nxt = fetch(jt + 1 < nt ? jt + 1 : 0);      // after the last P1 tile: tile 0 of P2
+        consume(t, [&](const float (&v)[32], int cbase) {
+          body_negsum(v, &ms.col[slot][0][cbase], &ms.col[slot][1][cbase], yi, p.c1, nsum);
+        });
+        publish(slot ^ 1, nxt);
+        if (jt + 1 == nt) ms.xch[half][r] = nsum;
+        epi_barrier();
+      }
+      const float n_row = ms.xch[0][r] + ms.xch[1][r];
+      // ---- P2: positives -> row loss and A_i; teacher tile -> cross sum / count   (:186-229)
+      float lsum = 0.f, asum = 0.f, csum = 0.f, ccnt = 0.f;
+      for (int jt = 0; jt < nt; ++jt) {
+        const int slot = (nt + jt) & 1;
+        const float nxt = fetch(jt + 1 < nt ? jt + 1 : jt);
+        const int dloc = jt == (int)blockIdx.x ? r : -1;
+        consume(t++, [&](const float (&v)[32], int cbase) {
+          body_pos<kFocal>(v, &ms.col[slot][0][cbase], &ms.col[slot][1][cbase], yi, dloc - cbase, p.c1, n_row,
+                           p.sc.gamma, lsum, asum);
+        });
+        if (teacher_on) {
+          consume(t++, [&](const float (&v)[32], int cbase) {
+            body_cross(v, &ms.col[slot][0][cbase], &ms.col[slot][1][cbase], yi, p.sc.cross_thresh, csum, ccnt);
+          });
+        }
+        publish(slot ^ 1, nxt);
+        epi_barrier();
+      }
+      if (half == 1) { ms.xch[0][r] = lsum; ms.xch[1][r] = asum; }
+      epi_barrier();
+      if (half == 0 && row_ok) {
+        const size_t g = (size_t)b * p.N + i;
+        const float ls = -kLn2 * (lsum + ms.xch[0][r]), as = asum + ms.xch[1][r];
         p.stat_n[g] = n_row;
         p.stat_a[g] = as;
-        red[0] = (double)(__ldg(p.stat_kappa + g) * ls);
+        red[0] = (double)(__ldg(p.stat_kappa + g) * ls);   // kappa_i = r_i c_i inv_rows
       }
+      if (row_ok) { red[1] = (double)(-kLn2 * csum); red[2] = (double)ccnt; }
     }
-    if (kMode == 1) { red[1] = (double)acc2; red[2] = (double)acc3; }
   }
 
   // ---- block / grid reduction of {student, cross_sum, cross_cnt} (mode 1) ----
@@ -386,10 +453,10 @@ struct BwdMisc {
   uint64_t h_full, h_free, df_full;
   uint32_t tmem_slot;
   uint32_t pad_;
-  float col[2][5][64];   // [slot][y, m2, n, A, kappa][column]
+  alignas(16) float col[2][5][64];   // [slot][y, m2, n, A, kappa][column]
 };
 
-template <bool kBf16>
+template <bool kBf16, int kFocal>
 __global__ void __launch_bounds__(kThreads, 1)
 fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapF,
                    const __grid_constant__ CUtensorMap mapT, const BwdParams p) {
@@ -501,37 +568,41 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const bool row_ok = i < p.N;
     const size_t off = (size_t)b * p.N;
     const int ic = row_ok ? i : p.N - 1;
-    const float yi = row_ok ? __ldg(p.labels + off + ic) : __int_as_float(0x7fc00000);
+    const float qnan = __int_as_float(0x7fc00000);
+    const float yi = row_ok ? __ldg(p.labels + off + ic) : qnan;
     const float m2i = __ldg(p.stat_m + off + ic) * kLog2e;
     const float ni = __ldg(p.stat_n + off + ic), ai = __ldg(p.stat_a + off + ic);
     const float ki = row_ok ? __ldg(p.stat_kappa + off + ic) : 0.f;
     // H and Gc are scaled by a power of two (~ B N tau / 8, so |H| stays O(1)) before the 16-bit
     // conversion: exact, and it keeps fp16 out of its subnormal range.  Undone when dF is read out.
     const float hscale = __ldg(p.hdr);
-    const float gc_scale = teacher ? hscale * p.sc.lambda_cross / ((float)(*p.cross_cnt) + kTiny) : 0.f;
+    const float gc_scale = (teacher && row_ok) ? hscale * p.sc.lambda_cross / ((float)(*p.cross_cnt) + kTiny) : 0.f;
     const float h_mul = p.sc.inv_tau * hscale;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int cbase = half * 32;                  // this thread's 32 columns of the 64-column tile
 
+    // column statistics of tile t: 5 planes x 64 columns = 320 values; threads 0..255 fetch one each,
+    // threads 0..63 one more (the kappa plane).  Padded columns: y = NaN, m2 = +inf, rest 0.
+    auto fetch_one = [&](int t, int q) -> float {
+      const int st = q >> 6, j = t * 64 + (q & 63);
+      if (j >= p.N) return st == 0 ? qnan : st == 1 ? INFINITY : 0.f;
+      const float* src = st == 0 ? p.labels : st == 1 ? p.stat_m : st == 2 ? p.stat_n : st == 3 ? p.stat_a : p.stat_kappa;
+      const float val = __ldg(src + off + j);
+      return st == 1 ? val * kLog2e : val;
+    };
+    auto publish = [&](int slot, float v0, float v1) {
+      ms.col[slot][et >> 6][et & 63] = v0;
+      if (et < 64) ms.col[slot][4][et] = v1;
+    };
+    publish(0, fetch_one(0, et), et < 64 ? fetch_one(0, 256 + et) : 0.f);
+    epi_barrier();
+
     for (int t = 0; t < nt; ++t) {
       const int s = t & 1, j0 = t * 64;
-      // stage column statistics (5 x 64 floats) -- 256 threads cover 320 values in two rounds
-      for (int q = et; q < 320; q += kEpiThreads) {
-        const int st = q >> 6, cidx = q & 63, j = j0 + cidx;
-        float val;
-        if (j < p.N) {
-          const float* src = st == 0 ? p.labels : st == 1 ? p.stat_m : st == 2 ? p.stat_n : st == 3 ? p.stat_a : p.stat_kappa;
-          val = __ldg(src + off + j);
-          if (st == 1) val *= kLog2e;
-        } else {
-          val = st == 0 ? __int_as_float(0x7fc00000) : st == 1 ? INFINITY : 0.f;
-        }
-        ms.col[s][st][cidx] = val;
-      }
-      epi_barrier();
+      const int tn = t + 1 < nt ? t + 1 : t;
+      const float nx0 = fetch_one(tn, et), nx1 = et < 64 ? fetch_one(tn, 256 + et) : 0.f;
       mbar_wait(&ms.sc_full[s], (t >> 1) & 1);
       tcgen05_after_sync();
-      const bool diag_tile = (j0 >= i0) && (j0 < i0 + kTM);
       float sv[32], cv[32];
       tmem_ld32(tm_s + lane_base + s * 64 + cbase, sv);
       if (teacher) tmem_ld32(tm_cs + lane_base + s * 64 + cbase, cv);
@@ -540,48 +611,58 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&ms.sc_empty[s]);
 
+      const int rdiag = i - j0 - cbase;             // chunk-local index of the diagonal element (if in range)
+      const float* cy = &ms.col[s][0][cbase];
+      const float* cm = &ms.col[s][1][cbase];
+      const float* cn = &ms.col[s][2][cbase];
+      const float* ca = &ms.col[s][3][cbase];
+      const float* ck = &ms.col[s][4][cbase];
       uint32_t hp[16], gp[16];
 #pragma unroll
-      for (int q = 0; q < 16; ++q) {
-        float hv[2], gv[2];
+      for (int q = 0; q < 8; ++q) {
+        const float4 y4 = *reinterpret_cast<const float4*>(cy + q * 4), m4 = *reinterpret_cast<const float4*>(cm + q * 4);
+        const float4 n4 = *reinterpret_cast<const float4*>(cn + q * 4), a4 = *reinterpret_cast<const float4*>(ca + q * 4);
+        const float4 k4 = *reinterpret_cast<const float4*>(ck + q * 4);
+        const float ys[4] = {y4.x, y4.y, y4.z, y4.w}, m2[4] = {m4.x, m4.y, m4.z, m4.w}, ns[4] = {n4.x, n4.y, n4.z, n4.w};
+        const float as[4] = {a4.x, a4.y, a4.z, a4.w}, ks[4] = {k4.x, k4.y, k4.z, k4.w};
+        float hv[4], gv[4];
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const int lc = cbase + q * 2 + k;
-          const float yj = ms.col[s][0][lc], m2j = ms.col[s][1][lc], nj = ms.col[s][2][lc];
-          const float aj = ms.col[s][3][lc], kj = ms.col[s][4][lc];
-          const float x = sv[q * 2 + k];
-          const float tij = fmaf(x, p.c1, -m2j), tji = fmaf(x, p.c1, -m2i);
+        for (int k = 0; k < 4; ++k) {
+          const int c = q * 4 + k;
+          const float x = sv[c];
+          const float tij = fmaf(x, p.c1, -m2[k]), tji = fmaf(x, p.c1, -m2i);
           const float eij = ex2_approx(tij), eji = ex2_approx(tji);
-          float g;
-          if (yj == yi) {
-            g = ki * pos_bwd(tij, eij, ni, p.sc) + kj * pos_bwd(tji, eji, nj, p.sc);
-          } else {
-            g = -(ki * eij * ai + kj * eji * aj);
-          }
-          const bool offd = !(diag_tile && (j0 + lc == i));
-          hv[k] = (offd && (yj == yj)) ? g * h_mul : 0.f;
+          const float gpos = ki * pos_bwd<kFocal>(tij, eij, ni, p.sc.gamma) + ks[k] * pos_bwd<kFocal>(tji, eji, ns[k], p.sc.gamma);
+          const float gneg = -(ki * eij * ai + ks[k] * eji * as[k]);
+          const float g = ys[k] == yi ? gpos : gneg;            // select: the unused branch may be NaN
+          const bool live = (c != rdiag) && (m2[k] != INFINITY);  // diagonal and padded columns carry no gradient
+          hv[k] = live ? g * h_mul : 0.f;
           if (teacher) {
-            const float cs = cv[q * 2 + k];
-            const bool hard = (yj != yi) && (yj == yj) && row_ok && (cs > p.sc.cross_thresh);
+            const float cs = cv[c];
+            const bool hard = (ys[k] != yi) && (cs > p.sc.cross_thresh) && (m2[k] != INFINITY);
             gv[k] = hard ? gc_scale * rcp_approx(1.f - cs + kTiny) : 0.f;
           } else {
             gv[k] = 0.f;
           }
         }
-        hp[q] = Cvt<kBf16>::two(hv[0], hv[1]);
-        gp[q] = Cvt<kBf16>::two(gv[0], gv[1]);
+        hp[q * 2] = Cvt<kBf16>::two(hv[0], hv[1]);
+        hp[q * 2 + 1] = Cvt<kBf16>::two(hv[2], hv[3]);
+        gp[q * 2] = Cvt<kBf16>::two(gv[0], gv[1]);
+        gp[q * 2 + 1] = Cvt<kBf16>::two(gv[2], gv[3]);
       }
       // the previous tile's second GEMMs must have finished reading sH / sG
       if (t > 0) mbar_wait(&ms.h_free, (t - 1) & 1);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {     // four 16-byte units = 32 bf16 columns
+      for (int u = 0; u < 4; ++u) {     // four 16-byte units = 32 16-bit columns
         const uint32_t o = sw128_offset(r, cbase + u * 8);
         *reinterpret_cast<uint4*>(sH + o) = make_uint4(hp[u * 4], hp[u * 4 + 1], hp[u * 4 + 2], hp[u * 4 + 3]);
         if (teacher) *reinterpret_cast<uint4*>(sG + o) = make_uint4(gp[u * 4], gp[u * 4 + 1], gp[u * 4 + 2], gp[u * 4 + 3]);
       }
       fence_async_smem();
+      publish(s ^ 1, nx0, nx1);
       __syncwarp();
       if (lane == 0) mbar_arrive(&ms.h_full);
+      epi_barrier();
     }
 
     // ---- dF (TMEM) * go -> grad_feat ----
@@ -667,6 +748,8 @@ size_t fecl_tc_workspace_bytes(int, int, int) { return 16 + sizeof(double) * 3 *
 namespace {
 
 // Power of two ~ B_global N tau / 8: |H| <= 2 (1 + gamma/e) r_max / (B N tau), so scaled entries are O(1).
+int focal_kind(const FeclScalars& sc) { return !sc.focal ? kNoFocal : sc.gamma == 2.f ? kFocalG2 : kFocalAny; }
+
 float pick_hscale(double inv_rows, float inv_tau) {
   const double x = 1.0 / (inv_rows * (double)inv_tau * 8.0);
   int e = 0;
@@ -709,11 +792,18 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   // >= 120 KB of dynamic smem also pins one CTA per SM, so the 512-column TMEM allocation never contends
   size_t smem = (size_t)3 * KC * kChunk128 + sizeof(SweepMisc);
   if (smem < 120 * 1024) smem = 120 * 1024;
-  static const int once = set_smem(fecl_tc_sweep_kernel<0, kBf16>) | set_smem(fecl_tc_sweep_kernel<1, kBf16>);
+  static const int once = set_smem(fecl_tc_sweep_kernel<0, kBf16, kNoFocal>) |
+                          set_smem(fecl_tc_sweep_kernel<1, kBf16, kNoFocal>) |
+                          set_smem(fecl_tc_sweep_kernel<1, kBf16, kFocalG2>) |
+                          set_smem(fecl_tc_sweep_kernel<1, kBf16, kFocalAny>);
   if (once) return once;
   dim3 grid(Npad / 128, B);
-  fecl_tc_sweep_kernel<0, kBf16><<<grid, kThreads, smem, st>>>(mapF, mapT, sp);
-  fecl_tc_sweep_kernel<1, kBf16><<<grid, kThreads, smem, st>>>(mapF, mapT, sp);
+  fecl_tc_sweep_kernel<0, kBf16, kNoFocal><<<grid, kThreads, smem, st>>>(mapF, mapT, sp);
+  switch (focal_kind(p.sc)) {
+    case kNoFocal: fecl_tc_sweep_kernel<1, kBf16, kNoFocal><<<grid, kThreads, smem, st>>>(mapF, mapT, sp); break;
+    case kFocalG2: fecl_tc_sweep_kernel<1, kBf16, kFocalG2><<<grid, kThreads, smem, st>>>(mapF, mapT, sp); break;
+    default: fecl_tc_sweep_kernel<1, kBf16, kFocalAny><<<grid, kThreads, smem, st>>>(mapF, mapT, sp); break;
+  }
   DYCON_CUDA(cudaGetLastError());
   count_launches(p.has_teacher ? 4 : 3);
   return DYCON_OK;
@@ -740,11 +830,16 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
   bp.cross_cnt = a.cross_cnt; bp.grad_out = a.grad_out; bp.grad_feat = a.grad_feat;
   size_t smem = (size_t)KC * kChunk128 + 4 * (size_t)KC * kChunk64 + 2 * kChunk128 + sizeof(BwdMisc);
   if (smem < 120 * 1024) smem = 120 * 1024;
-  static const int once = set_smem(fecl_tc_bwd_kernel<kBf16>);
+  static const int once = set_smem(fecl_tc_bwd_kernel<kBf16, kNoFocal>) | set_smem(fecl_tc_bwd_kernel<kBf16, kFocalG2>) |
+                          set_smem(fecl_tc_bwd_kernel<kBf16, kFocalAny>);
   if (once) return once;
   DYCON_REQUIRE(smem <= 227 * 1024, DYCON_ERR_UNSUPPORTED, "FeCL tensor-core bwd: %zu bytes of shared memory needed", smem);
   dim3 grid(Npad / 128, B);
-  fecl_tc_bwd_kernel<kBf16><<<grid, kThreads, smem, st>>>(mapA, mapF, mapT, bp);
+  switch (focal_kind(p.sc)) {
+    case kNoFocal: fecl_tc_bwd_kernel<kBf16, kNoFocal><<<grid, kThreads, smem, st>>>(mapA, mapF, mapT, bp); break;
+    case kFocalG2: fecl_tc_bwd_kernel<kBf16, kFocalG2><<<grid, kThreads, smem, st>>>(mapA, mapF, mapT, bp); break;
+    default: fecl_tc_bwd_kernel<kBf16, kFocalAny><<<grid, kThreads, smem, st>>>(mapA, mapF, mapT, bp); break;
+  }
   DYCON_CUDA(cudaGetLastError());
   count_launches(1);
   return DYCON_OK;
