@@ -37,8 +37,9 @@ struct FeclBwdArgs {
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-// Per-row statistics kept between forward and backward: 4 planes of B*N floats.
-enum { kStatM = 0, kStatN = 1, kStatA = 2, kStatKappa = 3, kNumStats = 4 };
+// Per-row statistics kept between forward and backward: planes of B*N floats (P = positive count,
+// only used by the tensor-core path).
+enum { kStatM = 0, kStatN = 1, kStatA = 2, kStatKappa = 3, kStatP = 4, kNumStats = 5 };
 
 // fp32 SIMT path (fecl_simt.cu)
 size_t fecl_simt_state_bytes(int B, int N, int D, int has_teacher);

@@ -17,6 +17,8 @@
 //                            UMMA K-major swizzle) -> dF_I += H F_J + Gc T_J with F_J / T_J read as
 //                            MN-major operands from the very tiles that produced S / CS.
 // Pipelines: smem ring (TMA -> MMA) and TMEM ring (MMA -> epilogue), all mbarrier based.
+#include <cstdlib>
+
 #include "fecl_internal.h"
 #include "tc_common.cuh"
 
@@ -123,6 +125,7 @@ pack16_kernel(const float* __restrict__ src, int64_t sb, int64_t sn, int64_t sd,
 // =================================================================================================
 struct SweepParams {
   int N, Npad, KC, has_teacher;
+  int splits;          // column splits: grid.y CTAs share a row block, each sweeps 1/splits of the column tiles
   FeclScalars sc;
   float c1;            // inv_tau * log2(e)
   float inv_rows;
@@ -131,7 +134,8 @@ struct SweepParams {
   float* hdr;
   const float* labels;
   const float* row_weight;
-  float* stat_m;
+  float* stat_m;       // zero-filled before the sweeps; split CTAs combine with atomicMax / atomicAdd (<= 2
+  float* stat_p;       // contributors per address, so the float sums are order-independent: a+b == b+a)
   float* stat_n;
   float* stat_a;
   float* stat_kappa;
@@ -221,7 +225,13 @@ __device__ __forceinline__ void body_cross(const float (&v)[32], const float* cy
   }
 }
 
-template <int kMode, bool kBf16, int kFocal>  // kMode 0: row max + kappa,  1: n / loss / A / cross
+// kMode 0: row max m_i and positive count P_i          (P0)
+// kMode 1: kappa_i and the negative sums n_i           (P1; needs every m)
+// kMode 2: row loss, A_i and the teacher cross term    (P2; needs every n)
+// Grid (row blocks, column splits, samples).  Three launches instead of one fused sweep: n_i needs all m_k
+// and d_ij needs the complete n_i, i.e. two grid-wide dependencies, and splitting the columns of a row
+// block over several CTAs (so that small batches still fill 148 SMs) adds a third.
+template <int kMode, bool kBf16, int kFocal>
 __global__ void __launch_bounds__(kThreads, 1)
 fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapT,
                      const SweepParams p) {
@@ -232,11 +242,13 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
   uint8_t* const sA = smem;
   uint8_t* const sB0 = smem + tile_bytes;
   SweepMisc& ms = *reinterpret_cast<SweepMisc*>(smem + 3 * tile_bytes);
-  const int b = blockIdx.y, i0 = blockIdx.x * kTM;
-  const int nt = p.Npad / 128;
-  const bool teacher_on = kMode == 1 && p.has_teacher;
+  const int b = blockIdx.z, i0 = blockIdx.x * kTM, split = blockIdx.y;
+  const int nt_all = p.Npad / 128;
+  const int jt0 = (int)((long long)split * nt_all / p.splits), jt1 = (int)((long long)(split + 1) * nt_all / p.splits);
+  const int nt = jt1 - jt0;
+  const bool teacher_on = kMode == 2 && p.has_teacher;
   const int per_j = teacher_on ? 2 : 1;
-  const int total = kMode == 0 ? nt : nt + nt * per_j;   // P1 tiles, then per column tile: S [, CS]
+  const int total = nt * per_j;                            // per column tile: S [, CS]
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
@@ -246,7 +258,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
     fence_mbar_init();
     prefetch_tmap(&mapF);
     if (teacher_on) prefetch_tmap(&mapT);
-    if (kMode == 0 && blockIdx.x == 0 && blockIdx.y == 0) p.hdr[0] = p.hscale;
+    if (kMode == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.hdr[0] = p.hscale;
   }
   if (warp == 1) tmem_alloc(&ms.tmem_slot, 512);
   tcgen05_before_sync();
@@ -258,18 +270,13 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    if (lane == 0 && nt > 0) {
       mbar_expect_tx(&ms.a_full, tile_bytes);
       for (int c = 0; c < KC; ++c) tma_load_2d(sA + c * kChunk128, &mapF, c * 64, b * p.Npad + i0, &ms.a_full);
       for (int t = 0; t < total; ++t) {
         const int s = t & 1;
-        int jt = t;
-        bool teacher = false;
-        if (kMode == 1 && t >= nt) {
-          const int u = t - nt;
-          jt = u / per_j;
-          teacher = (u % per_j) == 1;
-        }
+        const int jt = jt0 + t / per_j;
+        const bool teacher = teacher_on && (t % per_j) == 1;
         uint8_t* dst = sB0 + s * tile_bytes;
         mbar_wait(&ms.b_empty[s], ((t >> 1) & 1) ^ 1);
         mbar_expect_tx(&ms.b_full[s], tile_bytes);
@@ -279,7 +286,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
     }
   } else if (warp == 1) {
     // ================================ MMA issuer ==================================
-    if (lane == 0) {
+    if (lane == 0 && nt > 0) {
       const uint32_t idesc = umma_idesc_16(128, 128, false, false, kBf16);
       const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB0);
       mbar_wait(&ms.a_full, 0);
@@ -299,14 +306,16 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
         umma_commit(&ms.acc_full[a]);
       }
     }
-  } else {
+  } else if (nt > 0) {
     // ================================ epilogue (8 warps) ==========================
     const int et = threadIdx.x - 64;              // 0..255
     const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane, i = i0 + r;
     const bool row_ok = i < p.N;
-    const float* yb = p.labels + (size_t)b * p.N;
-    const float* mb = p.stat_m + (size_t)b * p.N;
+    const size_t off = (size_t)b * p.N;
+    const size_t g = off + (row_ok ? i : 0);
+    const float* yb = p.labels + off;
+    const float* mb = p.stat_m + off;
     const float qnan = __int_as_float(0x7fc00000);
     const float yi = row_ok ? __ldg(yb + i) : qnan;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
@@ -338,80 +347,68 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
       if (lane == 0) mbar_arrive(&ms.acc_empty[a]);
     };
 
-    publish(0, fetch(0));
+    float n_row = 0.f;
+    if (kMode == 1 && half == 0 && row_ok) {     // every split writes the same value (a split may own no tile)
+      // kappa_i = r_i c_i / (B N),  c_i = 1/(P_i - 1 + 1e-18)   (dycon_losses.py:192; P from the P0 launch)
+      const float rw = p.row_weight ? __ldg(p.row_weight + g) : 1.f;
+      p.stat_kappa[g] = rw / ((__ldg(p.stat_p + g) - 1.f) + kTiny) * p.inv_rows;
+    }
+    if (kMode == 2) n_row = __ldg(p.stat_n + g);
+
+    publish(0, fetch(jt0));
     epi_barrier();
+    float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
     int t = 0;
-    if (kMode == 0) {
-      float mx = 0.f, cnt = 0.f;    // the zeroed diagonal always takes part in the max (dycon_losses.py:178-180)
-      for (int jt = 0; jt < nt; ++jt, ++t) {
-        const int slot = jt & 1;
-        const float nxt = fetch(jt + 1 < nt ? jt + 1 : jt);
-        const int dloc = jt == (int)blockIdx.x ? r : -1;
-        consume(t, [&](const float (&v)[32], int cbase) {
-          body_rowmax(v, &ms.col[slot][0][cbase], yi, dloc - cbase, mx, cnt);
+    for (int q = 0; q < nt; ++q) {
+      const int jt = jt0 + q, slot = q & 1;
+      const float nxt = fetch(q + 1 < nt ? jt + 1 : jt);
+      const int dloc = jt == (int)blockIdx.x ? r : -1;
+      if (kMode == 0) {         // acc0 = max (the zeroed diagonal always takes part: >= 0), acc1 = count
+        consume(t++, [&](const float (&v)[32], int cbase) {
+          body_rowmax(v, &ms.col[slot][0][cbase], yi, dloc - cbase, acc0, acc1);
         });
-        publish(slot ^ 1, nxt);
-        epi_barrier();
-      }
-      if (half == 1) { ms.xch[0][r] = mx; ms.xch[1][r] = cnt; }
-      epi_barrier();
-      if (half == 0 && row_ok) {
-        const size_t g = (size_t)b * p.N + i;
-        const float m = fmaxf(mx, ms.xch[0][r]) * p.sc.inv_tau;
-        const float P = cnt + ms.xch[1][r];
-        const float rw = p.row_weight ? __ldg(p.row_weight + g) : 1.f;
-        p.stat_m[g] = m;
-        p.stat_kappa[g] = rw / ((P - 1.f) + kTiny) * p.inv_rows;
-      }
-    } else {
-      // ---- P1: n_i = sum_k neg_ik exp(l_ik - m_k)              (dycon_losses.py:183-184)
-      float nsum = 0.f;
-      for (int jt = 0; jt < nt; ++jt, ++t) {
-        const int slot = jt & 1;
-        const float nxt = fetch(jt + 1 < nt ? jt + 1 : 0);      // after the last P1 tile: tile 0 of P2
-        consume(t, [&](const float (&v)[32], int cbase) {
-          body_negsum(v, &ms.col[slot][0][cbase], &ms.col[slot][1][cbase], yi, p.c1, nsum);
+      } else if (kMode == 1) {  // acc0 = n_i partial                     (dycon_losses.py:183-184)
+        consume(t++, [&](const float (&v)[32], int cbase) {
+          body_negsum(v, &ms.col[slot][0][cbase], &ms.col[slot][1][cbase], yi, p.c1, acc0);
         });
-        publish(slot ^ 1, nxt);
-        if (jt + 1 == nt) ms.xch[half][r] = nsum;
-        epi_barrier();
-      }
-      const float n_row = ms.xch[0][r] + ms.xch[1][r];
-      // ---- P2: positives -> row loss and A_i; teacher tile -> cross sum / count   (:186-229)
-      float lsum = 0.f, asum = 0.f, csum = 0.f, ccnt = 0.f;
-      for (int jt = 0; jt < nt; ++jt) {
-        const int slot = (nt + jt) & 1;
-        const float nxt = fetch(jt + 1 < nt ? jt + 1 : jt);
-        const int dloc = jt == (int)blockIdx.x ? r : -1;
+      } else {                  // acc0 / acc1 = loss / A partials, acc2 / acc3 = cross sum / count (:186-229)
         consume(t++, [&](const float (&v)[32], int cbase) {
           body_pos<kFocal>(v, &ms.col[slot][0][cbase], &ms.col[slot][1][cbase], yi, dloc - cbase, p.c1, n_row,
-                           p.sc.gamma, lsum, asum);
+                           p.sc.gamma, acc0, acc1);
         });
         if (teacher_on) {
           consume(t++, [&](const float (&v)[32], int cbase) {
-            body_cross(v, &ms.col[slot][0][cbase], &ms.col[slot][1][cbase], yi, p.sc.cross_thresh, csum, ccnt);
+            body_cross(v, &ms.col[slot][0][cbase], &ms.col[slot][1][cbase], yi, p.sc.cross_thresh, acc2, acc3);
           });
         }
-        publish(slot ^ 1, nxt);
-        epi_barrier();
       }
-      if (half == 1) { ms.xch[0][r] = lsum; ms.xch[1][r] = asum; }
+      publish(slot ^ 1, nxt);
       epi_barrier();
-      if (half == 0 && row_ok) {
-        const size_t g = (size_t)b * p.N + i;
-        const float ls = -kLn2 * (lsum + ms.xch[0][r]), as = asum + ms.xch[1][r];
-        p.stat_n[g] = n_row;
-        p.stat_a[g] = as;
+    }
+    // ---- combine the two column halves of the CTA, then the column splits through global memory ----
+    if (half == 1) { ms.xch[0][r] = acc0; ms.xch[1][r] = acc1; }
+    epi_barrier();
+    if (half == 0 && row_ok) {
+      if (kMode == 0) {
+        const float m = fmaxf(acc0, ms.xch[0][r]) * p.sc.inv_tau;      // >= 0, so the int ordering is the float ordering
+        atomicMax(reinterpret_cast<int*>(p.stat_m + g), __float_as_int(m));
+        atomicAdd(p.stat_p + g, acc1 + ms.xch[1][r]);                   // integer-valued: exact in any order
+      } else if (kMode == 1) {
+        atomicAdd(p.stat_n + g, acc0 + ms.xch[0][r]);
+      } else {
+        const float ls = -kLn2 * (acc0 + ms.xch[0][r]);
+        atomicAdd(p.stat_a + g, acc1 + ms.xch[1][r]);
         red[0] = (double)(__ldg(p.stat_kappa + g) * ls);   // kappa_i = r_i c_i inv_rows
       }
-      if (row_ok) { red[1] = (double)(-kLn2 * csum); red[2] = (double)ccnt; }
     }
+    if (kMode == 2 && row_ok) { red[1] = (double)(-kLn2 * acc2); red[2] = (double)acc3; }
   }
 
-  // ---- block / grid reduction of {student, cross_sum, cross_cnt} (mode 1) ----
-  if (kMode == 1) {
+  // ---- block / grid reduction of {student, cross_sum, cross_cnt} (mode 2) ----
+  if (kMode == 2) {
     double total_[3];
-    const unsigned int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+    const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     if (grid_sum_last_block<3>(red, total_, p.ticket, p.partials, nblocks, bid, ms.scratch) && threadIdx.x == 0) {
       const double student = total_[0] / p.inv_rows_d;
       p.sums_out[0] = student;
@@ -433,6 +430,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
 // =================================================================================================
 struct BwdParams {
   int N, Npad, KC, D, has_teacher;
+  int splits;          // column splits; with > 1 the partial dF are summed with red.global.add onto zeros
   FeclScalars sc;
   float c1;
   const float* labels;
@@ -470,8 +468,10 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   uint8_t* sH = smem + a_bytes + 2 * stage_bytes;     // [128 i][64 j] bf16, K-major SW128
   uint8_t* sG = sH + kChunk128;
   BwdMisc& ms = *reinterpret_cast<BwdMisc*>(sG + kChunk128);
-  const int b = blockIdx.y, i0 = blockIdx.x * kTM;
-  const int nt = p.Npad / 64;
+  const int b = blockIdx.z, i0 = blockIdx.x * kTM, split = blockIdx.y;
+  const int nt_all = p.Npad / 64;
+  const int t0 = (int)((long long)split * nt_all / p.splits), t1 = (int)((long long)(split + 1) * nt_all / p.splits);
+  const int nt = t1 - t0;                       // this CTA's 64-column tiles: t0 .. t1-1
   const bool teacher = p.has_teacher != 0;
 
   if (threadIdx.x == 0) {
@@ -500,21 +500,21 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   const uint32_t tm_s = tmem, tm_cs = tmem + 128, tm_df = tmem + 256;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (lane == 0 && nt > 0) {
       mbar_expect_tx(&ms.a_full, a_bytes);
       for (int c = 0; c < KC; ++c) tma_load_2d(sA + c * kChunk128, &mapA, c * 64, b * p.Npad + i0, &ms.a_full);
       for (int t = 0; t < nt; ++t) {
-        const int s = t & 1;
+        const int s = t & 1, row = b * p.Npad + (t0 + t) * 64;
         mbar_wait(&ms.b_empty[s], ((t >> 1) & 1) ^ 1);
         mbar_expect_tx(&ms.b_full[s], teacher ? stage_bytes : j_bytes);
         for (int c = 0; c < KC; ++c) {
-          tma_load_2d(sStage[s] + c * kChunk64, &mapF, c * 64, b * p.Npad + t * 64, &ms.b_full[s]);
-          if (teacher) tma_load_2d(sStage[s] + j_bytes + c * kChunk64, &mapT, c * 64, b * p.Npad + t * 64, &ms.b_full[s]);
+          tma_load_2d(sStage[s] + c * kChunk64, &mapF, c * 64, row, &ms.b_full[s]);
+          if (teacher) tma_load_2d(sStage[s] + j_bytes + c * kChunk64, &mapT, c * 64, row, &ms.b_full[s]);
         }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && nt > 0) {
       const uint32_t idesc_s = umma_idesc_16(128, 64, false, false, kBf16);
       const uint32_t idesc_d = umma_idesc_16(128, Dpad, false, true, kBf16);   // B = F_J / T_J read MN-major
       auto issue_sc = [&](int t) {
@@ -561,7 +561,7 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       }
       umma_commit(&ms.df_full);
     }
-  } else {
+  } else if (nt > 0) {
     const int et = threadIdx.x - 64;
     const int quarter = warp & 3, half = (warp - 2) >> 2;
     const int r = quarter * 32 + lane, i = i0 + r;
@@ -594,12 +594,12 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       ms.col[slot][et >> 6][et & 63] = v0;
       if (et < 64) ms.col[slot][4][et] = v1;
     };
-    publish(0, fetch_one(0, et), et < 64 ? fetch_one(0, 256 + et) : 0.f);
+    publish(0, fetch_one(t0, et), et < 64 ? fetch_one(t0, 256 + et) : 0.f);
     epi_barrier();
 
     for (int t = 0; t < nt; ++t) {
-      const int s = t & 1, j0 = t * 64;
-      const int tn = t + 1 < nt ? t + 1 : t;
+      const int s = t & 1, j0 = (t0 + t) * 64;
+      const int tn = t0 + (t + 1 < nt ? t + 1 : t);
       const float nx0 = fetch_one(tn, et), nx1 = et < 64 ? fetch_one(tn, 256 + et) : 0.f;
       mbar_wait(&ms.sc_full[s], (t >> 1) & 1);
       tcgen05_after_sync();
@@ -678,12 +678,21 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         float* dst = p.grad_feat + (off + i) * p.D + c0;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
+          const float o0 = go * v[q * 4], o1 = go * v[q * 4 + 1], o2 = go * v[q * 4 + 2], o3 = go * v[q * 4 + 3];
           if (c0 + q * 4 + 3 < p.D) {
-            *reinterpret_cast<float4*>(dst + q * 4) =
-                make_float4(go * v[q * 4], go * v[q * 4 + 1], go * v[q * 4 + 2], go * v[q * 4 + 3]);
+            if (p.splits == 1) {
+              *reinterpret_cast<float4*>(dst + q * 4) = make_float4(o0, o1, o2, o3);
+            } else {   // two partial sums onto a zero-filled buffer: a + b == b + a, still bit-reproducible
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + q * 4), "f"(o0), "f"(o1),
+                           "f"(o2), "f"(o3) : "memory");
+            }
           } else {
-            for (int k = 0; k < 4; ++k)
-              if (c0 + q * 4 + k < p.D) dst[q * 4 + k] = go * v[q * 4 + k];
+            const float o[4] = {o0, o1, o2, o3};
+            for (int k = 0; k < 4; ++k) {
+              if (c0 + q * 4 + k < p.D) {
+                if (p.splits == 1) dst[q * 4 + k] = o[k]; else atomicAdd(dst + q * 4 + k, o[k]);
+              }
+            }
           }
         }
       }
@@ -722,8 +731,8 @@ TcState carve(void* state, int B, int N, int D, int has_teacher) {
 int check_tc_shape(int B, int N, int D) {
   DYCON_REQUIRE(D % 4 == 0 && D <= 256, DYCON_ERR_UNSUPPORTED,
                 "FeCL bf16: D=%d must be a multiple of 4 and <= 256 (the reference projection head has D=256)", D);
-  DYCON_REQUIRE((long long)(npad_of(N) / 128) * B <= kMaxPartials && B <= 65535, DYCON_ERR_UNSUPPORTED,
-                "FeCL bf16: %d row blocks x B=%d exceeds %d CTAs", npad_of(N) / 128, B, kMaxPartials);
+  DYCON_REQUIRE((long long)(npad_of(N) / 128) * B * 2 <= kMaxPartials && B <= 65535, DYCON_ERR_UNSUPPORTED,
+                "FeCL tensor-core path: %d row blocks x B=%d exceeds %d CTAs", npad_of(N) / 128, B, kMaxPartials / 2);
   return DYCON_OK;
 }
 
@@ -748,6 +757,17 @@ size_t fecl_tc_workspace_bytes(int, int, int) { return 16 + sizeof(double) * 3 *
 namespace {
 
 // Power of two ~ B_global N tau / 8: |H| <= 2 (1 + gamma/e) r_max / (B N tau), so scaled entries are O(1).
+// Column splits per row block: 2 when that still fits one wave of SMs (small batches), else 1.  Never more
+// than 2, so every split reduction has at most two float contributors and stays order-independent.
+int pick_splits(int row_blocks, int B) {
+  static const int forced = [] {
+    const char* e = getenv("DYCON_FECL_SPLITS");
+    return e ? atoi(e) : 0;
+  }();
+  if (forced == 1 || forced == 2) return forced;
+  return (long long)row_blocks * B * 2 <= sm_count() ? 2 : 1;
+}
+
 int focal_kind(const FeclScalars& sc) { return !sc.focal ? kNoFocal : sc.gamma == 2.f ? kFocalG2 : kFocalAny; }
 
 float pick_hscale(double inv_rows, float inv_tau) {
@@ -779,6 +799,7 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   ReduceWorkspace ws = carve_reduce_workspace(a.workspace);
   SweepParams sp;
   sp.N = N; sp.Npad = Npad; sp.KC = KC; sp.has_teacher = p.has_teacher;
+  sp.splits = pick_splits(Npad / 128, B);
   sp.sc = p.sc;
   sp.c1 = p.sc.inv_tau * kLog2e;
   sp.inv_rows = (float)p.inv_rows;
@@ -788,24 +809,28 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   sp.labels = a.labels; sp.row_weight = a.row_weight;
   sp.stat_m = s.stats + kStatM * plane; sp.stat_n = s.stats + kStatN * plane;
   sp.stat_a = s.stats + kStatA * plane; sp.stat_kappa = s.stats + kStatKappa * plane;
+  sp.stat_p = s.stats + kStatP * plane;
   sp.ticket = ws.ticket; sp.partials = ws.partials; sp.sums_out = a.sums_out; sp.loss_out = a.loss_out;
   // >= 120 KB of dynamic smem also pins one CTA per SM, so the 512-column TMEM allocation never contends
   size_t smem = (size_t)3 * KC * kChunk128 + sizeof(SweepMisc);
   if (smem < 120 * 1024) smem = 120 * 1024;
   static const int once = set_smem(fecl_tc_sweep_kernel<0, kBf16, kNoFocal>) |
                           set_smem(fecl_tc_sweep_kernel<1, kBf16, kNoFocal>) |
-                          set_smem(fecl_tc_sweep_kernel<1, kBf16, kFocalG2>) |
-                          set_smem(fecl_tc_sweep_kernel<1, kBf16, kFocalAny>);
+                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kNoFocal>) |
+                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2>) |
+                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny>);
   if (once) return once;
-  dim3 grid(Npad / 128, B);
+  DYCON_CUDA(cudaMemsetAsync(s.stats, 0, (size_t)kNumStats * plane * sizeof(float), st));
+  dim3 grid(Npad / 128, sp.splits, B);
   fecl_tc_sweep_kernel<0, kBf16, kNoFocal><<<grid, kThreads, smem, st>>>(mapF, mapT, sp);
+  fecl_tc_sweep_kernel<1, kBf16, kNoFocal><<<grid, kThreads, smem, st>>>(mapF, mapT, sp);
   switch (focal_kind(p.sc)) {
-    case kNoFocal: fecl_tc_sweep_kernel<1, kBf16, kNoFocal><<<grid, kThreads, smem, st>>>(mapF, mapT, sp); break;
-    case kFocalG2: fecl_tc_sweep_kernel<1, kBf16, kFocalG2><<<grid, kThreads, smem, st>>>(mapF, mapT, sp); break;
-    default: fecl_tc_sweep_kernel<1, kBf16, kFocalAny><<<grid, kThreads, smem, st>>>(mapF, mapT, sp); break;
+    case kNoFocal: fecl_tc_sweep_kernel<2, kBf16, kNoFocal><<<grid, kThreads, smem, st>>>(mapF, mapT, sp); break;
+    case kFocalG2: fecl_tc_sweep_kernel<2, kBf16, kFocalG2><<<grid, kThreads, smem, st>>>(mapF, mapT, sp); break;
+    default: fecl_tc_sweep_kernel<2, kBf16, kFocalAny><<<grid, kThreads, smem, st>>>(mapF, mapT, sp); break;
   }
   DYCON_CUDA(cudaGetLastError());
-  count_launches(p.has_teacher ? 4 : 3);
+  count_launches(p.has_teacher ? 5 : 4);
   return DYCON_OK;
 }
 
@@ -821,6 +846,7 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
   if (int rc = make_tmap_16_2d(&mapT, p.has_teacher ? s.T : s.F, (uint64_t)B * Npad, Dpad, 64, kBf16)) return rc;
   BwdParams bp;
   bp.N = N; bp.Npad = Npad; bp.KC = KC; bp.D = D; bp.has_teacher = p.has_teacher;
+  bp.splits = pick_splits(Npad / 128, B);
   bp.sc = p.sc;
   bp.c1 = p.sc.inv_tau * kLog2e;
   bp.labels = a.labels;
@@ -834,7 +860,8 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
                           set_smem(fecl_tc_bwd_kernel<kBf16, kFocalAny>);
   if (once) return once;
   DYCON_REQUIRE(smem <= 227 * 1024, DYCON_ERR_UNSUPPORTED, "FeCL tensor-core bwd: %zu bytes of shared memory needed", smem);
-  dim3 grid(Npad / 128, B);
+  if (bp.splits > 1) DYCON_CUDA(cudaMemsetAsync(a.grad_feat, 0, (size_t)B * N * D * sizeof(float), st));
+  dim3 grid(Npad / 128, bp.splits, B);
   switch (focal_kind(p.sc)) {
     case kNoFocal: fecl_tc_bwd_kernel<kBf16, kNoFocal><<<grid, kThreads, smem, st>>>(mapA, mapF, mapT, bp); break;
     case kFocalG2: fecl_tc_bwd_kernel<kBf16, kFocalG2><<<grid, kThreads, smem, st>>>(mapA, mapF, mapT, bp); break;
