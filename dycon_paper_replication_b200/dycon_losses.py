@@ -29,7 +29,7 @@ import os
 import torch
 import torch.nn as nn
 
-from . import _lib
+from . import _lib, sharded
 
 __all__ = ["UnCLoss", "FeCLoss", "adaptive_beta", "sigmoid_rampup", "gambling_softmax",
            "update_ema_variables"]
@@ -160,8 +160,7 @@ class _UnCLFunction(torch.autograd.Function):
                        "dycon_uncl_fwd")
             _tock("uncl_fwd", t0)
             if process_group is not None:
-                torch.distributed.all_reduce(total, group=process_group)
-                loss = (total[0] * inv_count).to(torch.float32)
+                loss = sharded.uncl_loss_from_sum(sharded.all_reduce_sums(total, process_group), inv_count)
         ctx.dims = (B, Cn, V, float(beta), inv_count)
         ctx.shape = s_logits.shape
         if Cn == 2:
@@ -249,9 +248,8 @@ class _FeCLFunction(torch.autograd.Function):
                        "dycon_fecl_fwd")
             _tock("fecl_fwd", t0)
             if process_group is not None:
-                torch.distributed.all_reduce(sums, group=process_group)
-                cross = sums[1] / (sums[2] + 1e-18) if has_teacher else 0.0
-                loss = (sums[0] * inv_rows + lambda_cross * cross).to(torch.float32)
+                loss = sharded.fecl_loss_from_sums(sharded.all_reduce_sums(sums, process_group), inv_rows,
+                                                   lambda_cross, has_teacher)
         ctx.save_for_backward(state, labels, sums)
         ctx.cfg = (B, N, D, has_teacher, inv_tau, gamma, int(use_focal), row_weight is not None, cross_thresh,
                    lambda_cross, precision)
