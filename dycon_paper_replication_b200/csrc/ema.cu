@@ -3,8 +3,8 @@
 // The reference walks the parameter list in Python and launches mul_ + add_ per tensor
 // (96 launches for the 48 tensors of unet_3D, most of them a few hundred bytes).  Here the
 // pointer table travels in the kernel's parameter space (no host->device copy, capturable in a
-// CUDA graph) and one launch covers every tensor: a block owns a 4096-element chunk of one
-// tensor, found by binary search over the per-tensor block offsets.  HBM-bound: 12 B/param.
+// CUDA graph) and one launch covers every tensor: the tensors are cut into 1024-element
+// chunks, a block owns a contiguous range of chunks and finds its first tensor by binary search.  HBM-bound: 12 B/param.
 //
 // Rounding order matches ema.mul_(alpha).add_(p, alpha=1-alpha):  t = rn(ema*alpha), then
 // ema = fma(1-alpha, p, t) (ATen's CUDA add-with-alpha functor contracts a + alpha*b to one FMA).
@@ -14,51 +14,79 @@ namespace dycon {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kChunk = 4096;        // elements per block: 256 threads x 4 float4
+constexpr int kChunk = 1024;        // elements per chunk: 256 threads x one float4
 constexpr int kMaxTensors = 320;    // per launch; 320*(8+8+8+4) B = 8960 B of kernel parameters
 
 struct EmaTable {
   float* ema[kMaxTensors];
   const float* param[kMaxTensors];
   long long numel[kMaxTensors];
-  int block_start[kMaxTensors + 1];
+  int chunk_start[kMaxTensors + 1];
   int n;
 };
 
+__device__ __forceinline__ float ema_one(float e, float p, float alpha, float oma) {
+  return fmaf(oma, p, __fmul_rn(e, alpha));
+}
+
+// Persistent: every block owns an equal, contiguous range of chunks (one resident wave, no tail wave),
+// and keeps two chunks (4 x 16 B per thread) in flight.
 __global__ void __launch_bounds__(kThreads)
-ema_multi_kernel(const __grid_constant__ EmaTable tab, float alpha, float oma) {
-  // block -> tensor: largest k with block_start[k] <= blockIdx.x
-  int lo = 0, hi = tab.n;
-  while (hi - lo > 1) {
-    const int mid = (lo + hi) >> 1;
-    if (tab.block_start[mid] <= (int)blockIdx.x) lo = mid; else hi = mid;
+ema_multi_kernel(const __grid_constant__ EmaTable tab, float alpha, float oma, int total_chunks) {
+  const int per = total_chunks / (int)gridDim.x, rem = total_chunks % (int)gridDim.x;
+  const int bx = (int)blockIdx.x;
+  const int c_begin = bx * per + (bx < rem ? bx : rem), c_end = c_begin + per + (bx < rem ? 1 : 0);
+  if (c_begin >= c_end) return;
+  int k = 0;   // tensor of chunk c_begin: largest k with chunk_start[k] <= c_begin
+  {
+    int lo = 0, hi = tab.n;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (tab.chunk_start[mid] <= c_begin) lo = mid; else hi = mid;
+    }
+    k = lo;
   }
-  float* __restrict__ e = tab.ema[lo];
-  const float* __restrict__ p = tab.param[lo];
-  const long long n = tab.numel[lo];
-  const long long base = (long long)(blockIdx.x - tab.block_start[lo]) * kChunk;
-  const long long end = base + kChunk < n ? base + kChunk : n;
-  const bool vec = ((reinterpret_cast<uintptr_t>(e) | reinterpret_cast<uintptr_t>(p)) & 15) == 0;
-  if (vec && end - base == kChunk) {
-    float4 ev[4], pv[4];
+  for (int c = c_begin; c < c_end; c += 2) {
+    float* e[2];
+    const float* p[2];
+    long long left[2];
+    bool vec[2];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long long i = base + (long long)(k * kThreads + threadIdx.x) * 4;
-      ev[k] = *reinterpret_cast<const float4*>(e + i);
-      pv[k] = __ldcs(reinterpret_cast<const float4*>(p + i));
+    for (int u = 0; u < 2; ++u) {
+      const int cu = c + u;
+      if (cu < c_end) {
+        while (tab.chunk_start[k + 1] <= cu) ++k;
+        const long long base = (long long)(cu - tab.chunk_start[k]) * kChunk;
+        e[u] = tab.ema[k] + base;
+        p[u] = tab.param[k] + base;
+        left[u] = tab.numel[k] - base;
+        vec[u] = left[u] >= kChunk && ((reinterpret_cast<uintptr_t>(e[u]) | reinterpret_cast<uintptr_t>(p[u])) & 15) == 0;
+      } else {
+        e[u] = nullptr; p[u] = nullptr; left[u] = 0; vec[u] = false;
+      }
+    }
+    float4 ev[2], pv[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      if (vec[u]) {
+        ev[u] = *reinterpret_cast<const float4*>(e[u] + threadIdx.x * 4);
+        pv[u] = __ldcs(reinterpret_cast<const float4*>(p[u] + threadIdx.x * 4));
+      }
     }
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const long long i = base + (long long)(k * kThreads + threadIdx.x) * 4;
-      float4 o;
-      o.x = fmaf(oma, pv[k].x, __fmul_rn(ev[k].x, alpha));
-      o.y = fmaf(oma, pv[k].y, __fmul_rn(ev[k].y, alpha));
-      o.z = fmaf(oma, pv[k].z, __fmul_rn(ev[k].z, alpha));
-      o.w = fmaf(oma, pv[k].w, __fmul_rn(ev[k].w, alpha));
-      *reinterpret_cast<float4*>(e + i) = o;
+    for (int u = 0; u < 2; ++u) {
+      if (vec[u]) {
+        float4 o;
+        o.x = ema_one(ev[u].x, pv[u].x, alpha, oma);
+        o.y = ema_one(ev[u].y, pv[u].y, alpha, oma);
+        o.z = ema_one(ev[u].z, pv[u].z, alpha, oma);
+        o.w = ema_one(ev[u].w, pv[u].w, alpha, oma);
+        *reinterpret_cast<float4*>(e[u] + threadIdx.x * 4) = o;
+      } else {
+        const long long n = left[u] < kChunk ? left[u] : kChunk;
+        for (long long i = threadIdx.x; i < n; i += kThreads) e[u][i] = ema_one(e[u][i], p[u][i], alpha, oma);
+      }
     }
-  } else {
-    for (long long i = base + threadIdx.x; i < end; i += kThreads) e[i] = fmaf(oma, p[i], __fmul_rn(e[i], alpha));
   }
 }
 
@@ -82,7 +110,7 @@ extern "C" int dycon_ema_multi(float* const* ema_ptrs, const float* const* param
   while (k < n_tensors) {
     EmaTable tab;
     tab.n = 0;
-    long long blocks = 0;
+    long long blocks = 0;   // chunks
     while (k < n_tensors && tab.n < kMaxTensors) {
       const long long nb = (numels[k] + kChunk - 1) / kChunk;
       if (nb == 0) { ++k; continue; }
@@ -90,7 +118,7 @@ extern "C" int dycon_ema_multi(float* const* ema_ptrs, const float* const* param
       tab.ema[tab.n] = ema_ptrs[k];
       tab.param[tab.n] = param_ptrs[k];
       tab.numel[tab.n] = numels[k];
-      tab.block_start[tab.n] = (int)blocks;
+      tab.chunk_start[tab.n] = (int)blocks;
       blocks += nb;
       ++tab.n;
       ++k;
@@ -99,8 +127,16 @@ extern "C" int dycon_ema_multi(float* const* ema_ptrs, const float* const* param
       DYCON_REQUIRE(k >= n_tensors, DYCON_ERR_UNSUPPORTED, "EMA: tensor %d too large for one launch", k);
       break;
     }
-    tab.block_start[tab.n] = (int)blocks;
-    ema_multi_kernel<<<(unsigned)blocks, kThreads, 0, st>>>(tab, alpha, one_minus_alpha);
+    tab.chunk_start[tab.n] = (int)blocks;
+    // one resident wave (occupancy-derived blocks per SM), or fewer blocks when the work is small
+    static const int per_sm = [] {
+      int n = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, ema_multi_kernel, kThreads, 0) != cudaSuccess || n < 1) n = 4;
+      return n;
+    }();
+    long long grid = (long long)sm_count() * per_sm;
+    if (grid > blocks) grid = blocks;
+    ema_multi_kernel<<<(unsigned)grid, kThreads, 0, st>>>(tab, alpha, one_minus_alpha, (int)blocks);
     DYCON_CUDA(cudaGetLastError());
     count_launches(1);
   }

@@ -57,17 +57,18 @@ int dycon_fecl_fwd(const float* feat, int64_t f_sb, int64_t f_sn, int64_t f_sd, 
 int dycon_fecl_bwd(const void* state, size_t state_bytes, const float* labels, int B, int N, int D, int has_teacher,
                    float inv_tau, float gamma, int use_focal, int has_row_weight, float cross_thresh,
                    float lambda_cross, int precision, const double* cross_cnt, const float* grad_out,
-                   float* grad_feat, dycon_stream_t stream) {
+                   float* grad_feat, int64_t g_sb, int64_t g_sn, int64_t g_sd, dycon_stream_t stream) {
   if (int rc = check_shape(B, N, D, precision)) return rc;
   DYCON_REQUIRE(state && labels && grad_out && grad_feat, DYCON_ERR_ARG, "FeCL bwd: NULL state/labels/grad_out/grad_feat");
   DYCON_REQUIRE(!has_teacher || cross_cnt, DYCON_ERR_ARG, "FeCL bwd: the teacher term needs cross_cnt");
-  DYCON_REQUIRE(aligned(state, 128) && aligned(grad_feat, 16) && aligned(cross_cnt, 8), DYCON_ERR_ARG,
+  DYCON_REQUIRE(aligned(state, 128) && aligned(grad_feat, 4) && aligned(cross_cnt, 8), DYCON_ERR_ARG,
                 "FeCL bwd: misaligned pointer");
+  DYCON_REQUIRE(g_sn > 0 && g_sd > 0 && g_sb >= 0, DYCON_ERR_ARG, "FeCL bwd: non-positive grad_feat strides");
   DYCON_REQUIRE(state_bytes >= dycon_fecl_state_bytes(B, N, D, has_teacher, precision), DYCON_ERR_WORKSPACE,
                 "FeCL bwd: state %zu < %zu bytes", state_bytes, dycon_fecl_state_bytes(B, N, D, has_teacher, precision));
   FeclProblem p{B, N, D, has_teacher ? 1 : 0,
                 FeclScalars{inv_tau, gamma, cross_thresh, lambda_cross, (use_focal && !has_row_weight) ? 1 : 0}, 0.0, precision};
-  FeclBwdArgs a{state, labels, cross_cnt, grad_out, grad_feat};
+  FeclBwdArgs a{state, labels, cross_cnt, grad_out, grad_feat, g_sb, g_sn, g_sd};
   return precision != DYCON_FECL_FP32 ? fecl_tc_bwd(p, a, as_stream(stream)) : fecl_simt_bwd(p, a, as_stream(stream));
 }
 

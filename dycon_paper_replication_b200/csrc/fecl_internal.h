@@ -33,6 +33,7 @@ struct FeclBwdArgs {
   const double* cross_cnt;
   const float* grad_out;
   float* grad_feat;
+  int64_t g_sb, g_sn, g_sd;   // element strides of grad_feat
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

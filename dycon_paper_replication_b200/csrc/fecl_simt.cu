@@ -278,7 +278,8 @@ fecl_simt_bwd_kernel(const float* __restrict__ F, const float* __restrict__ T, c
                      int N, int D, FeclScalars sc, const float* __restrict__ stat_m,
                      const float* __restrict__ stat_n, const float* __restrict__ stat_a,
                      const float* __restrict__ stat_kappa, const double* __restrict__ cross_cnt,
-                     const float* __restrict__ grad_out, float* __restrict__ grad_feat) {
+                     const float* __restrict__ grad_out, float* __restrict__ grad_feat, int64_t g_sb, int64_t g_sn,
+                     int64_t g_sd) {
   __shared__ TileSmem sm;
   __shared__ float hT[BN][BM + PAD];  // hT[j][i]
   const int b = blockIdx.y, i0 = blockIdx.x * BM;
@@ -384,8 +385,13 @@ fecl_simt_bwd_kernel(const float* __restrict__ F, const float* __restrict__ T, c
     for (int g = 0; g < kGroups; ++g) {
       const int d = g * 64 + tx * 4;
       if (d < D) {
-        *reinterpret_cast<float4*>(grad_feat + (off + i) * D + d) =
-            make_float4(go * dF[r][g][0], go * dF[r][g][1], go * dF[r][g][2], go * dF[r][g][3]);
+        float* dst = grad_feat + (int64_t)b * g_sb + (int64_t)i * g_sn + (int64_t)d * g_sd;
+        if (g_sd == 1 && ((g_sb | g_sn) & 3) == 0) {
+          *reinterpret_cast<float4*>(dst) = make_float4(go * dF[r][g][0], go * dF[r][g][1], go * dF[r][g][2], go * dF[r][g][3]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) dst[(int64_t)c * g_sd] = go * dF[r][g][c];
+        }
       }
     }
   }
@@ -451,7 +457,7 @@ int fecl_simt_bwd(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
   fecl_simt_bwd_kernel<G><<<grid, kThreads, 0, st>>>(s.F, s.T, a.labels, N, D, p.sc, s.stats + kStatM * plane,   \
                                                      s.stats + kStatN * plane, s.stats + kStatA * plane,         \
                                                      s.stats + kStatKappa * plane, a.cross_cnt, a.grad_out,      \
-                                                     a.grad_feat)
+                                                     a.grad_feat, a.g_sb, a.g_sn, a.g_sd)
   if (D <= 64) DYCON_LAUNCH_BWD(1);
   else if (D <= 128) DYCON_LAUNCH_BWD(2);
   else DYCON_LAUNCH_BWD(4);

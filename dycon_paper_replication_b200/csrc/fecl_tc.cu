@@ -91,30 +91,59 @@ template <> struct Cvt<false> {
   }
 };
 
+// One launch packs the student and (if present) the teacher: fp32 (B,N,D) with element strides ->
+// 16-bit [B][Npad][Dpad], zero padded; the CTAs of the first column tile also zero the per-row
+// statistics (so no memset node is needed).  A CTA moves a 64 x 64 tile through shared memory: the
+// caller's layout has n contiguous (strides (D*N, 1, N)), the kernel layout has d contiguous.
+struct PackParams {
+  const float* src[2];
+  int64_t sb[2], sn[2], sd[2];
+  void* dst[2];
+  float* stats;        // kNumStats planes of B*N floats, zero-filled here
+  int B, N, D, Npad, Dpad;
+};
+
 template <bool kBf16>
 __global__ void __launch_bounds__(256)
-pack16_kernel(const float* __restrict__ src, int64_t sb, int64_t sn, int64_t sd, int N, int D, int Npad, int Dpad,
-              typename Cvt<kBf16>::type* __restrict__ dst) {
-  __shared__ float tile[32][33];
-  const int b = blockIdx.z, n0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const float* s = src + (int64_t)b * sb;
-  if (sn <= sd) {
-    for (int k = ty; k < 32; k += 8) {
+pack16_kernel(const PackParams p) {
+  using T16 = typename Cvt<kBf16>::type;
+  __shared__ float tile[64][65];
+  const int which = blockIdx.z / p.B, b = blockIdx.z - which * p.B;
+  const int n0 = blockIdx.x * 64, d0 = blockIdx.y * 64;
+  const int tid = threadIdx.x;
+  // (ternaries, not p.x[which]: a dynamic index would copy the parameter arrays to local memory)
+  const float* s = (which ? p.src[1] : p.src[0]) + (int64_t)b * (which ? p.sb[1] : p.sb[0]);
+  const int64_t sn = which ? p.sn[1] : p.sn[0], sd = which ? p.sd[1] : p.sd[0];
+  T16* dst = reinterpret_cast<T16*>(which ? p.dst[1] : p.dst[0]);
+  if (which == 0 && blockIdx.y == 0) {
+    for (int q = tid; q < kNumStats * 64; q += 256) {
+      const int n = n0 + (q & 63);
+      if (n < p.N) p.stats[(size_t)(q >> 6) * p.B * p.N + (size_t)b * p.N + n] = 0.f;
+    }
+  }
+  if (sn == 1) {   // lanes along n for the read, along d for the write
+    const int tx = tid & 63, ty = tid >> 6;
+#pragma unroll 4
+    for (int k = ty; k < 64; k += 4) {
       const int n = n0 + tx, d = d0 + k;
-      tile[k][tx] = (n < N && d < D) ? s[(int64_t)n * sn + (int64_t)d * sd] : 0.f;
+      tile[k][tx] = (n < p.N && d < p.D) ? __ldg(s + n + (int64_t)d * sd) : 0.f;
     }
     __syncthreads();
-    for (int k = ty; k < 32; k += 8) {
-      const int n = n0 + k, d = d0 + tx;
-      if (n < Npad && d < Dpad) dst[((size_t)b * Npad + n) * Dpad + d] = Cvt<kBf16>::one(tile[tx][k]);
+    const int kx = tid & 31, ry = tid >> 5;
+#pragma unroll 4
+    for (int r = ry; r < 64; r += 8) {
+      const int n = n0 + r;
+      if (n < p.Npad)
+        *reinterpret_cast<uint32_t*>(dst + ((size_t)b * p.Npad + n) * p.Dpad + d0 + 2 * kx) =
+            Cvt<kBf16>::two(tile[2 * kx][r], tile[2 * kx + 1][r]);
     }
-  } else {
-    for (int k = ty; k < 32; k += 8) {
-      const int n = n0 + k, d = d0 + tx;
-      if (n < Npad && d < Dpad) {
-        const float v = (n < N && d < D) ? s[(int64_t)n * sn + (int64_t)d * sd] : 0.f;
-        dst[((size_t)b * Npad + n) * Dpad + d] = Cvt<kBf16>::one(v);
+  } else {         // any other layout (d contiguous or generic): lanes along d for both
+    const int tx = tid & 63, ty = tid >> 6;
+    for (int r = ty; r < 64; r += 4) {
+      const int n = n0 + r, d = d0 + tx;
+      if (n < p.Npad) {
+        const float v = (n < p.N && d < p.D) ? __ldg(s + (int64_t)n * sn + (int64_t)d * sd) : 0.f;
+        dst[((size_t)b * p.Npad + n) * p.Dpad + d] = Cvt<kBf16>::one(v);
       }
     }
   }
@@ -442,6 +471,7 @@ struct BwdParams {
   const double* cross_cnt;
   const float* grad_out;
   float* grad_feat;
+  int64_t g_sb, g_sn, g_sd;
 };
 
 struct BwdMisc {
@@ -675,23 +705,34 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       tmem_ld32(tm_df + lane_base + c0, v);
       tmem_ld_wait();
       if (row_ok) {
-        float* dst = p.grad_feat + (off + i) * p.D + c0;
+        float* dst = p.grad_feat + (int64_t)b * p.g_sb + (int64_t)i * p.g_sn + (int64_t)c0 * p.g_sd;
+        if (p.g_sd == 1 && ((p.g_sn | p.g_sb) & 3) == 0) {       // rows contiguous: 16-byte stores
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float o0 = go * v[q * 4], o1 = go * v[q * 4 + 1], o2 = go * v[q * 4 + 2], o3 = go * v[q * 4 + 3];
-          if (c0 + q * 4 + 3 < p.D) {
-            if (p.splits == 1) {
-              *reinterpret_cast<float4*>(dst + q * 4) = make_float4(o0, o1, o2, o3);
-            } else {   // two partial sums onto a zero-filled buffer: a + b == b + a, still bit-reproducible
-              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + q * 4), "f"(o0), "f"(o1),
-                           "f"(o2), "f"(o3) : "memory");
-            }
-          } else {
-            const float o[4] = {o0, o1, o2, o3};
-            for (int k = 0; k < 4; ++k) {
-              if (c0 + q * 4 + k < p.D) {
-                if (p.splits == 1) dst[q * 4 + k] = o[k]; else atomicAdd(dst + q * 4 + k, o[k]);
+          for (int q = 0; q < 8; ++q) {
+            const float o0 = go * v[q * 4], o1 = go * v[q * 4 + 1], o2 = go * v[q * 4 + 2], o3 = go * v[q * 4 + 3];
+            if (c0 + q * 4 + 3 < p.D) {
+              if (p.splits == 1) {
+                *reinterpret_cast<float4*>(dst + q * 4) = make_float4(o0, o1, o2, o3);
+              } else {   // two partial sums onto a zero-filled buffer: a + b == b + a, still bit-reproducible
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + q * 4), "f"(o0), "f"(o1),
+                             "f"(o2), "f"(o3) : "memory");
               }
+            } else {
+              const float o[4] = {o0, o1, o2, o3};
+              for (int k = 0; k < 4; ++k) {
+                if (c0 + q * 4 + k < p.D) {
+                  if (p.splits == 1) dst[q * 4 + k] = o[k]; else atomicAdd(dst + q * 4 + k, o[k]);
+                }
+              }
+            }
+          }
+        } else {   // columns contiguous (the caller's (D*N, 1, N) layout): a warp stores 32 consecutive rows
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            if (c0 + c < p.D) {
+              float* q = dst + (int64_t)c * p.g_sd;
+              if (p.splits == 1) *q = go * v[c];
+              else asm volatile("red.global.add.f32 [%0], %1;" ::"l"(q), "f"(go * v[c]) : "memory");
             }
           }
         }
@@ -787,12 +828,12 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   const int Npad = npad_of(N), Dpad = dpad_of(D), KC = Dpad / 64;
   TcState s = carve(a.state, B, N, D, p.has_teacher);
   const size_t plane = (size_t)B * N;
-  dim3 pgrid(Npad / 32, Dpad / 32, B);
-  pack16_kernel<kBf16><<<pgrid, 256, 0, st>>>(a.feat, a.f_sb, a.f_sn, a.f_sd, N, D, Npad, Dpad,
-                                               reinterpret_cast<T16*>(s.F));
-  if (p.has_teacher)
-    pack16_kernel<kBf16><<<pgrid, 256, 0, st>>>(a.teacher, a.t_sb, a.t_sn, a.t_sd, N, D, Npad, Dpad,
-                                                 reinterpret_cast<T16*>(s.T));
+  PackParams pk;
+  pk.src[0] = a.feat; pk.sb[0] = a.f_sb; pk.sn[0] = a.f_sn; pk.sd[0] = a.f_sd; pk.dst[0] = s.F;
+  pk.src[1] = a.teacher; pk.sb[1] = a.t_sb; pk.sn[1] = a.t_sn; pk.sd[1] = a.t_sd; pk.dst[1] = s.T;
+  pk.stats = s.stats; pk.B = B; pk.N = N; pk.D = D; pk.Npad = Npad; pk.Dpad = Dpad;
+  dim3 pgrid(Npad / 64, Dpad / 64, B * (p.has_teacher ? 2 : 1));
+  pack16_kernel<kBf16><<<pgrid, 256, 0, st>>>(pk);
   CUtensorMap mapF, mapT;
   if (int rc = make_tmap_16_2d(&mapF, s.F, (uint64_t)B * Npad, Dpad, 128, kBf16)) return rc;
   if (int rc = make_tmap_16_2d(&mapT, p.has_teacher ? s.T : s.F, (uint64_t)B * Npad, Dpad, 128, kBf16)) return rc;
@@ -820,7 +861,6 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
                           set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2>) |
                           set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny>);
   if (once) return once;
-  DYCON_CUDA(cudaMemsetAsync(s.stats, 0, (size_t)kNumStats * plane * sizeof(float), st));
   dim3 grid(Npad / 128, sp.splits, B);
   fecl_tc_sweep_kernel<0, kBf16, kNoFocal><<<grid, kThreads, smem, st>>>(mapF, mapT, sp);
   fecl_tc_sweep_kernel<1, kBf16, kNoFocal><<<grid, kThreads, smem, st>>>(mapF, mapT, sp);
@@ -830,7 +870,7 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
     default: fecl_tc_sweep_kernel<2, kBf16, kFocalAny><<<grid, kThreads, smem, st>>>(mapF, mapT, sp); break;
   }
   DYCON_CUDA(cudaGetLastError());
-  count_launches(p.has_teacher ? 5 : 4);
+  count_launches(4);
   return DYCON_OK;
 }
 
@@ -846,7 +886,9 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
   if (int rc = make_tmap_16_2d(&mapT, p.has_teacher ? s.T : s.F, (uint64_t)B * Npad, Dpad, 64, kBf16)) return rc;
   BwdParams bp;
   bp.N = N; bp.Npad = Npad; bp.KC = KC; bp.D = D; bp.has_teacher = p.has_teacher;
-  bp.splits = pick_splits(Npad / 128, B);
+  // column splits accumulate into a zero-filled gradient: only for a dense layout (memset of B*N*D floats)
+  const bool dense = a.g_sb == (int64_t)N * D && ((a.g_sn == D && a.g_sd == 1) || (a.g_sn == 1 && a.g_sd == N));
+  bp.splits = dense ? pick_splits(Npad / 128, B) : 1;
   bp.sc = p.sc;
   bp.c1 = p.sc.inv_tau * kLog2e;
   bp.labels = a.labels;
@@ -854,6 +896,7 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
   bp.stat_a = s.stats + kStatA * plane; bp.stat_kappa = s.stats + kStatKappa * plane;
   bp.hdr = s.hdr;
   bp.cross_cnt = a.cross_cnt; bp.grad_out = a.grad_out; bp.grad_feat = a.grad_feat;
+  bp.g_sb = a.g_sb; bp.g_sn = a.g_sn; bp.g_sd = a.g_sd;
   size_t smem = (size_t)KC * kChunk128 + 4 * (size_t)KC * kChunk64 + 2 * kChunk128 + sizeof(BwdMisc);
   if (smem < 120 * 1024) smem = 120 * 1024;
   static const int once = set_smem(fecl_tc_bwd_kernel<kBf16, kNoFocal>) | set_smem(fecl_tc_bwd_kernel<kBf16, kFocalG2>) |

@@ -94,15 +94,56 @@ __device__ __forceinline__ void set_elem(float4& v, int k, float x) {
 }
 __device__ __forceinline__ void set_elem(float& v, int, float x) { v = x; }
 
+// Block + grid reduction tail of the C == 2 forward.  Warps 1.. leave their partial in shared memory and
+// retire at once (bar.arrive); only warp 0 waits for them, publishes the block partial and takes the
+// ticket, so no warp idles behind the L2 round trip of the atomic.  Fixed order -> bit-reproducible.
+__device__ __forceinline__ void uncl_finish(float acc, unsigned int* ticket, double* partials, double inv_count,
+                                            double* __restrict__ sum_out, float* __restrict__ loss_out) {
+  __shared__ float warp_part[kThreads / 32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float w = warp_sum(acc);
+  if (lane == 0) warp_part[warp] = w;
+  if (warp != 0) {
+    __threadfence_block();
+    asm volatile("bar.arrive 1, %0;" ::"n"(kThreads) : "memory");
+    return;
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+  double blk = 0.0;
+#pragma unroll
+  for (int k = 0; k < kThreads / 32; ++k) blk += (double)warp_part[k];
+  const unsigned int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+  unsigned int t = 0;
+  if (lane == 0) {
+    partials[bid] = blk;
+    __threadfence();
+    t = atomicAdd(ticket, 1u);
+  }
+  t = __shfl_sync(0xffffffffu, t, 0);
+  if (t != nblocks - 1) return;
+  __threadfence();
+  double tot = 0.0;
+  for (unsigned int k = lane; k < nblocks; k += 32) tot += __ldcg(&partials[k]);
+  tot = warp_sum(tot);
+  if (lane == 0) {
+    *sum_out = tot;
+    if (loss_out) *loss_out = (float)(tot * inv_count);
+    *ticket = 0u;
+  }
+}
+
+// Grid: (blocks per sample, sample lanes).  The loads of iteration k+1 are issued before the arithmetic of
+// iteration k (register double buffer): with ~80 instructions and 12 MUFU per voxel the kernel sits between
+// the XU pipe and HBM, and a warp that waits for its loads at the top of every iteration leaves both idle.
 template <int kVec>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 uncl_fwd_c2_kernel(const float* __restrict__ s, const float* __restrict__ t, int64_t B, int64_t V, float beta,
                    double inv_count, float* __restrict__ stash, unsigned int* ticket, double* partials,
                    double* __restrict__ sum_out, float* __restrict__ loss_out) {
   using P = Pack<kVec>;
   using vec_t = typename P::type;
-  __shared__ double scratch[32];
   const int64_t nvec = V / kVec;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
   float acc = 0.f;
   for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
     const float* s0 = s + (2 * b) * V;
@@ -110,9 +151,18 @@ uncl_fwd_c2_kernel(const float* __restrict__ s, const float* __restrict__ t, int
     const float* t0 = t + (2 * b) * V;
     const float* t1 = t0 + V;
     float* st = stash + b * V;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * kThreads) {
-      const vec_t a0 = P::load(s0 + i * kVec), a1 = P::load(s1 + i * kVec);
-      const vec_t b0 = P::load(t0 + i * kVec), b1 = P::load(t1 + i * kVec);
+    int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= nvec) continue;
+    vec_t a0 = P::load(s0 + i * kVec), a1 = P::load(s1 + i * kVec);
+    vec_t b0 = P::load(t0 + i * kVec), b1 = P::load(t1 + i * kVec);
+    while (true) {
+      const int64_t nx = i + stride;
+      const bool more = nx < nvec;
+      vec_t na0, na1, nb0, nb1;
+      if (more) {
+        na0 = P::load(s0 + nx * kVec); na1 = P::load(s1 + nx * kVec);
+        nb0 = P::load(t0 + nx * kVec); nb1 = P::load(t1 + nx * kVec);
+      }
       vec_t uo;
       float lsum = 0.f;
 #pragma unroll
@@ -124,14 +174,12 @@ uncl_fwd_c2_kernel(const float* __restrict__ s, const float* __restrict__ t, int
       }
       *reinterpret_cast<vec_t*>(st + i * kVec) = uo;  // default policy: re-read by the backward from L2
       acc += lsum;
+      if (!more) break;
+      a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
+      i = nx;
     }
   }
-  double v[1] = {(double)acc}, total[1];
-  const unsigned int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
-  if (grid_sum_last_block<1>(v, total, ticket, partials, nblocks, bid, scratch) && threadIdx.x == 0) {
-    *sum_out = total[0];
-    if (loss_out) *loss_out = (float)(total[0] * inv_count);
-  }
+  uncl_finish(acc, ticket, partials, inv_count, sum_out, loss_out);
 }
 
 template <int kVec>
@@ -145,17 +193,28 @@ uncl_bwd_c2_kernel(const float* __restrict__ stash, int64_t B, int64_t V, float 
     const float* st = stash + b * V;
     float* g0 = grad_s + (2 * b) * V;
     float* g1 = g0 + V;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * kThreads) {
+    const int64_t stride = (int64_t)gridDim.x * kThreads;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += 2 * stride) {   // two loads in flight
+      const int64_t i2 = i + stride;
+      const bool two = i2 < nvec;
       const vec_t u = *reinterpret_cast<const vec_t*>(st + i * kVec);
-      vec_t p, n;
+      vec_t u2 = u;
+      if (two) u2 = *reinterpret_cast<const vec_t*>(st + i2 * kVec);
+      vec_t p, n, p2, n2;
 #pragma unroll
       for (int k = 0; k < kVec; ++k) {
-        const float x = elem(u, k) * scale;
+        const float x = elem(u, k) * scale, x2 = elem(u2, k) * scale;
         set_elem(p, k, x);
         set_elem(n, k, -x);
+        set_elem(p2, k, x2);
+        set_elem(n2, k, -x2);
       }
-      *reinterpret_cast<vec_t*>(g0 + i * kVec) = n;
-      *reinterpret_cast<vec_t*>(g1 + i * kVec) = p;
+      __stcs(reinterpret_cast<vec_t*>(g0 + i * kVec), n);
+      __stcs(reinterpret_cast<vec_t*>(g1 + i * kVec), p);
+      if (two) {
+        __stcs(reinterpret_cast<vec_t*>(g0 + i2 * kVec), n2);
+        __stcs(reinterpret_cast<vec_t*>(g1 + i2 * kVec), p2);
+      }
     }
   }
 }

@@ -124,6 +124,15 @@ def _ptr(x):
     return ctypes.c_void_p(x.data_ptr()) if x is not None else None
 
 
+def _dense_strides(x):
+    """x's strides if x is a dense (B, N, D) tensor whose rows or columns are contiguous, else None."""
+    B, N, D = x.shape
+    st = tuple(x.stride())
+    if st in ((N * D, D, 1), (N * D, 1, N)):
+        return st
+    return None
+
+
 def _scalar_grad(go):
     go = go.reshape(()).to(torch.float32)
     return go.contiguous()
@@ -253,6 +262,9 @@ class _FeCLFunction(torch.autograd.Function):
         ctx.save_for_backward(state, labels, sums)
         ctx.cfg = (B, N, D, has_teacher, inv_tau, gamma, int(use_focal), row_weight is not None, cross_thresh,
                    lambda_cross, precision)
+        # the gradient is written in feat's own layout when that is dense ((D*N, 1, N) for the caller's
+        # normalize(transpose(view)), train_DyCON_BraTS19.py:316-323): autograd then hands it on as is
+        ctx.grad_strides = _dense_strides(feat)
         return loss
 
     @staticmethod
@@ -260,14 +272,17 @@ class _FeCLFunction(torch.autograd.Function):
         state, labels, sums = ctx.saved_tensors
         B, N, D, has_teacher, inv_tau, gamma, use_focal, has_rw, cross_thresh, lambda_cross, precision = ctx.cfg
         dev = state.device
-        grad = torch.empty((B, N, D), dtype=torch.float32, device=dev)
+        if ctx.grad_strides is None:
+            grad = torch.empty((B, N, D), dtype=torch.float32, device=dev)
+        else:
+            grad = torch.empty_strided((B, N, D), ctx.grad_strides, dtype=torch.float32, device=dev)
         go = _scalar_grad(go)
         with torch.cuda.device(dev):
             t0 = _tick()
             _lib.check(_lib.lib().dycon_fecl_bwd(_ptr(state), state.numel(), _ptr(labels), B, N, D, int(has_teacher),
                                                  inv_tau, gamma, use_focal, int(has_rw), cross_thresh, lambda_cross,
                                                  precision, ctypes.c_void_p(sums.data_ptr() + 16), _ptr(go),
-                                                 _ptr(grad), _stream_ptr(dev)),
+                                                 _ptr(grad), *grad.stride(), _stream_ptr(dev)),
                        "dycon_fecl_bwd")
             _tock("fecl_bwd", t0)
         return (grad,) + (None,) * 11

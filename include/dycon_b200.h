@@ -112,11 +112,15 @@ int dycon_fecl_fwd(const float* feat, int64_t f_sb, int64_t f_sn, int64_t f_sd,
                    dycon_stream_t stream);
 /* cross_cnt: 1 double on the device -- the BATCH-GLOBAL hard-negative count
  * (dycon_losses.py:229; the all-reduced sums_out[2] when the batch is sharded).
- * grad_out: 1 float on the device.  grad_feat: (B, N, D) fp32 contiguous, overwritten. */
+ * grad_out: 1 float on the device.  grad_feat: (B, N, D) fp32 with ELEMENT strides g_sb/g_sn/g_sd
+ * (dense: every element is written exactly once).  Passing feat's own strides -- (D*N, 1, N) for the
+ * caller's normalize(transpose(view)) layout -- lets autograd hand the gradient on without a re-layout
+ * copy; either g_sd == 1 (rows contiguous) or g_sn == 1 (columns contiguous) is the fast path. */
 int dycon_fecl_bwd(const void* state, size_t state_bytes, const float* labels, int B, int N, int D,
                    int has_teacher, float inv_tau, float gamma, int use_focal, int has_row_weight,
                    float cross_thresh, float lambda_cross, int precision, const double* cross_cnt,
-                   const float* grad_out, float* grad_feat, dycon_stream_t stream);
+                   const float* grad_out, float* grad_feat, int64_t g_sb, int64_t g_sn, int64_t g_sd,
+                   dycon_stream_t stream);
 
 /* ------------------------------------------------------------------ EMA
  * For every tensor k:  ema[k] = fma(one_minus_alpha, param[k], rn(ema[k]*alpha))  -- the

@@ -69,7 +69,7 @@ def test_argument_validation_happens_before_any_launch(so_path):
     assert rc == -1 and b"NULL" in L.dycon_last_error()
     rc = L.dycon_uncl_fwd(None, None, 0, 2, 8, 1.0, 1.0, None, None, None, None, 0, None)
     assert rc == -1
-    rc = L.dycon_fecl_bwd(None, 0, None, 1, 8, 8, 0, 1.0, 2.0, 0, 0, 0.3, 1.0, 7, None, None, None, None)
+    rc = L.dycon_fecl_bwd(None, 0, None, 1, 8, 8, 0, 1.0, 2.0, 0, 0, 0.3, 1.0, 7, None, None, None, 64, 8, 1, None)
     assert rc == -1 and b"precision" in L.dycon_last_error()
     assert L.dycon_ema_multi(None, None, None, 0, 0.5, 0.5, None) == 0      # empty list is a no-op
     assert L.dycon_ema_multi(None, None, None, 3, 0.5, 0.5, None) == -1

@@ -70,3 +70,30 @@ def test_cuda_graph_capture_and_replay():
     torch.cuda.synchronize()
     assert captured.item() == eager_loss
     assert torch.equal(gs, eager_gs) and torch.equal(gf, eager_gf)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16"])
+@pytest.mark.parametrize("layout", ["caller", "contiguous", "sliced"])
+def test_gradient_is_written_in_the_layout_of_feat(layout, precision):
+    """feat arrives with strides (D*N, 1, N) (train_DyCON_BraTS19.py:316-323): the gradient must come back in
+    the same layout (no re-layout copy in autograd) and hold the same values as for a contiguous feat."""
+    from dycon_paper_replication_b200 import FeCLoss
+    from dycon_paper_replication_b200.synthetic import make_inputs
+    inp = make_inputs("tiny", dim=64, mask_kind="bernoulli").to("cuda")
+    fecl = FeCLoss("cuda", use_focal=True, rampup_epochs=1500, precision=precision)
+    base = inp.feat.detach().contiguous().clone().requires_grad_(True)
+    fecl(base, inp.mask, inp.teacher, None, 100).backward()
+    if layout == "caller":
+        f = inp.feat.detach().transpose(1, 2).contiguous().transpose(1, 2).requires_grad_(True)
+        assert f.stride() == (f.shape[1] * f.shape[2], 1, f.shape[1])
+    elif layout == "contiguous":
+        f = inp.feat.detach().contiguous().clone().requires_grad_(True)
+    else:   # neither rows nor columns dense: falls back to a contiguous gradient
+        wide = torch.zeros(f_shape := (inp.feat.shape[0], inp.feat.shape[1], 2 * inp.feat.shape[2]), device="cuda")
+        wide[..., ::2] = inp.feat
+        f = wide[..., ::2].detach().requires_grad_(True)
+        assert f_shape[2] == 2 * f.shape[2]
+    fecl(f, inp.mask, inp.teacher, None, 100).backward()
+    if layout != "sliced":
+        assert f.grad.stride() == f.stride()
+    assert torch.equal(f.grad.contiguous(), base.grad)
