@@ -14,7 +14,7 @@ import re
 import subprocess
 import sys
 
-RAW = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+RAW = ["gpu__time_duration.sum", "sm__cycles_elapsed.max", "smsp__inst_executed.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
        "smsp__issue_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
        "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
@@ -36,6 +36,8 @@ def launches(path):
     ki, vi, ui = h.index("Kernel Name"), h.index("Metric Value"), h.index("Metric Unit")
     agg = collections.OrderedDict()
     for r in data:
+        if "spin_kernel" in r[ki]:        # torch.cuda._sleep: bench.py's pacing kernel, not part of the step
+            continue
         v = float(r[vi].replace(",", ""))
         v = v / 1e3 if r[ui] in ("ns", "nsecond") else v
         agg.setdefault(short(r[ki]), []).append(v)
