@@ -281,12 +281,12 @@ def run_ours(args):
     # per-call durations (roofline): eager launches with CUDA events around every C-ABI call, queued
     # behind a GPU-side sleep so the device -- not Python -- paces them (no idle gaps inside the events)
     with dycon_losses.kernel_timer() as kt:
-        for rep in range(3):
-            torch.cuda._sleep(int(25e6))
-            for k in range(10):
+        for rep in range(5):
+            torch.cuda._sleep(int(60e6))          # ~30 ms: every launch of the repetition is queued behind it
+            for k in range(6):
                 step(k)
         fence()
-        calls = {k: v[len(v) // 3:] for k, v in kt.ms().items()}      # drop the first repetition
+        calls = {k: v[len(v) // 5:] for k, v in kt.ms().items()}      # drop the first repetition
     if world > 1:
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

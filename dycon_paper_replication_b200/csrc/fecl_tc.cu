@@ -86,8 +86,9 @@ template <> struct Cvt<false> {
   using type = __half;
   static __device__ __forceinline__ type one(float x) { return __float2half_rn(x); }
   static __device__ __forceinline__ uint32_t two(float a, float b) {   // saturate: fp16 overflows at 65504
-    __half2 v = __floats2half2_rn(fminf(fmaxf(a, -60000.f), 60000.f), fminf(fmaxf(b, -60000.f), 60000.f));
-    return *reinterpret_cast<uint32_t*>(&v);
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));   // a -> low half, b -> high half
+    return r;
   }
 };
 
@@ -457,6 +458,25 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
 // =================================================================================================
 //  Backward
 // =================================================================================================
+// A CTA owns 128 rows of one sample and walks 32-column sub-tiles J of its column range:
+//   MMA1: S = F_I F_J^T, CS = F_I T_J^T (128x32, K = D)   -> TMEM slot J & 1
+//   epilogue: H = G + G^T, Gc (16-bit) -> column half J & 1 of the K-major smem tiles sH / sG
+//   MMA2: dF_I += H F_J + Gc T_J  (B operands read MN-major from the very tiles that produced S / CS)
+// TMA is a high-latency path (~1.5-3 us per tile when few are in flight), so the operand ring is four
+// 32 KB stages deep, and the work is decoupled over independent agents that only meet on mbarriers:
+//   warp 0 TMA producer | warp 1 MMA1 issuer | warp 2 MMA2 issuer | warp 3 idle |
+//   warps 4..11 epilogue team 0 (even sub-tiles) | warps 12..19 epilogue team 1 (odd sub-tiles)
+// An epilogue thread owns one row and 16 of the 32 columns of its team's sub-tile (TMEM lane quadrant =
+// warp % 4).  The two teams run out of phase: while one is in its MUFU-heavy arithmetic the other waits for
+// TMEM or stores H.
+constexpr int kBwdThreads = 640;
+constexpr int kBwdTeamThreads = 256;
+constexpr int kBwdStages = 4;
+constexpr uint32_t kChunk32 = 32 * 128;     // bytes of a [32 rows][64 16-bit] swizzle chunk
+__device__ __forceinline__ void bwd_team_barrier(int team) {
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(kBwdTeamThreads) : "memory");
+}
+
 struct BwdParams {
   int N, Npad, KC, D, has_teacher;
   int splits;          // column splits; with > 1 the partial dF are summed with red.global.add onto zeros
@@ -476,45 +496,95 @@ struct BwdParams {
 
 struct BwdMisc {
   uint64_t a_full;
-  uint64_t b_full[2], b_empty[2];
-  uint64_t sc_full[2], sc_empty[2];
-  uint64_t h_full, h_free, df_full;
+  uint64_t b_full[kBwdStages], b_empty[kBwdStages];
+  uint64_t sc_full[2], sc_empty[2];      // per team: S / CS accumulators of its sub-tile
+  uint64_t h_full[2], h_free[2];         // per team: its column half of sH / sG
+  uint64_t df_full;
   uint32_t tmem_slot;
   uint32_t pad_;
-  alignas(16) float col[2][5][64];   // [slot][y, m2, n, A, kappa][column]
+  alignas(16) float col[2][2][5][32];    // [team][slot][y, m2, n, -kappa A h, kappa h][column]
 };
 
+template <int kFocal, bool kTeacher>
+__device__ __forceinline__ void bwd_pair(float x, float cs, float yi, float m2i, float ni, float Pi, float ki,
+                                         float yj, float m2j, float nj, float Pj, float kj, float c1, float gamma,
+                                         float gl, float thresh, float gcs, float& h, float& g) {
+  const float tij = fmaf(x, c1, -m2j), tji = fmaf(x, c1, -m2i);
+  const float eij = ex2_approx(tij), eji = ex2_approx(tji);     // padded column: m2j = +inf -> eij = 0
+  const float Tij = eij + ni, Tji = eji + nj;
+  const float p2 = Tij * Tji;
+  float r2, rom = 0.f;
+  if (kTeacher) {
+    const float om = (1.f - cs) + kTiny;                         // dycon_losses.py:228
+    const float r = rcp_approx(p2 * om);
+    rom = r * p2;
+    r2 = r * om;
+  } else {
+    r2 = rcp_approx(p2);
+  }
+  const float rij = r2 * Tji, rji = r2 * Tij;
+  float pij, pji;                                                // phi'(d) d (1 - d)
+  if (kFocal == kNoFocal) {
+    pij = fmaf(eij, rij, -1.f);
+    pji = fmaf(eji, rji, -1.f);
+  } else {
+    const float dij = eij * rij, dji = eji * rji;
+    const float oij = fmaf(-eij, rij, 1.f), oji = fmaf(-eji, rji, 1.f);
+    const float Lij = tij - lg2_approx(Tij), Lji = tji - lg2_approx(Tji);   // log2 d
+    const float aij = fmaf(gl, dij * Lij, -oij), aji = fmaf(gl, dji * Lji, -oji);
+    if (kFocal == kFocalG2) {
+      pij = oij * oij * aij;
+      pji = oji * oji * aji;
+    } else {
+      pij = ex2_approx((gamma - 1.f) * lg2_approx(oij)) * oij * aij;
+      pji = ex2_approx((gamma - 1.f) * lg2_approx(oji)) * oji * aji;
+    }
+  }
+  const float gpos = fmaf(ki, pij, kj * pji);
+  const float gneg = fmaf(Pi, eij, Pj * eji);
+  const bool same = yj == yi;                                    // NaN labels (padding) compare unequal
+  h = same ? gpos : gneg;                                        // select: the unused branch may be NaN
+  if (kTeacher) {
+    const bool hard = (yj < yi || yj > yi) && cs > thresh;       // ordered !=: never true for padding
+    g = hard ? gcs * rom : 0.f;
+  } else {
+    g = 0.f;
+  }
+}
+
 template <bool kBf16, int kFocal>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kBwdThreads, 1)
 fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapF,
                    const __grid_constant__ CUtensorMap mapT, const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KC = p.KC, Dpad = KC * 64;
-  const uint32_t a_bytes = (uint32_t)KC * kChunk128, j_bytes = (uint32_t)KC * kChunk64;
-  const uint32_t stage_bytes = j_bytes * 2;       // F_J tile + T_J tile
-  uint8_t* sA = smem;
-  uint8_t* sStage[2] = {smem + a_bytes, smem + a_bytes + stage_bytes};
-  uint8_t* sH = smem + a_bytes + 2 * stage_bytes;     // [128 i][64 j] bf16, K-major SW128
-  uint8_t* sG = sH + kChunk128;
+  const uint32_t a_bytes = (uint32_t)KC * kChunk128, j_bytes = (uint32_t)KC * kChunk32;
+  const uint32_t stage_bytes = j_bytes * 2;       // F_J sub-tile + T_J sub-tile, interleaved per K chunk
+  uint8_t* const sA = smem;
+  uint8_t* const sStage = smem + a_bytes;         // kBwdStages x stage_bytes
+  uint8_t* const sH = sStage + kBwdStages * stage_bytes;     // [128 i][64 j] 16-bit, K-major SW128
+  uint8_t* const sG = sH + kChunk128;
   BwdMisc& ms = *reinterpret_cast<BwdMisc*>(sG + kChunk128);
   const int b = blockIdx.z, i0 = blockIdx.x * kTM, split = blockIdx.y;
-  const int nt_all = p.Npad / 64;
+  const int nt_all = (p.N + 31) / 32;           // sub-tiles that hold at least one real column
   const int t0 = (int)((long long)split * nt_all / p.splits), t1 = (int)((long long)(split + 1) * nt_all / p.splits);
-  const int nt = t1 - t0;                       // this CTA's 64-column tiles: t0 .. t1-1
+  const int nt = t1 - t0;                       // this CTA's 32-column sub-tiles: t0 .. t1-1
   const bool teacher = p.has_teacher != 0;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     mbar_init(&ms.a_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kBwdStages; ++s) {
       mbar_init(&ms.b_full[s], 1);
       mbar_init(&ms.b_empty[s], 1);
-      mbar_init(&ms.sc_full[s], 1);
-      mbar_init(&ms.sc_empty[s], 8);
     }
-    mbar_init(&ms.h_full, 8);
-    mbar_init(&ms.h_free, 1);
+    for (int g = 0; g < 2; ++g) {
+      mbar_init(&ms.sc_full[g], 1);
+      mbar_init(&ms.sc_empty[g], kBwdTeamThreads / 32);
+      mbar_init(&ms.h_full[g], kBwdTeamThreads / 32);
+      mbar_init(&ms.h_free[g], 1);
+    }
     mbar_init(&ms.df_full, 1);
     fence_mbar_init();
     prefetch_tmap(&mapA);
@@ -526,189 +596,196 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   __syncthreads();
   tcgen05_after_sync();
   const uint32_t tmem = ms.tmem_slot;
-  // TMEM columns: S[s] at s*64, CS[s] at 128 + s*64, dF at 256 (Dpad columns)
-  const uint32_t tm_s = tmem, tm_cs = tmem + 128, tm_df = tmem + 256;
+  // TMEM columns: team g's S | CS at g*64 (32 + 32 columns), dF at 256 (Dpad columns)
+  const uint32_t tm_sc = tmem, tm_df = tmem + 256;
 
   if (warp == 0) {
+    // ================================ TMA producer ================================
     if (lane == 0 && nt > 0) {
       mbar_expect_tx(&ms.a_full, a_bytes);
       for (int c = 0; c < KC; ++c) tma_load_2d(sA + c * kChunk128, &mapA, c * 64, b * p.Npad + i0, &ms.a_full);
       for (int t = 0; t < nt; ++t) {
-        const int s = t & 1, row = b * p.Npad + (t0 + t) * 64;
-        mbar_wait(&ms.b_empty[s], ((t >> 1) & 1) ^ 1);
+        const int s = t % kBwdStages, row = b * p.Npad + (t0 + t) * 32;
+        uint8_t* dst = sStage + s * stage_bytes;
+        mbar_wait_relaxed(&ms.b_empty[s], ((t / kBwdStages) & 1) ^ 1);
         mbar_expect_tx(&ms.b_full[s], teacher ? stage_bytes : j_bytes);
-        for (int c = 0; c < KC; ++c) {
-          tma_load_2d(sStage[s] + c * kChunk64, &mapF, c * 64, row, &ms.b_full[s]);
-          if (teacher) tma_load_2d(sStage[s] + j_bytes + c * kChunk64, &mapT, c * 64, row, &ms.b_full[s]);
+        for (int c = 0; c < KC; ++c) {     // chunk c = [32 F rows | 32 T rows] x 64 K: one N = 64 B operand for MMA1
+          tma_load_2d(dst + c * kChunk64, &mapF, c * 64, row, &ms.b_full[s]);
+          if (teacher) tma_load_2d(dst + c * kChunk64 + kChunk32, &mapT, c * 64, row, &ms.b_full[s]);
         }
       }
     }
   } else if (warp == 1) {
+    // ================================ MMA1 issuer: S, CS ==========================
     if (lane == 0 && nt > 0) {
-      const uint32_t idesc_s = umma_idesc_16(128, 64, false, false, kBf16);
-      const uint32_t idesc_d = umma_idesc_16(128, Dpad, false, true, kBf16);   // B = F_J / T_J read MN-major
-      auto issue_sc = [&](int t) {
-        const int s = t & 1;
-        mbar_wait(&ms.b_full[s], (t >> 1) & 1);
-        mbar_wait(&ms.sc_empty[s], ((t >> 1) & 1) ^ 1);
+      // one MMA per K step computes S | CS side by side (N = 64: the F and T rows of a chunk are contiguous)
+      const uint32_t idesc_s = umma_idesc_16(128, teacher ? 64 : 32, false, false, kBf16);
+      const uint64_t a_desc0 = umma_desc_kmajor(smem_u32(sA));
+      mbar_wait_relaxed(&ms.a_full, 0);
+      for (int t = 0; t < nt; ++t) {
+        const int s = t % kBwdStages, g = t & 1;
+        const uint64_t b_desc0 = umma_desc_kmajor(smem_u32(sStage + s * stage_bytes));
+        mbar_wait_relaxed(&ms.b_full[s], (t / kBwdStages) & 1);
+        mbar_wait_relaxed(&ms.sc_empty[g], ((t >> 1) & 1) ^ 1);
         tcgen05_after_sync();
-        for (int c = 0; c < KC; ++c) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tm_s + s * 64, umma_desc_kmajor(smem_u32(sA + c * kChunk128) + k * 32),
-                      umma_desc_kmajor(smem_u32(sStage[s] + c * kChunk64) + k * 32), idesc_s, (c | k) != 0);
-        }
-        if (teacher) {
-          for (int c = 0; c < KC; ++c) {
+        for (int c = 0; c < 4; ++c) {
+          if (c < KC) {
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-              umma_bf16(tm_cs + s * 64, umma_desc_kmajor(smem_u32(sA + c * kChunk128) + k * 32),
-                        umma_desc_kmajor(smem_u32(sStage[s] + j_bytes + c * kChunk64) + k * 32), idesc_s, (c | k) != 0);
+              umma_bf16(tm_sc + g * 64, desc_advance(a_desc0, c * kChunk128 + k * 32),
+                        desc_advance(b_desc0, c * kChunk64 + k * 32), idesc_s, (c | k) != 0);
           }
         }
-        umma_commit(&ms.sc_full[s]);
-      };
-      mbar_wait(&ms.a_full, 0);
-      issue_sc(0);
+        umma_commit(&ms.sc_full[g]);
+      }
+    }
+  } else if (warp == 2) {
+    // ================================ MMA2 issuer: dF += H F_J + Gc T_J ===========
+    if (lane == 0 && nt > 0) {
+      const uint32_t idesc_d = umma_idesc_16(128, Dpad, false, true, kBf16);   // B = F_J / T_J read MN-major
+      const uint64_t h_desc0 = umma_desc_kmajor(smem_u32(sH)), g_desc0 = umma_desc_kmajor(smem_u32(sG));
       for (int t = 0; t < nt; ++t) {
-        if (t + 1 < nt) issue_sc(t + 1);
-        const int s = t & 1;
-        mbar_wait(&ms.h_full, t & 1);
+        const int s = t % kBwdStages, g = t & 1;
+        // MN-major B: 64-element MN blocks are the chunks (LBO = 8 KB), 8 K rows per 1 KB atom (SBO)
+        const uint64_t f_desc0 = umma_desc(smem_u32(sStage + s * stage_bytes), kChunk64, 1024);
+        mbar_wait_relaxed(&ms.h_full[g], (t >> 1) & 1);
         tcgen05_after_sync();
-        // dF += H * F_J (+ Gc * T_J): K = 64 columns of the tile = 4 steps of 16 rows (2048 B) of the B tile
+        // K = the 32 columns of the sub-tile = 2 steps of 16: columns g*32 + k*16 of sH, rows k*16 (2048 B) of F_J
 #pragma unroll
-        for (int k = 0; k < 4; ++k)
-          umma_bf16(tm_df, umma_desc_kmajor(smem_u32(sH) + k * 32),
-                    umma_desc(smem_u32(sStage[s]) + k * 2048, kChunk64, 1024), idesc_d, (t | k) != 0);
+        for (int k = 0; k < 2; ++k)
+          umma_bf16(tm_df, desc_advance(h_desc0, (g * 2 + k) * 32), desc_advance(f_desc0, k * 2048), idesc_d, (t | k) != 0);
         if (teacher) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tm_df, umma_desc_kmajor(smem_u32(sG) + k * 32),
-                      umma_desc(smem_u32(sStage[s] + j_bytes) + k * 2048, kChunk64, 1024), idesc_d, true);
+          for (int k = 0; k < 2; ++k)
+            umma_bf16(tm_df, desc_advance(g_desc0, (g * 2 + k) * 32), desc_advance(f_desc0, kChunk32 + k * 2048), idesc_d, true);
         }
         umma_commit(&ms.b_empty[s]);
-        umma_commit(&ms.h_free);
+        umma_commit(&ms.h_free[g]);
       }
       umma_commit(&ms.df_full);
     }
-  } else if (nt > 0) {
-    const int et = threadIdx.x - 64;
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
+  } else if (warp >= 4 && nt > 0) {
+    // ================================ epilogue teams ==============================
+    const int team = (warp - 4) >> 3;             // 0: even sub-tiles, 1: odd sub-tiles
+    const int tt = threadIdx.x - 128 - team * kBwdTeamThreads;   // 0..255 inside the team
+    const int quarter = warp & 3, chalf = ((warp - 4) >> 2) & 1;
     const int r = quarter * 32 + lane, i = i0 + r;
     const bool row_ok = i < p.N;
     const size_t off = (size_t)b * p.N;
     const int ic = row_ok ? i : p.N - 1;
     const float qnan = __int_as_float(0x7fc00000);
-    const float yi = row_ok ? __ldg(p.labels + off + ic) : qnan;
-    const float m2i = __ldg(p.stat_m + off + ic) * kLog2e;
-    const float ni = __ldg(p.stat_n + off + ic), ai = __ldg(p.stat_a + off + ic);
-    const float ki = row_ok ? __ldg(p.stat_kappa + off + ic) : 0.f;
     // H and Gc are scaled by a power of two (~ B N tau / 8, so |H| stays O(1)) before the 16-bit
     // conversion: exact, and it keeps fp16 out of its subnormal range.  Undone when dF is read out.
     const float hscale = __ldg(p.hdr);
-    const float gc_scale = (teacher && row_ok) ? hscale * p.sc.lambda_cross / ((float)(*p.cross_cnt) + kTiny) : 0.f;
     const float h_mul = p.sc.inv_tau * hscale;
+    const float yi = row_ok ? __ldg(p.labels + off + ic) : qnan;
+    const float m2i = __ldg(p.stat_m + off + ic) * kLog2e;
+    const float ni = __ldg(p.stat_n + off + ic);
+    const float ki = row_ok ? __ldg(p.stat_kappa + off + ic) * h_mul : 0.f;
+    const float Pi = -ki * __ldg(p.stat_a + off + ic);
+    const float gcs = (teacher && row_ok) ? hscale * p.sc.lambda_cross / ((float)(*p.cross_cnt) + kTiny) : 0.f;
+    const float gl = p.sc.gamma * kLn2;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    const int cbase = half * 32;                  // this thread's 32 columns of the 64-column tile
+    const int cbase = chalf * 16;                 // this thread's 16 columns of the 32-column sub-tile
+    const int hcol = team * 32 + cbase;           // ... and of the 64-column sH / sG tiles
 
-    // column statistics of tile t: 5 planes x 64 columns = 320 values; threads 0..255 fetch one each,
-    // threads 0..63 one more (the kappa plane).  Padded columns: y = NaN, m2 = +inf, rest 0.
-    auto fetch_one = [&](int t, int q) -> float {
-      const int st = q >> 6, j = t * 64 + (q & 63);
+    // column statistics of sub-tile t: 5 planes x 32 columns, fetched by threads 0..159 of the team and
+    // published through shared memory.  Padded columns: y = NaN, m2 = +inf, rest 0 (-> e_ij = 0, h = g = 0).
+    auto fetch_one = [&](int t) -> float {
+      if (tt >= 160) return 0.f;
+      const int st = tt >> 5, j = t * 32 + (tt & 31);
       if (j >= p.N) return st == 0 ? qnan : st == 1 ? INFINITY : 0.f;
-      const float* src = st == 0 ? p.labels : st == 1 ? p.stat_m : st == 2 ? p.stat_n : st == 3 ? p.stat_a : p.stat_kappa;
-      const float val = __ldg(src + off + j);
-      return st == 1 ? val * kLog2e : val;
+      const size_t g = off + j;
+      if (st == 0) return __ldg(p.labels + g);
+      if (st == 1) return __ldg(p.stat_m + g) * kLog2e;
+      if (st == 2) return __ldg(p.stat_n + g);
+      const float kh = __ldg(p.stat_kappa + g) * h_mul;
+      return st == 3 ? -kh * __ldg(p.stat_a + g) : kh;
     };
-    auto publish = [&](int slot, float v0, float v1) {
-      ms.col[slot][et >> 6][et & 63] = v0;
-      if (et < 64) ms.col[slot][4][et] = v1;
+    auto publish = [&](int slot, float v) {
+      if (tt < 160) ms.col[team][slot][tt >> 5][tt & 31] = v;
     };
-    publish(0, fetch_one(t0, et), et < 64 ? fetch_one(t0, 256 + et) : 0.f);
-    epi_barrier();
+    if (team < nt) publish(0, fetch_one(t0 + team));
+    bwd_team_barrier(team);
 
-    for (int t = 0; t < nt; ++t) {
-      const int s = t & 1, j0 = (t0 + t) * 64;
-      const int tn = t0 + (t + 1 < nt ? t + 1 : t);
-      const float nx0 = fetch_one(tn, et), nx1 = et < 64 ? fetch_one(tn, 256 + et) : 0.f;
-      mbar_wait(&ms.sc_full[s], (t >> 1) & 1);
+    int it = 0;                                   // team-local iteration: sub-tile t = team + 2 * it
+    for (int t = team; t < nt; t += 2, ++it) {
+      const int slot = it & 1, j0 = (t0 + t) * 32;
+      const float nx = fetch_one(t0 + (t + 2 < nt ? t + 2 : t));
+      mbar_wait(&ms.sc_full[team], it & 1);
       tcgen05_after_sync();
-      float sv[32], cv[32];
-      tmem_ld32(tm_s + lane_base + s * 64 + cbase, sv);
-      if (teacher) tmem_ld32(tm_cs + lane_base + s * 64 + cbase, cv);
+      float sv[16], cv[16];
+      tmem_ld16(tm_sc + lane_base + team * 64 + cbase, sv);
+      if (teacher) tmem_ld16(tm_sc + lane_base + team * 64 + 32 + cbase, cv);
       tmem_ld_wait();
       tcgen05_before_sync();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ms.sc_empty[s]);
+      if (lane == 0) mbar_arrive(&ms.sc_empty[team]);
 
-      const int rdiag = i - j0 - cbase;             // chunk-local index of the diagonal element (if in range)
-      const float* cy = &ms.col[s][0][cbase];
-      const float* cm = &ms.col[s][1][cbase];
-      const float* cn = &ms.col[s][2][cbase];
-      const float* ca = &ms.col[s][3][cbase];
-      const float* ck = &ms.col[s][4][cbase];
-      uint32_t hp[16], gp[16];
+      const float* cy = &ms.col[team][slot][0][cbase];
+      const float* cm = &ms.col[team][slot][1][cbase];
+      const float* cn = &ms.col[team][slot][2][cbase];
+      const float* cp = &ms.col[team][slot][3][cbase];
+      const float* ck = &ms.col[team][slot][4][cbase];
+      uint32_t hp[8], gp[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
+      for (int q = 0; q < 4; ++q) {
         const float4 y4 = *reinterpret_cast<const float4*>(cy + q * 4), m4 = *reinterpret_cast<const float4*>(cm + q * 4);
-        const float4 n4 = *reinterpret_cast<const float4*>(cn + q * 4), a4 = *reinterpret_cast<const float4*>(ca + q * 4);
+        const float4 n4 = *reinterpret_cast<const float4*>(cn + q * 4), p4 = *reinterpret_cast<const float4*>(cp + q * 4);
         const float4 k4 = *reinterpret_cast<const float4*>(ck + q * 4);
         const float ys[4] = {y4.x, y4.y, y4.z, y4.w}, m2[4] = {m4.x, m4.y, m4.z, m4.w}, ns[4] = {n4.x, n4.y, n4.z, n4.w};
-        const float as[4] = {a4.x, a4.y, a4.z, a4.w}, ks[4] = {k4.x, k4.y, k4.z, k4.w};
+        const float ps[4] = {p4.x, p4.y, p4.z, p4.w}, ks[4] = {k4.x, k4.y, k4.z, k4.w};
         float hv[4], gv[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const int c = q * 4 + k;
-          const float x = sv[c];
-          const float tij = fmaf(x, p.c1, -m2[k]), tji = fmaf(x, p.c1, -m2i);
-          const float eij = ex2_approx(tij), eji = ex2_approx(tji);
-          const float gpos = ki * pos_bwd<kFocal>(tij, eij, ni, p.sc.gamma) + ks[k] * pos_bwd<kFocal>(tji, eji, ns[k], p.sc.gamma);
-          const float gneg = -(ki * eij * ai + ks[k] * eji * as[k]);
-          const float g = ys[k] == yi ? gpos : gneg;            // select: the unused branch may be NaN
-          const bool live = (c != rdiag) && (m2[k] != INFINITY);  // diagonal and padded columns carry no gradient
-          hv[k] = live ? g * h_mul : 0.f;
-          if (teacher) {
-            const float cs = cv[c];
-            const bool hard = (ys[k] != yi) && (cs > p.sc.cross_thresh) && (m2[k] != INFINITY);
-            gv[k] = hard ? gc_scale * rcp_approx(1.f - cs + kTiny) : 0.f;
-          } else {
-            gv[k] = 0.f;
-          }
+          if (teacher)
+            bwd_pair<kFocal, true>(sv[c], cv[c], yi, m2i, ni, Pi, ki, ys[k], m2[k], ns[k], ps[k], ks[k], p.c1,
+                                   p.sc.gamma, gl, p.sc.cross_thresh, gcs, hv[k], gv[k]);
+          else
+            bwd_pair<kFocal, false>(sv[c], 0.f, yi, m2i, ni, Pi, ki, ys[k], m2[k], ns[k], ps[k], ks[k], p.c1,
+                                    p.sc.gamma, gl, p.sc.cross_thresh, gcs, hv[k], gv[k]);
         }
         hp[q * 2] = Cvt<kBf16>::two(hv[0], hv[1]);
         hp[q * 2 + 1] = Cvt<kBf16>::two(hv[2], hv[3]);
         gp[q * 2] = Cvt<kBf16>::two(gv[0], gv[1]);
         gp[q * 2 + 1] = Cvt<kBf16>::two(gv[2], gv[3]);
       }
-      // the previous tile's second GEMMs must have finished reading sH / sG
-      if (t > 0) mbar_wait(&ms.h_free, (t - 1) & 1);
+      // the team's previous MMA2 must have finished reading this column half of sH / sG
+      if (it > 0) mbar_wait(&ms.h_free[team], (it - 1) & 1);
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {     // four 16-byte units = 32 16-bit columns
-        const uint32_t o = sw128_offset(r, cbase + u * 8);
+      for (int u = 0; u < 2; ++u) {     // two 16-byte units = 16 16-bit columns
+        const uint32_t o = sw128_offset(r, hcol + u * 8);
         *reinterpret_cast<uint4*>(sH + o) = make_uint4(hp[u * 4], hp[u * 4 + 1], hp[u * 4 + 2], hp[u * 4 + 3]);
         if (teacher) *reinterpret_cast<uint4*>(sG + o) = make_uint4(gp[u * 4], gp[u * 4 + 1], gp[u * 4 + 2], gp[u * 4 + 3]);
       }
+      // the diagonal pair carries no gradient (l_ii is multiplied by 0, dycon_losses.py:176-178): clear it in
+      // place instead of testing every pair.  (Its Gc is already 0: same label, never a hard negative.)
+      const int rdiag = i - j0 - cbase;
+      if (rdiag >= 0 && rdiag < 16) *reinterpret_cast<uint16_t*>(sH + sw128_offset(r, hcol + rdiag)) = 0;
       fence_async_smem();
-      publish(s ^ 1, nx0, nx1);
+      publish(slot ^ 1, nx);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&ms.h_full);
-      epi_barrier();
+      if (lane == 0) mbar_arrive(&ms.h_full[team]);
+      bwd_team_barrier(team);
     }
 
-    // ---- dF (TMEM) * go -> grad_feat ----
+    // ---- dF (TMEM) * go -> grad_feat: the 16 epilogue warps split the Dpad columns four ways ----
     mbar_wait(&ms.df_full, 0);
     tcgen05_after_sync();
     const float go = __ldg(p.grad_out) / hscale;
-    const int dhalf = Dpad / 2;                      // columns per half (multiple of 32)
-    for (int c0 = half * dhalf; c0 < (half + 1) * dhalf; c0 += 32) {
-      float v[32];
-      tmem_ld32(tm_df + lane_base + c0, v);
+    const int cgrp = (warp - 4) >> 2;               // 0..3
+    const int dq = Dpad / 4;                         // columns per column group (multiple of 16)
+    for (int c0 = cgrp * dq; c0 < (cgrp + 1) * dq; c0 += 16) {
+      float v[16];
+      tmem_ld16(tm_df + lane_base + c0, v);
       tmem_ld_wait();
       if (row_ok) {
         float* dst = p.grad_feat + (int64_t)b * p.g_sb + (int64_t)i * p.g_sn + (int64_t)c0 * p.g_sd;
         if (p.g_sd == 1 && ((p.g_sn | p.g_sb) & 3) == 0) {       // rows contiguous: 16-byte stores
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < 4; ++q) {
             const float o0 = go * v[q * 4], o1 = go * v[q * 4 + 1], o2 = go * v[q * 4 + 2], o3 = go * v[q * 4 + 3];
             if (c0 + q * 4 + 3 < p.D) {
               if (p.splits == 1) {
@@ -728,7 +805,7 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           }
         } else {   // columns contiguous (the caller's (D*N, 1, N) layout): a warp stores 32 consecutive rows
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
+          for (int c = 0; c < 16; ++c) {
             if (c0 + c < p.D) {
               float* q = dst + (int64_t)c * p.g_sd;
               if (p.splits == 1) *q = go * v[c];
@@ -882,8 +959,8 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
   const size_t plane = (size_t)B * N;
   CUtensorMap mapA, mapF, mapT;
   if (int rc = make_tmap_16_2d(&mapA, s.F, (uint64_t)B * Npad, Dpad, 128, kBf16)) return rc;
-  if (int rc = make_tmap_16_2d(&mapF, s.F, (uint64_t)B * Npad, Dpad, 64, kBf16)) return rc;
-  if (int rc = make_tmap_16_2d(&mapT, p.has_teacher ? s.T : s.F, (uint64_t)B * Npad, Dpad, 64, kBf16)) return rc;
+  if (int rc = make_tmap_16_2d(&mapF, s.F, (uint64_t)B * Npad, Dpad, 32, kBf16)) return rc;
+  if (int rc = make_tmap_16_2d(&mapT, p.has_teacher ? s.T : s.F, (uint64_t)B * Npad, Dpad, 32, kBf16)) return rc;
   BwdParams bp;
   bp.N = N; bp.Npad = Npad; bp.KC = KC; bp.D = D; bp.has_teacher = p.has_teacher;
   // column splits accumulate into a zero-filled gradient: only for a dense layout (memset of B*N*D floats)
@@ -897,7 +974,7 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
   bp.hdr = s.hdr;
   bp.cross_cnt = a.cross_cnt; bp.grad_out = a.grad_out; bp.grad_feat = a.grad_feat;
   bp.g_sb = a.g_sb; bp.g_sn = a.g_sn; bp.g_sd = a.g_sd;
-  size_t smem = (size_t)KC * kChunk128 + 4 * (size_t)KC * kChunk64 + 2 * kChunk128 + sizeof(BwdMisc);
+  size_t smem = (size_t)KC * kChunk128 + (size_t)kBwdStages * 2 * KC * kChunk32 + 2 * kChunk128 + sizeof(BwdMisc);
   if (smem < 120 * 1024) smem = 120 * 1024;
   static const int once = set_smem(fecl_tc_bwd_kernel<kBf16, kNoFocal>) | set_smem(fecl_tc_bwd_kernel<kBf16, kFocalG2>) |
                           set_smem(fecl_tc_bwd_kernel<kBf16, kFocalAny>);
@@ -906,9 +983,9 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
   if (bp.splits > 1) DYCON_CUDA(cudaMemsetAsync(a.grad_feat, 0, (size_t)B * N * D * sizeof(float), st));
   dim3 grid(Npad / 128, bp.splits, B);
   switch (focal_kind(p.sc)) {
-    case kNoFocal: fecl_tc_bwd_kernel<kBf16, kNoFocal><<<grid, kThreads, smem, st>>>(mapA, mapF, mapT, bp); break;
-    case kFocalG2: fecl_tc_bwd_kernel<kBf16, kFocalG2><<<grid, kThreads, smem, st>>>(mapA, mapF, mapT, bp); break;
-    default: fecl_tc_bwd_kernel<kBf16, kFocalAny><<<grid, kThreads, smem, st>>>(mapA, mapF, mapT, bp); break;
+    case kNoFocal: fecl_tc_bwd_kernel<kBf16, kNoFocal><<<grid, kBwdThreads, smem, st>>>(mapA, mapF, mapT, bp); break;
+    case kFocalG2: fecl_tc_bwd_kernel<kBf16, kFocalG2><<<grid, kBwdThreads, smem, st>>>(mapA, mapF, mapT, bp); break;
+    default: fecl_tc_bwd_kernel<kBf16, kFocalAny><<<grid, kBwdThreads, smem, st>>>(mapA, mapF, mapT, bp); break;
   }
   DYCON_CUDA(cudaGetLastError());
   count_launches(1);

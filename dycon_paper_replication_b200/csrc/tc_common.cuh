@@ -54,6 +54,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Same, for the single-lane producer / MMA-issuer warps: back off between polls so that their spin loop
+// does not take issue slots from the epilogue warps of the same SM sub-partition.
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+  for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+    __nanosleep(32);
+    if (spin > (1u << 24)) __trap();
+  }
+}
+
 // ---- proxy / tcgen05 fences ----------------------------------------------------------------------
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -138,6 +147,11 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo_b
          (uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32);
 }
 __device__ __forceinline__ uint64_t umma_desc_kmajor(uint32_t smem_addr) { return umma_desc(smem_addr, 16, 1024); }
+// Descriptor of the same layout `bytes` further into shared memory (a multiple of 16; the sum must stay below
+// 256 KB so that only the 14-bit start-address field changes): one 32-bit add in the MMA issue loop.
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t bytes) {
+  return (desc & 0xffffffff00000000ull) | (uint32_t)((uint32_t)desc + (bytes >> 4));
+}
 
 // Instruction descriptor, kind::f16: D = f32 (bits [4,6) = 1), A / B format at bits [7,10) / [10,13)
 // (0 = fp16, 1 = bf16), bit 15 / 16 = A / B major (0 = K, 1 = MN), [17,23) = N >> 3, [24,29) = M >> 4.
