@@ -85,22 +85,23 @@ __device__ __forceinline__ void block_sum(double (&v)[kLanes], double* scratch) 
 // Second stage: the block that takes the last ticket sums every block's partials in index
 // order and returns true (in all of its threads) with the totals in thread 0's `total`.
 // The ticket is reset so the workspace is left zeroed (re-entrant across launches).
+// `last_flag`: one int of shared memory (kernels whose dynamic shared memory is 1024-byte aligned and nearly
+// full pass a slot of it: even one byte of static shared memory would cost them a whole kilobyte).
 template <int kLanes>
 __device__ __forceinline__ bool grid_sum_last_block(double (&v)[kLanes], double (&total)[kLanes],
                                                     unsigned int* ticket, double* partials,
                                                     unsigned int nblocks, unsigned int block_id,
-                                                    double* scratch) {
-  __shared__ bool is_last;
+                                                    double* scratch, int* last_flag) {
   block_sum<kLanes>(v, scratch);
   if (threadIdx.x == 0) {
 #pragma unroll
     for (int k = 0; k < kLanes; ++k) partials[(size_t)block_id * kLanes + k] = v[k];
     __threadfence();
     unsigned int t = atomicAdd(ticket, 1u);
-    is_last = (t == nblocks - 1);
+    *last_flag = (t == nblocks - 1);
   }
   __syncthreads();
-  if (!is_last) return false;
+  if (!*last_flag) return false;
   __threadfence();
   double acc[kLanes];
 #pragma unroll
@@ -116,6 +117,14 @@ __device__ __forceinline__ bool grid_sum_last_block(double (&v)[kLanes], double 
     *ticket = 0u;
   }
   return true;
+}
+template <int kLanes>
+__device__ __forceinline__ bool grid_sum_last_block(double (&v)[kLanes], double (&total)[kLanes],
+                                                    unsigned int* ticket, double* partials,
+                                                    unsigned int nblocks, unsigned int block_id,
+                                                    double* scratch) {
+  __shared__ int is_last;
+  return grid_sum_last_block<kLanes>(v, total, ticket, partials, nblocks, block_id, scratch, &is_last);
 }
 #endif  // __CUDACC__
 

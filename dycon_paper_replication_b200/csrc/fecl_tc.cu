@@ -28,16 +28,14 @@ namespace {
 using namespace tc;
 
 constexpr int kTM = 128;               // rows per CTA (UMMA M)
-constexpr int kThreads = 320;          // warp 0: TMA, warp 1: MMA, warps 2..9: epilogue
-constexpr int kEpiThreads = 256;
 constexpr uint32_t kChunk128 = 128 * 128;   // bytes of a [128 rows][64 bf16] swizzle chunk
 constexpr uint32_t kChunk64 = 64 * 128;     // bytes of a [ 64 rows][64 bf16] swizzle chunk
+constexpr uint32_t kChunk32 = 32 * 128;     // bytes of a [ 32 rows][64 bf16] swizzle chunk
 constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
-__device__ __forceinline__ void epi_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 // Focal variants are compile-time (a runtime `if (focal)` / gamma test per pair costs branches in the
 // hottest loop): 0 = no focal weight, 1 = gamma == 2 (the scripts' value), 2 = any gamma.
 enum { kNoFocal = 0, kFocalG2 = 1, kFocalAny = 2 };
@@ -153,9 +151,26 @@ pack16_kernel(const PackParams p) {
 // =================================================================================================
 //  Forward sweeps
 // =================================================================================================
+// A CTA owns 128 rows of one sample (A tile resident in shared memory) and walks the sub-tiles of its
+// column range.  A sub-tile is one 32 KB ring stage and one N = 64 MMA per K step:
+//   modes 0 / 1 and mode 2 without a teacher: 64 columns of F_J            -> S  (64 TMEM columns)
+//   mode 2 with a teacher: 32 columns, the F_J and T_J rows interleaved per K chunk -> S | CS (32 + 32)
+// TMA is a high-latency path, so the ring is five stages deep.  Agents (they only meet on mbarriers):
+//   warp 0 TMA producer | warps 1..3 MMA issuers (sub-tile t is issued by warp 1 + t % 3) |
+//   warps 4..11 epilogue team 0 (even sub-tiles) | warps 12..19 epilogue team 1 (odd sub-tiles)
+// An epilogue thread owns one row (TMEM lane quadrant = warp % 4) and half of the sub-tile's columns.
+constexpr int kSwThreads = 640;
+constexpr int kSwTeamThreads = 256;
+constexpr int kSwStages = 5;
+constexpr int kSwSlots = 4;                 // TMEM accumulator slots of 64 columns (two per team)
+__device__ __forceinline__ void sw_team_barrier(int team) {
+  asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(kSwTeamThreads) : "memory");
+}
+__device__ __forceinline__ void sw_epi_barrier() { asm volatile("bar.sync 3, 512;" ::: "memory"); }
+
 struct SweepParams {
   int N, Npad, KC, has_teacher;
-  int splits;          // column splits: grid.y CTAs share a row block, each sweeps 1/splits of the column tiles
+  int splits;          // column splits: grid.y CTAs share a row block, each sweeps 1/splits of the sub-tiles
   FeclScalars sc;
   float c1;            // inv_tau * log2(e)
   float inv_rows;
@@ -177,120 +192,49 @@ struct SweepParams {
 
 struct SweepMisc {
   uint64_t a_full;
-  uint64_t b_full[2], b_empty[2];
-  uint64_t acc_full[4], acc_empty[4];
+  uint64_t b_full[kSwStages], b_empty[kSwStages];
+  uint64_t acc_full[kSwSlots], acc_empty[kSwSlots];
   uint32_t tmem_slot;
   uint32_t pad_;
-  alignas(16) float col[2][2][128];    // [slot][stat: y, m2][column]; padded columns carry y = NaN, m2 = +inf
-  float xch[2][128];       // column-half 1 -> column-half 0 exchange of per-row partials
-  double scratch[3 * 32];
+  alignas(16) float col[2][2][2][64];   // [team][slot][stat: y, m2][column]; padded columns: y = NaN, m2 = +inf
 };
 
-// Epilogue bodies: one 32-column chunk of one accumulator row per thread.  `cy` / `cm` point at this
-// chunk's staged column labels / scaled column maxima in shared memory (read as broadcast float4).
-// rdiag = the chunk-local index of the diagonal element of this row, or -1.
-__device__ __forceinline__ void body_rowmax(const float (&v)[32], const float* cy, float yi, int rdiag, float& mx,
-                                            float& cnt) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
-    const float ys[4] = {yy.x, yy.y, yy.z, yy.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = q * 4 + k;
-      mx = fmaxf(mx, c == rdiag ? 0.f : v[c]);     // padded columns hold S = 0 <= mx
-      cnt += ys[k] == yi ? 1.f : 0.f;
-    }
-  }
-}
-__device__ __forceinline__ void body_negsum(const float (&v)[32], const float* cy, const float* cm, float yi, float c1,
-                                            float& nsum) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
-    const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
-    const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float e = ex2_approx(fmaf(v[q * 4 + k], c1, -m2[k]));   // padded: m2 = +inf -> e = 0
-      nsum += ys[k] != yi ? e : 0.f;
-    }
-  }
-}
-template <int kFocal>
-__device__ __forceinline__ void body_pos(const float (&v)[32], const float* cy, const float* cm, float yi, int rdiag,
-                                         float c1, float n_row, float gamma, float& lsum, float& asum) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
-    const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
-    const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = q * 4 + k;
-      const float t = fmaf(v[c], c1, -m2[k]);
-      float phi2, at;
-      pos_fwd<kFocal>(t, ex2_approx(t), n_row, gamma, phi2, at);
-      const bool pos = (ys[k] == yi) && (c != rdiag);    // select, never multiply: the unused lane may be NaN
-      lsum += pos ? phi2 : 0.f;
-      asum += pos ? at : 0.f;
-    }
-  }
-}
-__device__ __forceinline__ void body_cross(const float (&v)[32], const float* cy, const float* cm, float yi,
-                                           float thresh, float& csum, float& ccnt) {
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
-    const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
-    const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float cs = v[q * 4 + k];
-      const bool hard = (ys[k] != yi) && (cs > thresh) && (m2[k] != INFINITY);   // m2 = +inf marks padding
-      const float term = lg2_approx(1.f - cs + kTiny);       // NaN for cs > 1, like the reference's log
-      csum += hard ? term : 0.f;
-      ccnt += hard ? 1.f : 0.f;
-    }
-  }
-}
-
-// kMode 0: row max m_i and positive count P_i          (P0)
-// kMode 1: kappa_i and the negative sums n_i           (P1; needs every m)
-// kMode 2: row loss, A_i and the teacher cross term    (P2; needs every n)
+// kMode 0: row max m_i                                            (P0)
+// kMode 1: negative sums n_i and the positive counts P_i           (P1; needs every m)
+// kMode 2: kappa_i, row loss, A_i and the teacher cross term       (P2; needs every n and P)
 // Grid (row blocks, column splits, samples).  Three launches instead of one fused sweep: n_i needs all m_k
 // and d_ij needs the complete n_i, i.e. two grid-wide dependencies, and splitting the columns of a row
 // block over several CTAs (so that small batches still fill 148 SMs) adds a third.
 template <int kMode, bool kBf16, int kFocal>
-__global__ void __launch_bounds__(kThreads, 1)
-fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapT,
-                     const SweepParams p) {
+__global__ void __launch_bounds__(kSwThreads, 1)
+fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapF,
+                     const __grid_constant__ CUtensorMap mapT, const SweepParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KC = p.KC;
-  const uint32_t tile_bytes = (uint32_t)KC * kChunk128;
+  const uint32_t a_bytes = (uint32_t)KC * kChunk128, stage_bytes = (uint32_t)KC * kChunk64;
   uint8_t* const sA = smem;
-  uint8_t* const sB0 = smem + tile_bytes;
-  SweepMisc& ms = *reinterpret_cast<SweepMisc*>(smem + 3 * tile_bytes);
+  uint8_t* const sStage = smem + a_bytes;
+  SweepMisc& ms = *reinterpret_cast<SweepMisc*>(sStage + kSwStages * stage_bytes);
   const int b = blockIdx.z, i0 = blockIdx.x * kTM, split = blockIdx.y;
-  const int nt_all = p.Npad / 128;
+  const bool teacher_on = kMode == 2 && p.has_teacher;
+  const int tcols = teacher_on ? 32 : 64;                  // columns per sub-tile
+  const int nt_all = (p.N + tcols - 1) / tcols;            // sub-tiles that hold at least one real column
   const int jt0 = (int)((long long)split * nt_all / p.splits), jt1 = (int)((long long)(split + 1) * nt_all / p.splits);
   const int nt = jt1 - jt0;
-  const bool teacher_on = kMode == 2 && p.has_teacher;
-  const int per_j = teacher_on ? 2 : 1;
-  const int total = nt * per_j;                            // per column tile: S [, CS]
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
     mbar_init(&ms.a_full, 1);
-    for (int s = 0; s < 2; ++s) mbar_init(&ms.b_full[s], 1), mbar_init(&ms.b_empty[s], 1);
-    for (int a = 0; a < 4; ++a) mbar_init(&ms.acc_full[a], 1), mbar_init(&ms.acc_empty[a], 8);
+    for (int s = 0; s < kSwStages; ++s) mbar_init(&ms.b_full[s], 1), mbar_init(&ms.b_empty[s], 1);
+    for (int a = 0; a < kSwSlots; ++a) mbar_init(&ms.acc_full[a], 1), mbar_init(&ms.acc_empty[a], kSwTeamThreads / 32);
     fence_mbar_init();
+    prefetch_tmap(&mapA);
     prefetch_tmap(&mapF);
     if (teacher_on) prefetch_tmap(&mapT);
     if (kMode == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.hdr[0] = p.hscale;
   }
-  if (warp == 1) tmem_alloc(&ms.tmem_slot, 512);
+  if (warp == 1) tmem_alloc(&ms.tmem_slot, 256);
   tcgen05_before_sync();
   __syncthreads();
   tcgen05_after_sync();
@@ -301,45 +245,51 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0 && nt > 0) {
-      mbar_expect_tx(&ms.a_full, tile_bytes);
-      for (int c = 0; c < KC; ++c) tma_load_2d(sA + c * kChunk128, &mapF, c * 64, b * p.Npad + i0, &ms.a_full);
-      for (int t = 0; t < total; ++t) {
-        const int s = t & 1;
-        const int jt = jt0 + t / per_j;
-        const bool teacher = teacher_on && (t % per_j) == 1;
-        uint8_t* dst = sB0 + s * tile_bytes;
-        mbar_wait(&ms.b_empty[s], ((t >> 1) & 1) ^ 1);
-        mbar_expect_tx(&ms.b_full[s], tile_bytes);
-        for (int c = 0; c < KC; ++c)
-          tma_load_2d(dst + c * kChunk128, teacher ? &mapT : &mapF, c * 64, b * p.Npad + jt * 128, &ms.b_full[s]);
+      mbar_expect_tx(&ms.a_full, a_bytes);
+      for (int c = 0; c < KC; ++c) tma_load_2d(sA + c * kChunk128, &mapA, c * 64, b * p.Npad + i0, &ms.a_full);
+      for (int t = 0; t < nt; ++t) {
+        const int s = t % kSwStages, row = b * p.Npad + (jt0 + t) * tcols;
+        uint8_t* dst = sStage + s * stage_bytes;
+        mbar_wait_relaxed(&ms.b_empty[s], ((t / kSwStages) & 1) ^ 1);
+        mbar_expect_tx(&ms.b_full[s], stage_bytes);
+        for (int c = 0; c < KC; ++c) {
+          tma_load_2d(dst + c * kChunk64, &mapF, c * 64, row, &ms.b_full[s]);       // box: 64 rows, or 32 with a teacher
+          if (teacher_on) tma_load_2d(dst + c * kChunk64 + kChunk32, &mapT, c * 64, row, &ms.b_full[s]);
+        }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA issuer ==================================
+  } else if (warp < 4) {
+    // ================================ MMA issuers =================================
+    // One thread needs ~130 cycles of issue slots per tcgen05.mma (descriptor arithmetic + the election
+    // wrapper) but an N = 64 MMA only occupies the tensor pipe for 32: three warps issue alternate sub-tiles.
     if (lane == 0 && nt > 0) {
-      const uint32_t idesc = umma_idesc_16(128, 128, false, false, kBf16);
-      const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB0);
-      mbar_wait(&ms.a_full, 0);
-      for (int t = 0; t < total; ++t) {
-        const int s = t & 1, a = t & 3;
-        mbar_wait(&ms.b_full[s], (t >> 1) & 1);
-        mbar_wait(&ms.acc_empty[a], ((t >> 2) & 1) ^ 1);
+      const uint32_t idesc = umma_idesc_16(128, 64, false, false, kBf16);
+      const uint64_t a_desc0 = umma_desc_kmajor(smem_u32(sA));
+      mbar_wait_relaxed(&ms.a_full, 0);
+      for (int t = warp - 1; t < nt; t += 3) {
+        const int s = t % kSwStages, a = t & (kSwSlots - 1);
+        const uint64_t b_desc0 = umma_desc_kmajor(smem_u32(sStage + s * stage_bytes));
+        mbar_wait_relaxed(&ms.b_full[s], (t / kSwStages) & 1);
+        mbar_wait_relaxed(&ms.acc_empty[a], ((t / kSwSlots) & 1) ^ 1);
         tcgen05_after_sync();
-        const uint32_t d_tmem = tmem + a * 128;
-        for (int c = 0; c < KC; ++c) {
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(d_tmem, umma_desc_kmajor(a_addr + c * kChunk128 + k * 32),
-                      umma_desc_kmajor(b_addr + s * tile_bytes + c * kChunk128 + k * 32), idesc, (c | k) != 0);
+        for (int c = 0; c < 4; ++c) {
+          if (c < KC) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem + a * 64, desc_advance(a_desc0, c * kChunk128 + k * 32),
+                        desc_advance(b_desc0, c * kChunk64 + k * 32), idesc, (c | k) != 0);
+          }
         }
         umma_commit(&ms.b_empty[s]);
         umma_commit(&ms.acc_full[a]);
       }
     }
-  } else if (nt > 0) {
-    // ================================ epilogue (8 warps) ==========================
-    const int et = threadIdx.x - 64;              // 0..255
-    const int quarter = warp & 3, half = (warp - 2) >> 2;
+  } else if (warp >= 4) {
+    // ================================ epilogue teams ==============================
+    const int team = (warp - 4) >> 3;             // 0: even sub-tiles, 1: odd sub-tiles
+    const int tt = threadIdx.x - 128 - team * kSwTeamThreads;   // 0..255 inside the team
+    const int quarter = warp & 3, chalf = ((warp - 4) >> 2) & 1;
     const int r = quarter * 32 + lane, i = i0 + r;
     const bool row_ok = i < p.N;
     const size_t off = (size_t)b * p.N;
@@ -349,97 +299,172 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
     const float qnan = __int_as_float(0x7fc00000);
     const float yi = row_ok ? __ldg(yb + i) : qnan;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    const int cidx = et & 127;
+    // this thread's columns of a sub-tile: 32 of 64 (F only), or 16 of 32 of both S and CS (teacher)
+    const int cbase = teacher_on ? chalf * 16 : chalf * 32;
 
-    // column statistics of tile jt: threads 0..127 fetch the label, 128..255 the (scaled) column max
-    auto fetch = [&](int jt) -> float {
-      const int j = jt * 128 + cidx;
-      if (et < 128) return j < p.N ? __ldg(yb + j) : qnan;
+    // column statistics of sub-tile t (tcols columns): threads 0..63 fetch the label, 64..127 the scaled max
+    auto fetch = [&](int t) -> float {
+      if (tt >= 128) return 0.f;
+      const int c = tt & 63, j = t * tcols + c;
+      const bool ok = c < tcols && j < p.N;
+      if (tt < 64) return ok ? __ldg(yb + j) : qnan;
       if (kMode == 0) return 0.f;
-      return j < p.N ? __ldg(mb + j) * kLog2e : INFINITY;
+      return ok ? __ldg(mb + j) * kLog2e : INFINITY;
     };
-    auto publish = [&](int slot, float val) { ms.col[slot][et >> 7][cidx] = val; };
-    // wait for accumulator `t`, hand each 32-column chunk of this thread's half to `body`, release it
-    auto consume = [&](int t, auto&& body) {
-      const int a = t & 3;
-      mbar_wait(&ms.acc_full[a], (t >> 2) & 1);
-      tcgen05_after_sync();
-#pragma unroll 1
-      for (int ch = 0; ch < 2; ++ch) {
-        const int cbase = half * 64 + ch * 32;
-        float v[32];
-        tmem_ld32(tmem + lane_base + a * 128 + cbase, v);
-        tmem_ld_wait();
-        body(v, cbase);
-      }
-      tcgen05_before_sync();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&ms.acc_empty[a]);
+    auto publish = [&](int slot, float val) {
+      if (tt < 128) ms.col[team][slot][tt >> 6][tt & 63] = val;
     };
 
-    float n_row = 0.f;
-    if (kMode == 1 && half == 0 && row_ok) {     // every split writes the same value (a split may own no tile)
-      // kappa_i = r_i c_i / (B N),  c_i = 1/(P_i - 1 + 1e-18)   (dycon_losses.py:192; P from the P0 launch)
+    float n_row = 0.f, kappa = 0.f;
+    if (kMode == 2) {
+      n_row = __ldg(p.stat_n + g);
+      // kappa_i = r_i c_i / (B N),  c_i = 1/(P_i - 1 + 1e-18)   (dycon_losses.py:192; P from the P1 launch)
       const float rw = p.row_weight ? __ldg(p.row_weight + g) : 1.f;
-      p.stat_kappa[g] = rw / ((__ldg(p.stat_p + g) - 1.f) + kTiny) * p.inv_rows;
+      kappa = rw / ((__ldg(p.stat_p + g) - 1.f) + kTiny) * p.inv_rows;
+      if (split == 0 && team == 0 && chalf == 0 && row_ok) p.stat_kappa[g] = kappa;
     }
-    if (kMode == 2) n_row = __ldg(p.stat_n + g);
 
-    publish(0, fetch(jt0));
-    epi_barrier();
+    if (team < nt) publish(0, fetch(jt0 + team));
+    sw_team_barrier(team);
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
-    int t = 0;
-    for (int q = 0; q < nt; ++q) {
-      const int jt = jt0 + q, slot = q & 1;
-      const float nxt = fetch(q + 1 < nt ? jt + 1 : jt);
-      const int dloc = jt == (int)blockIdx.x ? r : -1;
-      if (kMode == 0) {         // acc0 = max (the zeroed diagonal always takes part: >= 0), acc1 = count
-        consume(t++, [&](const float (&v)[32], int cbase) {
-          body_rowmax(v, &ms.col[slot][0][cbase], yi, dloc - cbase, acc0, acc1);
-        });
-      } else if (kMode == 1) {  // acc0 = n_i partial                     (dycon_losses.py:183-184)
-        consume(t++, [&](const float (&v)[32], int cbase) {
-          body_negsum(v, &ms.col[slot][0][cbase], &ms.col[slot][1][cbase], yi, p.c1, acc0);
-        });
-      } else {                  // acc0 / acc1 = loss / A partials, acc2 / acc3 = cross sum / count (:186-229)
-        consume(t++, [&](const float (&v)[32], int cbase) {
-          body_pos<kFocal>(v, &ms.col[slot][0][cbase], &ms.col[slot][1][cbase], yi, dloc - cbase, p.c1, n_row,
-                           p.sc.gamma, acc0, acc1);
-        });
-        if (teacher_on) {
-          consume(t++, [&](const float (&v)[32], int cbase) {
-            body_cross(v, &ms.col[slot][0][cbase], &ms.col[slot][1][cbase], yi, p.sc.cross_thresh, acc2, acc3);
-          });
+    int it = 0;                                   // team-local iteration: sub-tile t = team + 2 * it
+    for (int t = team; t < nt; t += 2, ++it) {
+      const int slot = it & 1, a = t & (kSwSlots - 1), j0 = (jt0 + t) * tcols;
+      const float nxt = fetch(jt0 + (t + 2 < nt ? t + 2 : t));
+      const float* cy = &ms.col[team][slot][0][cbase];
+      const float* cm = &ms.col[team][slot][1][cbase];
+      const int rdiag = i - j0 - cbase;           // chunk-local column of the diagonal pair, if in range
+      mbar_wait(&ms.acc_full[a], (t / kSwSlots) & 1);
+      tcgen05_after_sync();
+      if (!teacher_on) {
+        float v[32];
+        tmem_ld32(tmem + lane_base + a * 64 + cbase, v);
+        tmem_ld_wait();
+        tcgen05_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ms.acc_empty[a]);
+        // does any row of this warp meet its diagonal inside this chunk?  (warp-uniform)
+        const int w0 = i0 + quarter * 32 - j0 - cbase;     // rdiag of lane 0
+        const bool diag_here = w0 + 31 >= 0 && w0 < 32;
+        if (kMode == 0) {          // acc0 = max_j l_ij, the zeroed diagonal takes part (>= 0)   (dycon_losses.py:176-181)
+          if (diag_here) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc0 = fmaxf(acc0, c == rdiag ? 0.f : v[c]);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) acc0 = fmaxf(acc0, v[c]);     // padded columns hold S = 0 <= acc0
+          }
+        } else if (kMode == 1) {   // acc0 = n_i partial, acc1 = positive count                  (dycon_losses.py:183-184,192)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
+            const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
+            const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const float e = ex2_approx(fmaf(v[q * 4 + k], p.c1, -m2[k]));   // padded: m2 = +inf -> e = 0
+              const bool same = ys[k] == yi;
+              acc0 += same ? 0.f : e;
+              acc1 += same ? 1.f : 0.f;
+            }
+          }
+        } else {                   // acc0 / acc1 = loss / A partials                              (dycon_losses.py:186-206)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
+            const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
+            const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int c = q * 4 + k;
+              const float tl = fmaf(v[c], p.c1, -m2[k]);
+              float phi2, at;
+              pos_fwd<kFocal>(tl, ex2_approx(tl), n_row, p.sc.gamma, phi2, at);
+              const bool pos = diag_here ? (ys[k] == yi) && (c != rdiag) : (ys[k] == yi);   // select, never multiply
+              acc0 += pos ? phi2 : 0.f;
+              acc1 += pos ? at : 0.f;
+            }
+          }
         }
+      } else {
+        // teacher mode (kMode == 2): 16 columns of S and the same 16 columns of CS
+        float v[16], w[16];
+        tmem_ld16(tmem + lane_base + a * 64 + cbase, v);
+        tmem_ld16(tmem + lane_base + a * 64 + 32 + cbase, w);
+        tmem_ld_wait();
+        tcgen05_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ms.acc_empty[a]);
+        const int w0 = i0 + quarter * 32 - j0 - cbase;
+        const bool diag_here = w0 + 31 >= 0 && w0 < 16;
+        float cprod = 1.f;         // product of (1 - cs) over this chunk's hard negatives: one log per 16 pairs
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
+          const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
+          const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int c = q * 4 + k;
+            const float tl = fmaf(v[c], p.c1, -m2[k]);
+            float phi2, at;
+            pos_fwd<kFocal>(tl, ex2_approx(tl), n_row, p.sc.gamma, phi2, at);
+            const bool same = ys[k] == yi;
+            const bool pos = diag_here ? same && (c != rdiag) : same;
+            acc0 += pos ? phi2 : 0.f;
+            acc1 += pos ? at : 0.f;
+            // cross term: -log(1 - cs + 1e-18) over labels differ && cs > thresh (dycon_losses.py:217-229);
+            // ordered != so that padding (y = NaN) is never a hard negative
+            const float cs = w[c];
+            const bool hard = (ys[k] < yi || ys[k] > yi) && cs > p.sc.cross_thresh;
+            cprod *= hard ? (1.f - cs) + kTiny : 1.f;
+            acc3 += hard ? 1.f : 0.f;
+          }
+        }
+        acc2 += lg2_approx(cprod);       // NaN for cs > 1, like the reference's log of a negative number
       }
       publish(slot ^ 1, nxt);
-      epi_barrier();
+      sw_team_barrier(team);
     }
-    // ---- combine the two column halves of the CTA, then the column splits through global memory ----
-    if (half == 1) { ms.xch[0][r] = acc0; ms.xch[1][r] = acc1; }
-    epi_barrier();
-    if (half == 0 && row_ok) {
-      if (kMode == 0) {
-        const float m = fmaxf(acc0, ms.xch[0][r]) * p.sc.inv_tau;      // >= 0, so the int ordering is the float ordering
-        atomicMax(reinterpret_cast<int*>(p.stat_m + g), __float_as_int(m));
-        atomicAdd(p.stat_p + g, acc1 + ms.xch[1][r]);                   // integer-valued: exact in any order
-      } else if (kMode == 1) {
-        atomicAdd(p.stat_n + g, acc0 + ms.xch[0][r]);
-      } else {
-        const float ls = -kLn2 * (acc0 + ms.xch[0][r]);
-        atomicAdd(p.stat_a + g, acc1 + ms.xch[1][r]);
-        red[0] = (double)(__ldg(p.stat_kappa + g) * ls);   // kappa_i = r_i c_i inv_rows
+
+    // ---- combine the four threads that share a row (2 teams x 2 column halves), then the column splits ----
+    sw_epi_barrier();                    // every sub-tile is consumed: all MMAs are done, the ring is free
+    float* xch = reinterpret_cast<float*>(sStage);       // [3 writers][128 rows][4]
+    const int wr = team * 2 + chalf;
+    if (wr != 0) *reinterpret_cast<float4*>(xch + ((wr - 1) * 128 + r) * 4) = make_float4(acc0, acc1, acc2, acc3);
+    sw_epi_barrier();
+    if (wr == 0) {
+#pragma unroll
+      for (int u = 0; u < 3; ++u) {
+        const float4 o = *reinterpret_cast<const float4*>(xch + (u * 128 + r) * 4);
+        if (kMode == 0) acc0 = fmaxf(acc0, o.x); else acc0 += o.x;
+        acc1 += o.y; acc2 += o.z; acc3 += o.w;
+      }
+      if (row_ok && nt > 0) {
+        if (kMode == 0) {
+          const float m = acc0 * p.sc.inv_tau;                           // >= 0, so the int ordering is the float ordering
+          atomicMax(reinterpret_cast<int*>(p.stat_m + g), __float_as_int(m));
+        } else if (kMode == 1) {
+          atomicAdd(p.stat_n + g, acc0);
+          atomicAdd(p.stat_p + g, acc1);                                  // integer-valued: exact in any order
+        } else {
+          atomicAdd(p.stat_a + g, acc1);
+          red[0] = (double)(kappa * (-kLn2 * acc0));                      // kappa_i = r_i c_i inv_rows
+          red[1] = (double)(-kLn2 * acc2);
+          red[2] = (double)acc3;
+        }
       }
     }
-    if (kMode == 2 && row_ok) { red[1] = (double)(-kLn2 * acc2); red[2] = (double)acc3; }
   }
 
   // ---- block / grid reduction of {student, cross_sum, cross_cnt} (mode 2) ----
   if (kMode == 2) {
+    double* scratch = reinterpret_cast<double*>(sStage + 8192);    // the ring is idle by now (xch uses its first 6 KB)
     double total_[3];
     const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
     const unsigned int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
-    if (grid_sum_last_block<3>(red, total_, p.ticket, p.partials, nblocks, bid, ms.scratch) && threadIdx.x == 0) {
+    if (grid_sum_last_block<3>(red, total_, p.ticket, p.partials, nblocks, bid, scratch, reinterpret_cast<int*>(sStage + 12288)) &&
+        threadIdx.x == 0) {
       const double student = total_[0] / p.inv_rows_d;
       p.sums_out[0] = student;
       p.sums_out[1] = total_[1];
@@ -452,7 +477,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
   }
   tcgen05_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
 // =================================================================================================
@@ -464,7 +489,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
 //   MMA2: dF_I += H F_J + Gc T_J  (B operands read MN-major from the very tiles that produced S / CS)
 // TMA is a high-latency path (~1.5-3 us per tile when few are in flight), so the operand ring is four
 // 32 KB stages deep, and the work is decoupled over independent agents that only meet on mbarriers:
-//   warp 0 TMA producer | warp 1 MMA1 issuer | warp 2 MMA2 issuer | warp 3 idle |
+//   warp 0 TMA producer | warps 1, 3 MMA1 issuers (even / odd sub-tiles) | warp 2 MMA2 issuer |
 //   warps 4..11 epilogue team 0 (even sub-tiles) | warps 12..19 epilogue team 1 (odd sub-tiles)
 // An epilogue thread owns one row and 16 of the 32 columns of its team's sub-tile (TMEM lane quadrant =
 // warp % 4).  The two teams run out of phase: while one is in its MUFU-heavy arithmetic the other waits for
@@ -472,7 +497,6 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_cons
 constexpr int kBwdThreads = 640;
 constexpr int kBwdTeamThreads = 256;
 constexpr int kBwdStages = 4;
-constexpr uint32_t kChunk32 = 32 * 128;     // bytes of a [32 rows][64 16-bit] swizzle chunk
 __device__ __forceinline__ void bwd_team_barrier(int team) {
   asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(kBwdTeamThreads) : "memory");
 }
@@ -615,14 +639,14 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
-    // ================================ MMA1 issuer: S, CS ==========================
+  } else if (warp == 1 || warp == 3) {
+    // ================================ MMA1 issuers: S, CS (warp 1: team 0's sub-tiles, warp 3: team 1's) ====
     if (lane == 0 && nt > 0) {
       // one MMA per K step computes S | CS side by side (N = 64: the F and T rows of a chunk are contiguous)
       const uint32_t idesc_s = umma_idesc_16(128, teacher ? 64 : 32, false, false, kBf16);
       const uint64_t a_desc0 = umma_desc_kmajor(smem_u32(sA));
       mbar_wait_relaxed(&ms.a_full, 0);
-      for (int t = 0; t < nt; ++t) {
+      for (int t = warp >> 1; t < nt; t += 2) {
         const int s = t % kBwdStages, g = t & 1;
         const uint64_t b_desc0 = umma_desc_kmajor(smem_u32(sStage + s * stage_bytes));
         mbar_wait_relaxed(&ms.b_full[s], (t / kBwdStages) & 1);
@@ -911,9 +935,12 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   pk.stats = s.stats; pk.B = B; pk.N = N; pk.D = D; pk.Npad = Npad; pk.Dpad = Dpad;
   dim3 pgrid(Npad / 64, Dpad / 64, B * (p.has_teacher ? 2 : 1));
   pack16_kernel<kBf16><<<pgrid, 256, 0, st>>>(pk);
-  CUtensorMap mapF, mapT;
-  if (int rc = make_tmap_16_2d(&mapF, s.F, (uint64_t)B * Npad, Dpad, 128, kBf16)) return rc;
-  if (int rc = make_tmap_16_2d(&mapT, p.has_teacher ? s.T : s.F, (uint64_t)B * Npad, Dpad, 128, kBf16)) return rc;
+  // boxes: 128 rows (A tile), 64 rows (a sub-tile of F alone), 32 rows (F | T interleaved in teacher mode)
+  CUtensorMap mapA, mapF64, mapF32, mapT32;
+  if (int rc = make_tmap_16_2d(&mapA, s.F, (uint64_t)B * Npad, Dpad, 128, kBf16)) return rc;
+  if (int rc = make_tmap_16_2d(&mapF64, s.F, (uint64_t)B * Npad, Dpad, 64, kBf16)) return rc;
+  if (int rc = make_tmap_16_2d(&mapF32, s.F, (uint64_t)B * Npad, Dpad, 32, kBf16)) return rc;
+  if (int rc = make_tmap_16_2d(&mapT32, p.has_teacher ? s.T : s.F, (uint64_t)B * Npad, Dpad, 32, kBf16)) return rc;
   ReduceWorkspace ws = carve_reduce_workspace(a.workspace);
   SweepParams sp;
   sp.N = N; sp.Npad = Npad; sp.KC = KC; sp.has_teacher = p.has_teacher;
@@ -929,8 +956,8 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   sp.stat_a = s.stats + kStatA * plane; sp.stat_kappa = s.stats + kStatKappa * plane;
   sp.stat_p = s.stats + kStatP * plane;
   sp.ticket = ws.ticket; sp.partials = ws.partials; sp.sums_out = a.sums_out; sp.loss_out = a.loss_out;
-  // >= 120 KB of dynamic smem also pins one CTA per SM, so the 512-column TMEM allocation never contends
-  size_t smem = (size_t)3 * KC * kChunk128 + sizeof(SweepMisc);
+  // >= 120 KB of dynamic smem also pins one CTA per SM
+  size_t smem = (size_t)KC * kChunk128 + (size_t)kSwStages * KC * kChunk64 + sizeof(SweepMisc);
   if (smem < 120 * 1024) smem = 120 * 1024;
   static const int once = set_smem(fecl_tc_sweep_kernel<0, kBf16, kNoFocal>) |
                           set_smem(fecl_tc_sweep_kernel<1, kBf16, kNoFocal>) |
@@ -938,13 +965,15 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
                           set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2>) |
                           set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny>);
   if (once) return once;
+  DYCON_REQUIRE(smem <= 227 * 1024, DYCON_ERR_UNSUPPORTED, "FeCL tensor-core fwd: %zu bytes of shared memory needed", smem);
   dim3 grid(Npad / 128, sp.splits, B);
-  fecl_tc_sweep_kernel<0, kBf16, kNoFocal><<<grid, kThreads, smem, st>>>(mapF, mapT, sp);
-  fecl_tc_sweep_kernel<1, kBf16, kNoFocal><<<grid, kThreads, smem, st>>>(mapF, mapT, sp);
+  const CUtensorMap& mapF2 = p.has_teacher ? mapF32 : mapF64;      // mode 2 walks 32-column sub-tiles with a teacher
+  fecl_tc_sweep_kernel<0, kBf16, kNoFocal><<<grid, kSwThreads, smem, st>>>(mapA, mapF64, mapT32, sp);
+  fecl_tc_sweep_kernel<1, kBf16, kNoFocal><<<grid, kSwThreads, smem, st>>>(mapA, mapF64, mapT32, sp);
   switch (focal_kind(p.sc)) {
-    case kNoFocal: fecl_tc_sweep_kernel<2, kBf16, kNoFocal><<<grid, kThreads, smem, st>>>(mapF, mapT, sp); break;
-    case kFocalG2: fecl_tc_sweep_kernel<2, kBf16, kFocalG2><<<grid, kThreads, smem, st>>>(mapF, mapT, sp); break;
-    default: fecl_tc_sweep_kernel<2, kBf16, kFocalAny><<<grid, kThreads, smem, st>>>(mapF, mapT, sp); break;
+    case kNoFocal: fecl_tc_sweep_kernel<2, kBf16, kNoFocal><<<grid, kSwThreads, smem, st>>>(mapA, mapF2, mapT32, sp); break;
+    case kFocalG2: fecl_tc_sweep_kernel<2, kBf16, kFocalG2><<<grid, kSwThreads, smem, st>>>(mapA, mapF2, mapT32, sp); break;
+    default: fecl_tc_sweep_kernel<2, kBf16, kFocalAny><<<grid, kSwThreads, smem, st>>>(mapA, mapF2, mapT32, sp); break;
   }
   DYCON_CUDA(cudaGetLastError());
   count_launches(4);
