@@ -11,6 +11,7 @@
 // Sums are two-stage and fixed-order (bit-reproducible); the last block to finish reduces the
 // per-block partials, so there is no second launch and no float atomics.
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace dycon {
 namespace {
@@ -32,46 +33,67 @@ constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 //   p_hi = 1/(1+e), p_lo = e p_hi,
 //   ln(p_hi+eps) = log1p(y) - ln(1+e)      (log1p(y) = y - y^2/2 exactly in fp32, y <= 2e-6)
 //   ln(p_lo+eps) = ln(e + y) - ln(1+e)
+// Two-class algebra, in log2 units (entropies H2 = H / ln 2: the ln 2 factors are applied once per voxel or
+// once per thread instead of once per logarithm).  Per distribution, with a = |x1 - x0|, e = exp(-a):
+//   p_hi = 1/(1+e), p_lo = e p_hi, y = eps (1+e), x = e + y,
+//   log2(p_hi + eps) = yh - l1,  yh = log2(e) (y - y^2/2)   (log1p(y) exactly in fp32, y <= 2e-6)
+//   log2(p_lo + eps) = lx - l1,  lx = log2(x),  l1 = log2(1+e)
+//   H2 = l1 - p_hi yh - p_lo lx                               (p_hi + p_lo = 1)
 struct TwoClass {
-  float p_hi, p_lo, ln_hi, ln_lo, e, x;   // x = e + y (reused by the gradient: p_lo/(p_lo+eps) = e/x)
-  float H;
+  float p_hi, p_lo, e, x, y;
+  float yh, lx;       // log2 terms (see above)
+  float H2;
   bool hi_is_1;
 };
-__device__ __forceinline__ TwoClass two_class(float x0, float x1) {
-  TwoClass o;
+// Stage 1 (before the reciprocal): e, 1 + e and x.  Stage 2 gets 1/(1 + e) from the caller, which takes the
+// reciprocals of several quantities with ONE MUFU.RCP of their product (MUFU issues 16 lanes/clk/SM and is,
+// with the issue slots, what bounds this kernel).
+__device__ __forceinline__ void two_class_begin(float x0, float x1, TwoClass& o, float& ope) {
   const float d = x1 - x0, a = fabsf(d);
   o.hi_is_1 = d >= 0.f;
   o.e = ex2_approx(-a * kLog2e) + (a - a);          // (a - a): +-inf logits become NaN like torch.softmax
-  const float ope = 1.f + o.e;
-  o.p_hi = rcp_approx(ope);
-  o.p_lo = o.e * o.p_hi;
-  const float y = kEps * ope;
-  const float l1 = kLn2 * lg2_approx(ope);
-  o.ln_hi = fmaf(y, fmaf(-0.5f, y, 1.f), -l1);
-  o.x = o.e + y;
-  o.ln_lo = fmaf(kLn2, lg2_approx(o.x), -l1);
-  o.H = -(o.p_hi * o.ln_hi + o.p_lo * o.ln_lo);
-  return o;
+  ope = 1.f + o.e;
+  o.y = kEps * ope;
+  o.x = o.e + o.y;
+}
+__device__ __forceinline__ void two_class_finish(TwoClass& o, float ope, float r_ope) {
+  o.p_hi = r_ope;
+  o.p_lo = o.e * r_ope;
+  const float l1 = lg2_approx(ope);
+  o.lx = lg2_approx(o.x);
+  o.yh = (kLog2e * o.y) * fmaf(-0.5f, o.y, 1.f);
+  o.H2 = fmaf(-o.p_lo, o.lx, fmaf(-o.p_hi, o.yh, l1));
 }
 
-// Returns L_v and the unit gradient dL_v/ds1 (SURVEY.md section 0.1 closed form).
+// Returns the two parts of L_v = q W + beta ln2 (Hs2 + Ht2) separately (the caller accumulates them apart and
+// applies beta ln2 once) and the unit gradient dL_v/ds1 (SURVEY.md section 0.1 closed form):
 //   u = ps0 ps1 (g1 - g0),  g_c = 2 (ps_c - pt_c) W - dL/dHs (ln(ps_c+eps) + ps_c/(ps_c+eps))
-__device__ __forceinline__ void voxel2(float s0, float s1, float t0, float t1, float beta, float& L,
+// Two classes: ps0 - pt0 = -(ps1 - pt1) = -d, so q = 2 d^2 and 2 (d1 - d0) W = 4 d W.
+__device__ __forceinline__ void voxel2(float s0, float s1, float t0, float t1, float beta, float& qw, float& h2,
                                        float& u) {
-  const TwoClass S = two_class(s0, s1), T = two_class(t0, t1);
-  const float es = ex2_approx(beta * kLog2e * S.H), et = ex2_approx(beta * kLog2e * T.H);
+  TwoClass S, T;
+  float as, at;                                     // 1 + e of the student / teacher
+  two_class_begin(s0, s1, S, as);
+  two_class_begin(t0, t1, T, at);
+  // 1/as, 1/at, 1/S.x from one reciprocal (as, at in [1, 2], S.x in [1e-6, 2]: the product cannot over/underflow)
+  const float p12 = as * at;
+  const float r = rcp_approx(p12 * S.x);
+  const float r_x = r * p12, r12 = r * S.x;
+  two_class_finish(S, as, r12 * at);
+  two_class_finish(T, at, r12 * as);
+  // exp(beta H) = 2^(beta log2(e) ln2 H2) = 2^(beta H2)
+  const float es = ex2_approx(beta * S.H2), et = ex2_approx(beta * T.H2);
   const float w = rcp_approx(es + et);
-  const float ps1 = S.hi_is_1 ? S.p_hi : S.p_lo, ps0 = S.hi_is_1 ? S.p_lo : S.p_hi;
-  const float pt1 = T.hi_is_1 ? T.p_hi : T.p_lo, pt0 = T.hi_is_1 ? T.p_lo : T.p_hi;
-  const float d0 = ps0 - pt0, d1 = ps1 - pt1;
-  const float q = d0 * d0 + d1 * d1;
-  L = fmaf(q, w, beta * (S.H + T.H));
-  const float dl_dh = beta - q * beta * es * w * w;
-  // (ln_hi - ln_lo) + (r_hi - r_lo),  r_hi = 1 - y(1-y),  r_lo = e / (e + y)
-  const float y = S.x - S.e;
-  const float r_hi = fmaf(-y, 1.f - y, 1.f), r_lo = S.e * rcp_approx(S.x);
-  const float hi_minus_lo = (S.ln_hi - S.ln_lo) + (r_hi - r_lo);
-  const float g1_minus_g0 = 2.f * (d1 - d0) * w - dl_dh * (S.hi_is_1 ? hi_minus_lo : -hi_minus_lo);
+  const float d = (S.hi_is_1 ? S.p_hi : S.p_lo) - (T.hi_is_1 ? T.p_hi : T.p_lo);   // ps1 - pt1
+  const float dw = d * w;
+  qw = 2.f * d * dw;
+  h2 = S.H2 + T.H2;
+  // dL/dHs = beta (1 - q es W^2)
+  const float dl_dh = fmaf(-beta * (2.f * dw * dw), es, beta);
+  // (ln_hi - ln_lo) + (r_hi - r_lo),  r_hi = p_hi/(p_hi+eps) = 1 - y(1-y),  r_lo = e / (e + y)
+  const float r_hi = fmaf(-S.y, 1.f - S.y, 1.f), r_lo = S.e * r_x;
+  const float hi_minus_lo = fmaf(kLn2, S.yh - S.lx, r_hi - r_lo);
+  const float g1_minus_g0 = fmaf(-dl_dh, S.hi_is_1 ? hi_minus_lo : -hi_minus_lo, 4.f * dw);
   u = S.p_hi * S.p_lo * g1_minus_g0;
 }
 
@@ -144,7 +166,7 @@ uncl_fwd_c2_kernel(const float* __restrict__ s, const float* __restrict__ t, int
   using vec_t = typename P::type;
   const int64_t nvec = V / kVec;
   const int64_t stride = (int64_t)gridDim.x * kThreads;
-  float acc = 0.f;
+  float acc = 0.f, acc_h = 0.f;     // sum of q W, sum of Hs2 + Ht2 (log2 units)
   for (int64_t b = blockIdx.y; b < B; b += gridDim.y) {
     const float* s0 = s + (2 * b) * V;
     const float* s1 = s0 + V;
@@ -164,22 +186,113 @@ uncl_fwd_c2_kernel(const float* __restrict__ s, const float* __restrict__ t, int
         nb0 = P::load(t0 + nx * kVec); nb1 = P::load(t1 + nx * kVec);
       }
       vec_t uo;
-      float lsum = 0.f;
+      float qsum = 0.f, hsum = 0.f;
 #pragma unroll
       for (int k = 0; k < kVec; ++k) {
-        float L, u;
-        voxel2(elem(a0, k), elem(a1, k), elem(b0, k), elem(b1, k), beta, L, u);
-        lsum += L;
+        float qw, h2, u;
+        voxel2(elem(a0, k), elem(a1, k), elem(b0, k), elem(b1, k), beta, qw, h2, u);
+        qsum += qw;
+        hsum += h2;
         set_elem(uo, k, u);
       }
       *reinterpret_cast<vec_t*>(st + i * kVec) = uo;  // default policy: re-read by the backward from L2
-      acc += lsum;
+      acc += qsum;
+      acc_h += hsum;
       if (!more) break;
       a0 = na0; a1 = na1; b0 = nb0; b1 = nb1;
       i = nx;
     }
   }
-  uncl_finish(acc, ticket, partials, inv_count, sum_out, loss_out);
+  uncl_finish(fmaf(beta * kLn2, acc_h, acc), ticket, partials, inv_count, sum_out, loss_out);
+}
+
+// ---- C == 2, 16-byte aligned: cp.async pipelined forward ------------------------------------------
+// A persistent CTA walks chunks of 1024 voxels.  Every thread runs its own 3-stage cp.async pipeline: it
+// copies the four float4 it will need two chunks from now (s0, s1, t0, t1) into its private slots of a
+// shared-memory ring, waits for the oldest group and computes from shared memory.  Nothing is shared between
+// threads, so there are no barriers; 1024 threads x 2 groups x 64 B = 131 KB of loads are in flight per SM no
+// matter how the compiler schedules the arithmetic.  (The register-prefetch version had its loads sunk to the
+// end of the loop body by ptxas and waited for them a third of the time; a TMA-bulk + mbarrier version was
+// limited to ~12 B/clk/SM from HBM by the TMA unit's outstanding-request budget -- profiles/.)
+constexpr int kPipeStages = 3;
+constexpr int kPipeChunk = 1024;                 // voxels per chunk = 256 threads x float4
+constexpr size_t kPipeSmemBytes = (size_t)kPipeStages * 4 * kThreads * sizeof(float4);   // 48 KB: four CTAs per SM
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int kPending>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(kPending) : "memory"); }
+
+__global__ void __launch_bounds__(kThreads, 4)
+uncl_fwd_c2_pipe_kernel(const float* __restrict__ s, const float* __restrict__ t, int64_t V, int64_t chunks_per_sample,
+                        int64_t total_chunks, float beta, double inv_count, float* __restrict__ stash,
+                        unsigned int* ticket, double* partials, double* __restrict__ sum_out,
+                        float* __restrict__ loss_out) {
+  extern __shared__ __align__(16) float4 ring[];          // [kPipeStages][4 streams][kThreads]
+  const int tid = threadIdx.x;
+  const int step = gridDim.x, cps = (int)chunks_per_sample;
+  // (sample, chunk-in-sample) positions advance incrementally: no 64-bit division in the loop
+  struct Pos { int b, k; };
+  auto advance = [&](Pos& p, int n) {
+    p.k += n;
+    while (p.k >= cps) { p.k -= cps; ++p.b; }
+  };
+  const int nb = (int)(total_chunks / chunks_per_sample);
+
+  auto issue = [&](const Pos& p, int st) {                // this thread's four 16-byte copies of chunk p
+    if (p.b < nb) {
+      const int64_t v = (int64_t)p.k * kPipeChunk + tid * 4;
+      if (v < V) {
+        const float* s0 = s + (2 * (int64_t)p.b) * V + v;
+        const float* t0 = t + (2 * (int64_t)p.b) * V + v;
+        float4* dst = ring + (size_t)st * 4 * kThreads + tid;
+        cp_async16(dst, s0);
+        cp_async16(dst + kThreads, s0 + V);
+        cp_async16(dst + 2 * kThreads, t0);
+        cp_async16(dst + 3 * kThreads, t0 + V);
+      }
+    }
+    cp_async_commit();                                    // always: keeps the group count uniform
+  };
+
+  Pos cur{0, 0}, nxt{0, 0};
+  advance(cur, blockIdx.x);
+  nxt = cur;
+#pragma unroll
+  for (int k = 0; k < kPipeStages - 1; ++k) {
+    issue(nxt, k);
+    advance(nxt, step);
+  }
+  float acc = 0.f, acc_h = 0.f;     // sum of q W, sum of Hs2 + Ht2 (log2 units)
+  for (int it = 0; cur.b < nb; ++it) {
+    issue(nxt, (it + kPipeStages - 1) % kPipeStages);
+    advance(nxt, step);
+    cp_async_wait<kPipeStages - 1>();                     // the current chunk has landed (in this thread's own slots)
+    const int64_t v = (int64_t)cur.k * kPipeChunk + tid * 4;
+    if (v < V) {
+      const float4* src = ring + (size_t)(it % kPipeStages) * 4 * kThreads + tid;
+      const float4 a0 = src[0], a1 = src[kThreads], b0 = src[2 * kThreads], b1 = src[3 * kThreads];
+      float4 uo;
+      float qsum = 0.f, hsum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float qw, h2, u;
+        voxel2(elem(a0, k), elem(a1, k), elem(b0, k), elem(b1, k), beta, qw, h2, u);
+        qsum += qw;
+        hsum += h2;
+        set_elem(uo, k, u);
+      }
+      *reinterpret_cast<float4*>(stash + (int64_t)cur.b * V + v) = uo;   // default policy: re-read by the backward from L2
+      acc += qsum;
+      acc_h += hsum;
+    }
+    advance(cur, step);
+  }
+  cp_async_wait<0>();
+  uncl_finish(fmaf(beta * kLn2, acc_h, acc), ticket, partials, inv_count, sum_out, loss_out);
 }
 
 template <int kVec>
@@ -344,10 +457,23 @@ int dycon_uncl_fwd(const float* s, const float* t, int64_t B, int C, int64_t V, 
     DYCON_REQUIRE(stash && aligned(stash, 4), DYCON_ERR_ARG, "UnCL fwd: C == 2 needs a stash of B*V floats");
     const bool vec = (V % 4 == 0) && aligned(s, 16) && aligned(t, 16) && aligned(stash, 16);
     if (vec) {
-      static const int res = resident_ctas(uncl_fwd_c2_kernel<4>);
-      dim3 grid = pick_grid(B, V / 4, res);
-      uncl_fwd_c2_kernel<4><<<grid, kThreads, 0, st>>>(s, t, B, V, beta, inv_count, stash, ws.ticket, ws.partials,
-                                                        sum_out, loss_out);
+      static const int per_sm = [] {
+        int n = 0;
+        if (cudaFuncSetAttribute(uncl_fwd_c2_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)kPipeSmemBytes) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, uncl_fwd_c2_pipe_kernel, kThreads, kPipeSmemBytes) !=
+                cudaSuccess || n < 1)
+          n = 0;
+        return n;
+      }();
+      DYCON_REQUIRE(per_sm > 0, DYCON_ERR_DEVICE, "UnCL fwd: cannot place the pipelined kernel (%zu B of shared memory)",
+                    kPipeSmemBytes);
+      const int64_t cps = (V + kPipeChunk - 1) / kPipeChunk, total = cps * B;
+      int64_t grid = (int64_t)per_sm * sm_count();
+      if (grid > total) grid = total;
+      if (grid > kMaxPartials) grid = kMaxPartials;
+      uncl_fwd_c2_pipe_kernel<<<(unsigned)grid, kThreads, kPipeSmemBytes, st>>>(
+          s, t, V, cps, total, beta, inv_count, stash, ws.ticket, ws.partials, sum_out, loss_out);
     } else {
       static const int res = resident_ctas(uncl_fwd_c2_kernel<1>);
       dim3 grid = pick_grid(B, V, res);
