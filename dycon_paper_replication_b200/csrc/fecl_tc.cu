@@ -110,6 +110,7 @@ pack16_kernel(const PackParams p) {
   const int which = blockIdx.z / p.B, b = blockIdx.z - which * p.B;
   const int n0 = blockIdx.x * 64, d0 = blockIdx.y * 64;
   const int tid = threadIdx.x;
+  pdl_trigger();     // the first sweep may set up (barriers, TMEM) while this grid drains; it waits before reading
   // (ternaries, not p.x[which]: a dynamic index would copy the parameter arrays to local memory)
   const float* s = (which ? p.src[1] : p.src[0]) + (int64_t)b * (which ? p.sb[1] : p.sb[0]);
   const int64_t sn = which ? p.sn[1] : p.sn[0], sd = which ? p.sd[1] : p.sd[0];
@@ -121,11 +122,28 @@ pack16_kernel(const PackParams p) {
     }
   }
   if (sn == 1) {   // lanes along n for the read, along d for the write
-    const int tx = tid & 63, ty = tid >> 6;
+    if (((p.N | sd | (which ? p.sb[1] : p.sb[0])) & 3) == 0 && (reinterpret_cast<uintptr_t>(s) & 15) == 0) {
+      // 16-byte loads, all four of a thread issued before the first use (the kernel is latency bound)
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = tid + 256 * k, d = d0 + (idx >> 4), n = n0 + (idx & 15) * 4;
+        v[k] = (n < p.N && d < p.D) ? __ldg(reinterpret_cast<const float4*>(s + n + (int64_t)d * sd))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int idx = tid + 256 * k;
+        float* row = &tile[idx >> 4][(idx & 15) * 4];
+        row[0] = v[k].x; row[1] = v[k].y; row[2] = v[k].z; row[3] = v[k].w;
+      }
+    } else {
+      const int tx = tid & 63, ty = tid >> 6;
 #pragma unroll 4
-    for (int k = ty; k < 64; k += 4) {
-      const int n = n0 + tx, d = d0 + k;
-      tile[k][tx] = (n < p.N && d < p.D) ? __ldg(s + n + (int64_t)d * sd) : 0.f;
+      for (int k = ty; k < 64; k += 4) {
+        const int n = n0 + tx, d = d0 + k;
+        tile[k][tx] = (n < p.N && d < p.D) ? __ldg(s + n + (int64_t)d * sd) : 0.f;
+      }
     }
     __syncthreads();
     const int kx = tid & 31, ry = tid >> 5;
@@ -242,6 +260,13 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 
   double red[3] = {0.0, 0.0, 0.0};
 
+  // Programmatic dependent launch: this grid may have started while the previous sweep (or the pack kernel)
+  // still runs.  P0 reads the pack kernel's output, so everybody waits here; P1 / P2 only depend on their
+  // predecessor through the row statistics, so the TMA producer and the MMA issuers run ahead (operands come
+  // from the pack kernel, which is complete once the predecessor has passed its own wait) and only the
+  // epilogue warps wait, right before they first touch the statistics.
+  if (kMode == 0) pdl_wait();
+
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0 && nt > 0) {
@@ -299,6 +324,8 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const float qnan = __int_as_float(0x7fc00000);
     const float yi = row_ok ? __ldg(yb + i) : qnan;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    if (kMode != 0) pdl_wait();                   // the statistics of the previous sweep are complete from here on
+    if (tt == 0) pdl_trigger();                   // (after the wait) the next kernel in the stream may set up
     // this thread's columns of a sub-tile: 32 of 64 (F only), or 16 of 32 of both S and CS (teacher)
     const int cbase = teacher_on ? chalf * 16 : chalf * 32;
 
@@ -968,12 +995,22 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   DYCON_REQUIRE(smem <= 227 * 1024, DYCON_ERR_UNSUPPORTED, "FeCL tensor-core fwd: %zu bytes of shared memory needed", smem);
   dim3 grid(Npad / 128, sp.splits, B);
   const CUtensorMap& mapF2 = p.has_teacher ? mapF32 : mapF64;      // mode 2 walks 32-column sub-tiles with a teacher
-  fecl_tc_sweep_kernel<0, kBf16, kNoFocal><<<grid, kSwThreads, smem, st>>>(mapA, mapF64, mapT32, sp);
-  fecl_tc_sweep_kernel<1, kBf16, kNoFocal><<<grid, kSwThreads, smem, st>>>(mapA, mapF64, mapT32, sp);
+  cudaLaunchAttribute pdl_attr[1];
+  pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kSwThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = pdl_attr;
+  cfg.numAttrs = 1;
+  DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<0, kBf16, kNoFocal>, mapA, mapF64, mapT32, sp));
+  DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<1, kBf16, kNoFocal>, mapA, mapF64, mapT32, sp));
   switch (focal_kind(p.sc)) {
-    case kNoFocal: fecl_tc_sweep_kernel<2, kBf16, kNoFocal><<<grid, kSwThreads, smem, st>>>(mapA, mapF2, mapT32, sp); break;
-    case kFocalG2: fecl_tc_sweep_kernel<2, kBf16, kFocalG2><<<grid, kSwThreads, smem, st>>>(mapA, mapF2, mapT32, sp); break;
-    default: fecl_tc_sweep_kernel<2, kBf16, kFocalAny><<<grid, kSwThreads, smem, st>>>(mapA, mapF2, mapT32, sp); break;
+    case kNoFocal: DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kNoFocal>, mapA, mapF2, mapT32, sp)); break;
+    case kFocalG2: DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kFocalG2>, mapA, mapF2, mapT32, sp)); break;
+    default: DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kFocalAny>, mapA, mapF2, mapT32, sp)); break;
   }
   DYCON_CUDA(cudaGetLastError());
   count_launches(4);
