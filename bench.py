@@ -202,7 +202,19 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     group = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to stdout when the communicator comes up: point fd 1 at stderr while
+        # that happens, so that stdout carries nothing but the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
         group = dist.group.WORLD
     n_gpus = world
     precision = args.precision or dycon_losses.default_fecl_precision()
@@ -378,9 +390,11 @@ def run_ours(args):
     ema_ms = ee0.elapsed_time(ee1) / 60.0
 
     clocks = sampler.stop() if sampler else None
+    # captured graphs hold NCCL kernels: release them before the communicator goes away
+    del graphs, graph_loss, eg
+    torch.cuda.synchronize()
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        shutdown(world)
         return
 
     # ---- roofline ------------------------------------------------------------------------------------
@@ -438,8 +452,28 @@ def run_ours(args):
         line["cpu_baseline"] = {"value": vps, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample,
                                 "ms_per_step": ms}
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    shutdown(world)
+
+
+def shutdown(world):
+    """Tear the process group down, but never let a stuck NCCL teardown hang the run."""
+    if world <= 1:
+        return
+    import threading
+    import torch.distributed as dist
+    done = threading.Event()
+
+    def _destroy():
+        try:
+            dist.destroy_process_group()
+        finally:
+            done.set()
+
+    threading.Thread(target=_destroy, daemon=True).start()
+    if not done.wait(20.0):
+        sys.stdout.flush()
+        sys.stderr.write("bench.py: process-group teardown did not finish in 20 s; exiting anyway\n")
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -15,6 +15,7 @@ SO_PATH = os.path.join(_HERE, "_dycon_b200.so")
 FECL_FP32 = 0
 FECL_BF16 = 1
 FECL_FP16 = 2
+EXCHANGE_NONE, EXCHANGE_UNCL, EXCHANGE_FECL, EXCHANGE_FECL_TEACHER = 0, 1, 2, 3
 
 _lock = threading.Lock()
 _lib = None
@@ -41,6 +42,9 @@ PROTOTYPES = {
                             _f, _f, _i, _f, _f, _d, _i, _p, _sz, _p, _p, _p, _sz, _p]),
     "dycon_fecl_bwd": (_i, [_p, _sz, _p, _i, _i, _i, _i, _f, _f, _i, _i, _f, _f, _i, _p, _p, _p, _i64, _i64, _i64, _p]),
     "dycon_ema_multi": (_i, [_p, _p, _p, _i, _f, _f, _p]),
+    "dycon_exchange_inbox_bytes": (_sz, []),
+    "dycon_exchange_enable_peer": (_i, [_i]),
+    "dycon_exchange_sums": (_i, [_p, _i, _p, _p, _i, _i, _p, _i, _d, _d, _p, _p]),
 }
 
 

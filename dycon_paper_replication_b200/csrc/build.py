@@ -19,7 +19,7 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 SO = os.path.join(PKG, "_dycon_b200.so")
 STAMP = SO + ".hash"
-SOURCES = ["api.cu", "uncl.cu", "ema.cu", "fecl_api.cu", "fecl_simt.cu", "fecl_tc.cu", "tc_host.cu"]
+SOURCES = ["api.cu", "uncl.cu", "ema.cu", "exchange.cu", "fecl_api.cu", "fecl_simt.cu", "fecl_tc.cu", "tc_host.cu"]
 HEADERS = ["common.cuh", "fecl_math.cuh", "fecl_internal.h", "tc_common.cuh", os.path.join(ROOT, "include", "dycon_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

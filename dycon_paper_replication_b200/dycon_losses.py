@@ -169,7 +169,7 @@ class _UnCLFunction(torch.autograd.Function):
                        "dycon_uncl_fwd")
             _tock("uncl_fwd", t0)
             if process_group is not None:
-                loss = sharded.uncl_loss_from_sum(sharded.all_reduce_sums(total, process_group), inv_count)
+                loss = sharded.reduce_uncl(total, inv_count, process_group)
         ctx.dims = (B, Cn, V, float(beta), inv_count)
         ctx.shape = s_logits.shape
         if Cn == 2:
@@ -257,8 +257,7 @@ class _FeCLFunction(torch.autograd.Function):
                        "dycon_fecl_fwd")
             _tock("fecl_fwd", t0)
             if process_group is not None:
-                loss = sharded.fecl_loss_from_sums(sharded.all_reduce_sums(sums, process_group), inv_rows,
-                                                   lambda_cross, has_teacher)
+                loss = sharded.reduce_fecl(sums, inv_rows, lambda_cross, has_teacher, process_group)
         ctx.save_for_backward(state, labels, sums)
         ctx.cfg = (B, N, D, has_teacher, inv_tau, gamma, int(use_focal), row_weight is not None, cross_thresh,
                    lambda_cross, precision)

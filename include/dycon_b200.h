@@ -133,6 +133,32 @@ int dycon_fecl_bwd(const void* state, size_t state_bytes, const float* labels, i
 int dycon_ema_multi(float* const* ema_ptrs, const float* const* param_ptrs, const int64_t* numels,
                     int n_tensors, float alpha, float one_minus_alpha, dycon_stream_t stream);
 
+/* ------------------------------------------------------------------ sharded batches
+ * The path shards over ranks along the batch; the only exchange is the all-reduce of the partial sums above
+ * (dycon_uncl_fwd: sum_out; dycon_fecl_fwd: sums_out; the reference has no multi-process mode, its
+ * DataParallel gather at train_DyCON_BraTS19.py:180-193 is what this replaces).  dycon_exchange_sums() does it
+ * over NVLink peer memory on the caller's stream: every rank owns an inbox of dycon_exchange_inbox_bytes()
+ * bytes (ZERO-FILLED once, 16-byte aligned, mapped into every peer, e.g. through CUDA IPC); peer_inboxes is a
+ * HOST array of `world` device pointers (entry r = rank r's inbox as mapped in THIS process, entry `rank` the
+ * local one).  local / out: n <= 7 doubles on the device (out may alias local).  seq_counter: one device
+ * uint64, zero-initialised, private to this exchange object; all ranks must issue the same sequence of calls.
+ * The totals are added in rank order, so every rank gets bit-identical results.  world <= 16.
+ */
+size_t dycon_exchange_inbox_bytes(void);
+/* Lets kernels of the CURRENT device store into memory of `peer_device` (cudaDeviceEnablePeerAccess; a no-op
+ * if already enabled).  Call once per peer before the first exchange. */
+int dycon_exchange_enable_peer(int peer_device);
+/* kind / scale / lambda_cross / loss_out: optionally evaluate the loss from the totals in the same launch
+ * (loss_out: 1 float on the device, may be NULL): UNCL: out[0]*scale (scale = 1/(B_global V));
+ * FECL: out[0]*scale (scale = 1/(B_global N)); FECL_TEACHER: out[0]*scale + lambda_cross*out[1]/(out[2]+1e-18). */
+#define DYCON_EXCHANGE_NONE 0
+#define DYCON_EXCHANGE_UNCL 1
+#define DYCON_EXCHANGE_FECL 2
+#define DYCON_EXCHANGE_FECL_TEACHER 3
+int dycon_exchange_sums(const double* local, int n, double* out, void* const* peer_inboxes, int rank, int world,
+                        unsigned long long* seq_counter, int kind, double scale, double lambda_cross, float* loss_out,
+                        dycon_stream_t stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif
