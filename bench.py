@@ -431,6 +431,18 @@ def run_ours(args):
     roof_all["ema"] = {"bound": "hbm", "achieved": 12.0 * n_params / (ema_ms * 1e-3) / 1e9, "peak": pk["hbm"],
                        "unit": "GB/s", "frac": 12.0 * n_params / (ema_ms * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
                        "avg_ms": ema_ms, "params": n_params}
+    # traffic: DRAM bytes per launch (read + write) of each family's kernels, from the committed ncu --set full
+    # capture (profiles/r1_traffic.json) -- not re-measured here (a run under ncu is never a bench run)
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    if os.path.exists(tpath) and args.shape == "brats19" and args.batch == 4 and args.dim == 256:
+        tk = json.load(open(tpath))["kernels"]
+        tot = lambda pref: sum(v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in tk.items() if k.startswith(pref))
+        fams = {"uncl_fwd": ("uncl_fwd",), "uncl_bwd": ("uncl_bwd",), "fecl_fwd": ("pack16", "fecl_tc_sweep"),
+                "fecl_bwd": ("fecl_tc_bwd",), "ema": ("ema_multi",)}
+        for name, prefs in fams.items():
+            if name in roof_all:
+                t = sum(tot(pf) for pf in prefs)
+                roof_all[name]["traffic"] = t if t > 0 else None
     dominant = max((k for k in fam if k in avg), key=lambda k: avg[k])
     roofline = dict(roof_all[dominant], kernel=dominant,
                     share_of_step=avg[dominant] / sum(avg[k] for k in fam if k in avg))

@@ -100,6 +100,7 @@ struct PackParams {
   void* dst[2];
   float* stats;        // kNumStats planes of B*N floats, zero-filled here
   int B, N, D, Npad, Dpad;
+  int pdl;
 };
 
 template <bool kBf16>
@@ -110,7 +111,7 @@ pack16_kernel(const PackParams p) {
   const int which = blockIdx.z / p.B, b = blockIdx.z - which * p.B;
   const int n0 = blockIdx.x * 64, d0 = blockIdx.y * 64;
   const int tid = threadIdx.x;
-  pdl_trigger();     // the first sweep may set up (barriers, TMEM) while this grid drains; it waits before reading
+  if (p.pdl) pdl_trigger();     // the first sweep may set up (barriers, TMEM) while this grid drains; it waits before reading
   // (ternaries, not p.x[which]: a dynamic index would copy the parameter arrays to local memory)
   const float* s = (which ? p.src[1] : p.src[0]) + (int64_t)b * (which ? p.sb[1] : p.sb[0]);
   const int64_t sn = which ? p.sn[1] : p.sn[0], sd = which ? p.sd[1] : p.sd[0];
@@ -188,6 +189,7 @@ __device__ __forceinline__ void sw_epi_barrier() { asm volatile("bar.sync 3, 512
 
 struct SweepParams {
   int N, Npad, KC, has_teacher;
+  int pdl;             // launched with programmatic stream serialization: griddepcontrol.wait / launch_dependents
   int splits;          // column splits: grid.y CTAs share a row block, each sweeps 1/splits of the sub-tiles
   FeclScalars sc;
   float c1;            // inv_tau * log2(e)
@@ -265,7 +267,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   // predecessor through the row statistics, so the TMA producer and the MMA issuers run ahead (operands come
   // from the pack kernel, which is complete once the predecessor has passed its own wait) and only the
   // epilogue warps wait, right before they first touch the statistics.
-  if (kMode == 0) pdl_wait();
+  if (kMode == 0 && p.pdl) pdl_wait();
 
   if (warp == 0) {
     // ================================ TMA producer ================================
@@ -324,8 +326,8 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const float qnan = __int_as_float(0x7fc00000);
     const float yi = row_ok ? __ldg(yb + i) : qnan;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    if (kMode != 0) pdl_wait();                   // the statistics of the previous sweep are complete from here on
-    if (tt == 0) pdl_trigger();                   // (after the wait) the next kernel in the stream may set up
+    if (kMode != 0 && p.pdl) pdl_wait();          // the statistics of the previous sweep are complete from here on
+    if (tt == 0 && p.pdl) pdl_trigger();          // (after the wait) the next kernel in the stream may set up
     // this thread's columns of a sub-tile: 32 of 64 (F only), or 16 of 32 of both S and CS (teacher)
     const int cbase = teacher_on ? chalf * 16 : chalf * 32;
 
@@ -960,6 +962,13 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   pk.src[0] = a.feat; pk.sb[0] = a.f_sb; pk.sn[0] = a.f_sn; pk.sd[0] = a.f_sd; pk.dst[0] = s.F;
   pk.src[1] = a.teacher; pk.sb[1] = a.t_sb; pk.sn[1] = a.t_sn; pk.sd[1] = a.t_sd; pk.dst[1] = s.T;
   pk.stats = s.stats; pk.B = B; pk.N = N; pk.D = D; pk.Npad = Npad; pk.Dpad = Dpad;
+  // DYCON_NO_PDL=1 launches the forward kernels fully serialised and without any griddepcontrol instruction
+  // (ncu's kernel replay of a --set full capture does not get along with programmatic dependent launches)
+  static const bool no_pdl = [] {
+    const char* e = getenv("DYCON_NO_PDL");
+    return e && e[0] == '1';
+  }();
+  pk.pdl = no_pdl ? 0 : 1;
   dim3 pgrid(Npad / 64, Dpad / 64, B * (p.has_teacher ? 2 : 1));
   pack16_kernel<kBf16><<<pgrid, 256, 0, st>>>(pk);
   // boxes: 128 rows (A tile), 64 rows (a sub-tile of F alone), 32 rows (F | T interleaved in teacher mode)
@@ -1004,7 +1013,8 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cfg.attrs = pdl_attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = no_pdl ? 0 : 1;
+  sp.pdl = no_pdl ? 0 : 1;
   DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<0, kBf16, kNoFocal>, mapA, mapF64, mapT32, sp));
   DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<1, kBf16, kNoFocal>, mapA, mapF64, mapT32, sp));
   switch (focal_kind(p.sc)) {

@@ -178,6 +178,26 @@ def test_isles22_size_properties(mode):
     assert abs(0.5 * (la + lb) - lab) <= 1e-5 * abs(lab)
 
 
+@pytest.mark.parametrize("mode", ["fp32", "fp16"])
+def test_unnormalised_features(mode):
+    """The reference's own smoke block feeds un-normalised randn features (dycon_losses.py:244-252): logits of
+    several units.  The exact mode must still meet 1e-5; the 16-bit mode stays finite and close (its operand
+    rounding is amplified by |f|^2 / tau, so the 2e-3 bound only holds for normalised embeddings)."""
+    skip_unavailable(mode)
+    g = torch.Generator().manual_seed(5)
+    b, n, d = 2, 300, 64
+    mask = (torch.rand(b, 1, n, generator=g) < 0.3).float()
+    f = 0.35 * torch.randn(b, n, d, generator=g)               # |f|^2 ~ 8, logits up to ~ +-10
+    ctor = dict(temperature=0.6, gamma=2.0, use_focal=True, rampup_epochs=1500)
+    # no teacher, like the reference's smoke call: with un-normalised features cs > 1 and log(1 - cs) is NaN
+    loss, grad = run(f, mask, None, None, 100, 1.0, mode, **ctor)
+    ref = reference(f, mask, None, 100, 1.0, **ctor)
+    assert np.isfinite(loss) and np.isfinite(grad).all()
+    tol = 1e-5 if mode == "fp32" else 3e-2
+    assert abs(loss - ref["loss"]) <= tol * abs(ref["loss"]), (loss, ref["loss"])
+    assert normwise(grad, ref["grad"]) <= (1e-5 if mode == "fp32" else 1e-1)
+
+
 def test_bad_arguments_raise():
     from dycon_paper_replication_b200 import FeCLoss
     crit = FeCLoss("cuda", precision="fp32")

@@ -82,7 +82,8 @@ def full(rep, regex=None):
             continue
         seen.add(sec["name"])
         h, data = sec["rows"][0], sec["rows"][1:]
-        si, so = h.index("# Samples"), h.index("Source")
+        si = h.index("# Samples") if "# Samples" in h else h.index("Warp Stall Sampling (All Samples)")
+        so = h.index("Source")
         stall = [i for i, c in enumerate(h) if c.startswith("stall_") and "Not Issued" not in c]
         tot = sum(int(r[si]) for r in data if len(r) > si and r[si].isdigit())
         agg = {h[i]: sum(int(r[i]) for r in data if len(r) > i and r[i].isdigit()) for i in stall}
