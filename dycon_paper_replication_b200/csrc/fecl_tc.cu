@@ -4,19 +4,22 @@
 // Reference: code/utils/dycon_losses.py:150-235; per-pair algebra in fecl_math.cuh / SURVEY.md 0.2.
 //
 // Data layout in HBM (the `state` buffer, written by the forward, read by the backward):
-//   hdr    : 128 bytes; hdr[0] = power-of-two scale applied to H / Gc before the 16-bit conversion
+//   hdr    : 1 KiB; hdr[0] = power-of-two scale applied to H / Gc before the 16-bit conversion
 //   Fb, Tb : 16-bit [B][Npad][Dpad], row-major (K-major for the MMAs), Npad = ceil128(N),
 //            Dpad = ceil64(D); padding rows / columns are zero.
-//   stats  : 4 planes of B*N floats: m (column == row max), n (negative sum), A, kappa.
+//   stats  : planes of B*N floats: m (column == row max), n (negative sum), A, kappa, P (positive count),
+//            then kMaxSplits planes of P1's per-split partial n.
 // No (N,N) tensor is ever written: every similarity tile lives in TMEM and is consumed in place.
 //
-// Kernels (a CTA owns 128 rows of one sample; 10 warps: TMA producer, MMA issuer, 8 epilogue):
-//   fecl_tc_sweep_kernel<0,..>  P0: S = F_I F_J^T tiles -> row max m_i, positive count -> kappa_i
-//   fecl_tc_sweep_kernel<1,..>  P1: S tiles -> n_i ;  P2: S tiles -> row loss, A_i ; F_I T_J^T tiles -> cross sum/count
-//   fecl_tc_bwd_kernel       per 64-column tile: S, CS -> H = G + G^T, Gc (bf16, written to smem in the
-//                            UMMA K-major swizzle) -> dF_I += H F_J + Gc T_J with F_J / T_J read as
-//                            MN-major operands from the very tiles that produced S / CS.
-// Pipelines: smem ring (TMA -> MMA) and TMEM ring (MMA -> epilogue), all mbarrier based.
+// Kernels (all: TMA producer warp, MMA issuer warps, 16 epilogue warps in two teams; mbarrier pipelines):
+//   pack16_kernel                 fp32 (B,N,D) with any strides -> Fb, Tb; zeroes the statistics
+//   fecl_tc_sweep_kernel<0,..,2>  P0: S = F_I F_J^T sub-tiles -> row max m_i            (256-row CTAs)
+//   fecl_tc_sweep_kernel<1,..,2>  P1: S sub-tiles -> partial n_i, positive counts P_i   (256-row CTAs)
+//   fecl_tc_sweep_kernel<2,..,1>  P2: S | CS sub-tiles -> kappa_i, row loss, A_i, cross sum / count, the loss
+//   fecl_tc_bwd_kernel            per 32-column sub-tile: S | CS -> H = G + G^T, Gc (16-bit, written to smem in
+//                                 the UMMA K-major swizzle) -> dF_I += H F_J + Gc T_J with F_J / T_J read as
+//                                 MN-major operands from the very stage that produced S | CS.
+// The four forward kernels are chained with programmatic dependent launch.
 #include <cstdlib>
 
 #include "fecl_internal.h"
@@ -180,8 +183,9 @@ pack16_kernel(const PackParams p) {
 // An epilogue thread owns one row (TMEM lane quadrant = warp % 4) and half of the sub-tile's columns.
 constexpr int kSwThreads = 640;
 constexpr int kSwTeamThreads = 256;
-constexpr int kSwStages = 5;
-constexpr int kSwSlots = 4;                 // TMEM accumulator slots of 64 columns (two per team)
+constexpr int kSwStages = 5;                // ring depth with a 128-row A tile (3 with the 256-row tile of P0 / P1)
+constexpr int kSwSlots = 4;                 // TMEM accumulator slots (two per team) of 64 columns per 128 rows
+constexpr int kMaxSplits = 8;               // column splits of a row block (P0 / P1); partial n_i go to slots
 __device__ __forceinline__ void sw_team_barrier(int team) {
   asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(kSwTeamThreads) : "memory");
 }
@@ -191,6 +195,8 @@ struct SweepParams {
   int N, Npad, KC, has_teacher;
   int pdl;             // launched with programmatic stream serialization: griddepcontrol.wait / launch_dependents
   int splits;          // column splits: grid.y CTAs share a row block, each sweeps 1/splits of the sub-tiles
+  int splits1;         // the split count of the P1 launch (P2 adds up that many partial n_i per row)
+  float* npart;        // kMaxSplits planes of B*N floats: P1's per-split partial n_i (summed in split order by P2)
   FeclScalars sc;
   float c1;            // inv_tau * log2(e)
   float inv_rows;
@@ -225,18 +231,25 @@ struct SweepMisc {
 // Grid (row blocks, column splits, samples).  Three launches instead of one fused sweep: n_i needs all m_k
 // and d_ij needs the complete n_i, i.e. two grid-wide dependencies, and splitting the columns of a row
 // block over several CTAs (so that small batches still fill 148 SMs) adds a third.
-template <int kMode, bool kBf16, int kFocal>
+// kRT = row tiles per CTA.  P0 / P1 have almost no epilogue work and are bound by the TMA delivery of the B
+// operand (~30 B/clk/SM): with kRT = 2 a CTA keeps TWO 128-row A tiles resident and every B sub-tile feeds two
+// MMAs, which halves the operand bytes per flop (ring of 3 stages, 128 TMEM columns per sub-tile; an epilogue
+// thread then owns one of 256 rows and all 64 columns).  P2 is epilogue bound and stays at kRT = 1.
+template <int kMode, bool kBf16, int kFocal, int kRT>
 __global__ void __launch_bounds__(kSwThreads, 1)
 fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapF,
                      const __grid_constant__ CUtensorMap mapT, const SweepParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KC = p.KC;
-  const uint32_t a_bytes = (uint32_t)KC * kChunk128, stage_bytes = (uint32_t)KC * kChunk64;
+  static_assert(kRT == 1 || kMode != 2, "the 256-row tile is for P0 / P1");
+  constexpr int kStages = kRT == 2 ? 3 : kSwStages;
+  constexpr int kSlotCols = 64 * kRT;
+  const uint32_t a_tile = (uint32_t)KC * kChunk128, a_bytes = a_tile * kRT, stage_bytes = (uint32_t)KC * kChunk64;
   uint8_t* const sA = smem;
   uint8_t* const sStage = smem + a_bytes;
-  SweepMisc& ms = *reinterpret_cast<SweepMisc*>(sStage + kSwStages * stage_bytes);
-  const int b = blockIdx.z, i0 = blockIdx.x * kTM, split = blockIdx.y;
+  SweepMisc& ms = *reinterpret_cast<SweepMisc*>(sStage + kStages * stage_bytes);
+  const int b = blockIdx.z, i0 = blockIdx.x * kTM * kRT, split = blockIdx.y;
   const bool teacher_on = kMode == 2 && p.has_teacher;
   const int tcols = teacher_on ? 32 : 64;                  // columns per sub-tile
   const int nt_all = (p.N + tcols - 1) / tcols;            // sub-tiles that hold at least one real column
@@ -254,7 +267,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     if (teacher_on) prefetch_tmap(&mapT);
     if (kMode == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.hdr[0] = p.hscale;
   }
-  if (warp == 1) tmem_alloc(&ms.tmem_slot, 256);
+  if (warp == 1) tmem_alloc(&ms.tmem_slot, kSwSlots * kSlotCols);
   tcgen05_before_sync();
   __syncthreads();
   tcgen05_after_sync();
@@ -273,11 +286,13 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     // ================================ TMA producer ================================
     if (lane == 0 && nt > 0) {
       mbar_expect_tx(&ms.a_full, a_bytes);
-      for (int c = 0; c < KC; ++c) tma_load_2d(sA + c * kChunk128, &mapA, c * 64, b * p.Npad + i0, &ms.a_full);
+      for (int h = 0; h < kRT; ++h)
+        for (int c = 0; c < KC; ++c)
+          tma_load_2d(sA + h * a_tile + c * kChunk128, &mapA, c * 64, b * p.Npad + i0 + h * kTM, &ms.a_full);
       for (int t = 0; t < nt; ++t) {
-        const int s = t % kSwStages, row = b * p.Npad + (jt0 + t) * tcols;
+        const int s = t % kStages, row = b * p.Npad + (jt0 + t) * tcols;
         uint8_t* dst = sStage + s * stage_bytes;
-        mbar_wait_relaxed(&ms.b_empty[s], ((t / kSwStages) & 1) ^ 1);
+        mbar_wait_relaxed(&ms.b_empty[s], ((t / kStages) & 1) ^ 1);
         mbar_expect_tx(&ms.b_full[s], stage_bytes);
         for (int c = 0; c < KC; ++c) {
           tma_load_2d(dst + c * kChunk64, &mapF, c * 64, row, &ms.b_full[s]);       // box: 64 rows, or 32 with a teacher
@@ -294,18 +309,21 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       const uint64_t a_desc0 = umma_desc_kmajor(smem_u32(sA));
       mbar_wait_relaxed(&ms.a_full, 0);
       for (int t = warp - 1; t < nt; t += 3) {
-        const int s = t % kSwStages, a = t & (kSwSlots - 1);
+        const int s = t % kStages, a = t & (kSwSlots - 1);
         const uint64_t b_desc0 = umma_desc_kmajor(smem_u32(sStage + s * stage_bytes));
-        mbar_wait_relaxed(&ms.b_full[s], (t / kSwStages) & 1);
+        mbar_wait_relaxed(&ms.b_full[s], (t / kStages) & 1);
         mbar_wait_relaxed(&ms.acc_empty[a], ((t / kSwSlots) & 1) ^ 1);
         tcgen05_after_sync();
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          if (c < KC) {
+        for (int h = 0; h < kRT; ++h) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k)
-              umma_bf16(tmem + a * 64, desc_advance(a_desc0, c * kChunk128 + k * 32),
-                        desc_advance(b_desc0, c * kChunk64 + k * 32), idesc, (c | k) != 0);
+          for (int c = 0; c < 4; ++c) {
+            if (c < KC) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem + a * kSlotCols + h * 64, desc_advance(a_desc0, h * a_tile + c * kChunk128 + k * 32),
+                          desc_advance(b_desc0, c * kChunk64 + k * 32), idesc, (c | k) != 0);
+            }
           }
         }
         umma_commit(&ms.b_empty[s]);
@@ -317,7 +335,10 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const int team = (warp - 4) >> 3;             // 0: even sub-tiles, 1: odd sub-tiles
     const int tt = threadIdx.x - 128 - team * kSwTeamThreads;   // 0..255 inside the team
     const int quarter = warp & 3, chalf = ((warp - 4) >> 2) & 1;
-    const int r = quarter * 32 + lane, i = i0 + r;
+    // kRT = 1: the two warp groups of a team split the columns of a sub-tile; kRT = 2: they split the two
+    // 128-row tiles and every thread walks all 64 columns in two chunks
+    const int rh = kRT == 2 ? chalf : 0;
+    const int r = rh * kTM + quarter * 32 + lane, i = i0 + r;
     const bool row_ok = i < p.N;
     const size_t off = (size_t)b * p.N;
     const size_t g = off + (row_ok ? i : 0);
@@ -329,7 +350,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     if (kMode != 0 && p.pdl) pdl_wait();          // the statistics of the previous sweep are complete from here on
     if (tt == 0 && p.pdl) pdl_trigger();          // (after the wait) the next kernel in the stream may set up
     // this thread's columns of a sub-tile: 32 of 64 (F only), or 16 of 32 of both S and CS (teacher)
-    const int cbase = teacher_on ? chalf * 16 : chalf * 32;
+    const int cbase = kRT == 2 ? 0 : teacher_on ? chalf * 16 : chalf * 32;
 
     // column statistics of sub-tile t (tcols columns): threads 0..63 fetch the label, 64..127 the scaled max
     auto fetch = [&](int t) -> float {
@@ -346,7 +367,10 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 
     float n_row = 0.f, kappa = 0.f;
     if (kMode == 2) {
-      n_row = __ldg(p.stat_n + g);
+      // n_i = the P1 launch's per-split partial sums, added in split order (deterministic for any split count);
+      // the total is also what the backward reads
+      for (int q = 0; q < p.splits1; ++q) n_row += __ldg(p.npart + (size_t)q * gridDim.z * p.N + g);
+      if (split == 0 && team == 0 && chalf == 0 && row_ok) p.stat_n[g] = n_row;
       // kappa_i = r_i c_i / (B N),  c_i = 1/(P_i - 1 + 1e-18)   (dycon_losses.py:192; P from the P1 launch)
       const float rw = p.row_weight ? __ldg(p.row_weight + g) : 1.f;
       kappa = rw / ((__ldg(p.stat_p + g) - 1.f) + kTiny) * p.inv_rows;
@@ -360,63 +384,72 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     for (int t = team; t < nt; t += 2, ++it) {
       const int slot = it & 1, a = t & (kSwSlots - 1), j0 = (jt0 + t) * tcols;
       const float nxt = fetch(jt0 + (t + 2 < nt ? t + 2 : t));
-      const float* cy = &ms.col[team][slot][0][cbase];
-      const float* cm = &ms.col[team][slot][1][cbase];
-      const int rdiag = i - j0 - cbase;           // chunk-local column of the diagonal pair, if in range
       mbar_wait(&ms.acc_full[a], (t / kSwSlots) & 1);
       tcgen05_after_sync();
       if (!teacher_on) {
-        float v[32];
-        tmem_ld32(tmem + lane_base + a * 64 + cbase, v);
-        tmem_ld_wait();
-        tcgen05_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ms.acc_empty[a]);
-        // does any row of this warp meet its diagonal inside this chunk?  (warp-uniform)
-        const int w0 = i0 + quarter * 32 - j0 - cbase;     // rdiag of lane 0
-        const bool diag_here = w0 + 31 >= 0 && w0 < 32;
-        if (kMode == 0) {          // acc0 = max_j l_ij, the zeroed diagonal takes part (>= 0)   (dycon_losses.py:176-181)
-          if (diag_here) {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) acc0 = fmaxf(acc0, c == rdiag ? 0.f : v[c]);
-          } else {
-#pragma unroll
-            for (int c = 0; c < 32; ++c) acc0 = fmaxf(acc0, v[c]);     // padded columns hold S = 0 <= acc0
+#pragma unroll 1
+        for (int ch = 0; ch < kRT; ++ch) {        // kRT = 2: the two 32-column chunks of this thread's row
+          const int cb = cbase + ch * 32;
+          const float* cy = &ms.col[team][slot][0][cb];
+          const float* cm = &ms.col[team][slot][1][cb];
+          const int rdiag = i - j0 - cb;          // chunk-local column of the diagonal pair, if in range
+          float v[32];
+          tmem_ld32(tmem + lane_base + a * kSlotCols + rh * 64 + cb, v);
+          tmem_ld_wait();
+          if (ch == kRT - 1) {                    // last read of this accumulator: hand it back to the MMA issuers
+            tcgen05_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ms.acc_empty[a]);
           }
-        } else if (kMode == 1) {   // acc0 = n_i partial, acc1 = positive count                  (dycon_losses.py:183-184,192)
+          // does any row of this warp meet its diagonal inside this chunk?  (warp-uniform)
+          const int w0 = i0 + rh * kTM + quarter * 32 - j0 - cb;     // rdiag of lane 0
+          const bool diag_here = w0 + 31 >= 0 && w0 < 32;
+          if (kMode == 0) {          // acc0 = max_j l_ij, the zeroed diagonal takes part (>= 0)   (dycon_losses.py:176-181)
+            if (diag_here) {
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
-            const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
-            const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
+              for (int c = 0; c < 32; ++c) acc0 = fmaxf(acc0, c == rdiag ? 0.f : v[c]);
+            } else {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const float e = ex2_approx(fmaf(v[q * 4 + k], p.c1, -m2[k]));   // padded: m2 = +inf -> e = 0
-              const bool same = ys[k] == yi;
-              acc0 += same ? 0.f : e;
-              acc1 += same ? 1.f : 0.f;
+              for (int c = 0; c < 32; ++c) acc0 = fmaxf(acc0, v[c]);     // padded columns hold S = 0 <= acc0
             }
-          }
-        } else {                   // acc0 / acc1 = loss / A partials                              (dycon_losses.py:186-206)
+          } else if (kMode == 1) {   // acc0 = n_i partial, acc1 = positive count                  (dycon_losses.py:183-184,192)
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
-            const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
-            const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
+            for (int q = 0; q < 8; ++q) {
+              const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
+              const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
+              const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int c = q * 4 + k;
-              const float tl = fmaf(v[c], p.c1, -m2[k]);
-              float phi2, at;
-              pos_fwd<kFocal>(tl, ex2_approx(tl), n_row, p.sc.gamma, phi2, at);
-              const bool pos = diag_here ? (ys[k] == yi) && (c != rdiag) : (ys[k] == yi);   // select, never multiply
-              acc0 += pos ? phi2 : 0.f;
-              acc1 += pos ? at : 0.f;
+              for (int k = 0; k < 4; ++k) {
+                const float e = ex2_approx(fmaf(v[q * 4 + k], p.c1, -m2[k]));   // padded: m2 = +inf -> e = 0
+                const bool same = ys[k] == yi;
+                acc0 += same ? 0.f : e;
+                acc1 += same ? 1.f : 0.f;
+              }
+            }
+          } else {                   // acc0 / acc1 = loss / A partials                              (dycon_losses.py:186-206)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
+              const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
+              const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int c = q * 4 + k;
+                const float tl = fmaf(v[c], p.c1, -m2[k]);
+                float phi2, at;
+                pos_fwd<kFocal>(tl, ex2_approx(tl), n_row, p.sc.gamma, phi2, at);
+                const bool pos = diag_here ? (ys[k] == yi) && (c != rdiag) : (ys[k] == yi);   // select, never multiply
+                acc0 += pos ? phi2 : 0.f;
+                acc1 += pos ? at : 0.f;
+              }
             }
           }
         }
       } else {
         // teacher mode (kMode == 2): 16 columns of S and the same 16 columns of CS
+        const float* cy = &ms.col[team][slot][0][cbase];
+        const float* cm = &ms.col[team][slot][1][cbase];
+        const int rdiag = i - j0 - cbase;         // chunk-local column of the diagonal pair, if in range
         float v[16], w[16];
         tmem_ld16(tmem + lane_base + a * 64 + cbase, v);
         tmem_ld16(tmem + lane_base + a * 64 + 32 + cbase, w);
@@ -456,16 +489,18 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       sw_team_barrier(team);
     }
 
-    // ---- combine the four threads that share a row (2 teams x 2 column halves), then the column splits ----
+    // ---- combine the threads that share a row (kRT = 1: 2 teams x 2 column halves; kRT = 2: the 2 teams),
+    //      then the column splits ----
     sw_epi_barrier();                    // every sub-tile is consumed: all MMAs are done, the ring is free
-    float* xch = reinterpret_cast<float*>(sStage);       // [3 writers][128 rows][4]
-    const int wr = team * 2 + chalf;
-    if (wr != 0) *reinterpret_cast<float4*>(xch + ((wr - 1) * 128 + r) * 4) = make_float4(acc0, acc1, acc2, acc3);
+    float* xch = reinterpret_cast<float*>(sStage);       // [writers - 1][rows of the CTA][4]
+    constexpr int kRows = kTM * kRT, kWriters = kRT == 2 ? 2 : 4;
+    const int wr = kRT == 2 ? team : team * 2 + chalf;
+    if (wr != 0) *reinterpret_cast<float4*>(xch + ((wr - 1) * kRows + r) * 4) = make_float4(acc0, acc1, acc2, acc3);
     sw_epi_barrier();
     if (wr == 0) {
 #pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        const float4 o = *reinterpret_cast<const float4*>(xch + (u * 128 + r) * 4);
+      for (int u = 0; u < kWriters - 1; ++u) {
+        const float4 o = *reinterpret_cast<const float4*>(xch + (u * kRows + r) * 4);
         if (kMode == 0) acc0 = fmaxf(acc0, o.x); else acc0 += o.x;
         acc1 += o.y; acc2 += o.z; acc3 += o.w;
       }
@@ -474,7 +509,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           const float m = acc0 * p.sc.inv_tau;                           // >= 0, so the int ordering is the float ordering
           atomicMax(reinterpret_cast<int*>(p.stat_m + g), __float_as_int(m));
         } else if (kMode == 1) {
-          atomicAdd(p.stat_n + g, acc0);
+          p.npart[(size_t)split * gridDim.z * p.N + g] = acc0;           // summed in split order by P2 (deterministic)
           atomicAdd(p.stat_p + g, acc1);                                  // integer-valued: exact in any order
         } else {
           atomicAdd(p.stat_a + g, acc1);
@@ -506,7 +541,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   }
   tcgen05_before_sync();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 256);
+  if (warp == 1) tmem_dealloc(tmem, kSwSlots * kSlotCols);
 }
 
 // =================================================================================================
@@ -885,7 +920,8 @@ constexpr size_t kHdrBytes = 1024;   // keeps the operand arrays 1024-B aligned 
 inline int npad_of(int N) { return (N + 127) / 128 * 128; }
 inline int dpad_of(int D) { return (D + 63) / 64 * 64; }
 size_t operand_bytes(int B, int N, int D) { return align_up((size_t)B * npad_of(N) * dpad_of(D) * 2, 1024); }
-size_t stats_bytes(int B, int N) { return align_up((size_t)kNumStats * B * N * sizeof(float), 128); }
+// kNumStats planes of row statistics + kMaxSplits planes of P1's per-split partial n_i
+size_t stats_bytes(int B, int N) { return align_up((size_t)(kNumStats + kMaxSplits) * B * N * sizeof(float), 128); }
 TcState carve(void* state, int B, int N, int D, int has_teacher) {
   char* p = reinterpret_cast<char*>(state);
   TcState s;
@@ -981,6 +1017,16 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   SweepParams sp;
   sp.N = N; sp.Npad = Npad; sp.KC = KC; sp.has_teacher = p.has_teacher;
   sp.splits = pick_splits(Npad / 128, B);
+  // P0 / P1: 256-row tiles when the sample has at least two 128-row blocks, and as many column splits (<= 8,
+  // at least one 64-column sub-tile each) as fit one wave of SMs
+  const int rt01 = Npad / 128 >= 2 ? 2 : 1;
+  const int rb01 = (Npad / 128 + rt01 - 1) / rt01;
+  int splits01 = sm_count() / (rb01 * B);
+  if (splits01 > kMaxSplits) splits01 = kMaxSplits;
+  if (splits01 > (N + 63) / 64) splits01 = (N + 63) / 64;
+  if (splits01 < 1) splits01 = 1;
+  sp.splits1 = splits01;
+  sp.npart = s.stats + (size_t)kNumStats * plane;
   sp.sc = p.sc;
   sp.c1 = p.sc.inv_tau * kLog2e;
   sp.inv_rows = (float)p.inv_rows;
@@ -994,15 +1040,20 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   sp.ticket = ws.ticket; sp.partials = ws.partials; sp.sums_out = a.sums_out; sp.loss_out = a.loss_out;
   // >= 120 KB of dynamic smem also pins one CTA per SM
   size_t smem = (size_t)KC * kChunk128 + (size_t)kSwStages * KC * kChunk64 + sizeof(SweepMisc);
+  size_t smem01 = rt01 == 2 ? (size_t)2 * KC * kChunk128 + (size_t)3 * KC * kChunk64 + sizeof(SweepMisc) : smem;
   if (smem < 120 * 1024) smem = 120 * 1024;
-  static const int once = set_smem(fecl_tc_sweep_kernel<0, kBf16, kNoFocal>) |
-                          set_smem(fecl_tc_sweep_kernel<1, kBf16, kNoFocal>) |
-                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kNoFocal>) |
-                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2>) |
-                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny>);
+  if (smem01 < 120 * 1024) smem01 = 120 * 1024;
+  static const int once = set_smem(fecl_tc_sweep_kernel<0, kBf16, kNoFocal, 1>) |
+                          set_smem(fecl_tc_sweep_kernel<1, kBf16, kNoFocal, 1>) |
+                          set_smem(fecl_tc_sweep_kernel<0, kBf16, kNoFocal, 2>) |
+                          set_smem(fecl_tc_sweep_kernel<1, kBf16, kNoFocal, 2>) |
+                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kNoFocal, 1>) |
+                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2, 1>) |
+                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 1>);
   if (once) return once;
-  DYCON_REQUIRE(smem <= 227 * 1024, DYCON_ERR_UNSUPPORTED, "FeCL tensor-core fwd: %zu bytes of shared memory needed", smem);
-  dim3 grid(Npad / 128, sp.splits, B);
+  DYCON_REQUIRE(smem <= 227 * 1024 && smem01 <= 227 * 1024, DYCON_ERR_UNSUPPORTED,
+                "FeCL tensor-core fwd: %zu / %zu bytes of shared memory needed", smem, smem01);
+  dim3 grid(Npad / 128, sp.splits, B), grid01(rb01, splits01, B);
   const CUtensorMap& mapF2 = p.has_teacher ? mapF32 : mapF64;      // mode 2 walks 32-column sub-tiles with a teacher
   cudaLaunchAttribute pdl_attr[1];
   pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1015,12 +1066,22 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   cfg.attrs = pdl_attr;
   cfg.numAttrs = no_pdl ? 0 : 1;
   sp.pdl = no_pdl ? 0 : 1;
-  DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<0, kBf16, kNoFocal>, mapA, mapF64, mapT32, sp));
-  DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<1, kBf16, kNoFocal>, mapA, mapF64, mapT32, sp));
+  SweepParams sp01 = sp;             // P0 / P1 run on their own grid: 256-row tiles, up to 8 column splits
+  sp01.splits = splits01;
+  cudaLaunchConfig_t cfg01 = cfg;
+  cfg01.gridDim = grid01;
+  cfg01.dynamicSmemBytes = smem01;
+  if (rt01 == 2) {
+    DYCON_CUDA(cudaLaunchKernelEx(&cfg01, fecl_tc_sweep_kernel<0, kBf16, kNoFocal, 2>, mapA, mapF64, mapT32, sp01));
+    DYCON_CUDA(cudaLaunchKernelEx(&cfg01, fecl_tc_sweep_kernel<1, kBf16, kNoFocal, 2>, mapA, mapF64, mapT32, sp01));
+  } else {
+    DYCON_CUDA(cudaLaunchKernelEx(&cfg01, fecl_tc_sweep_kernel<0, kBf16, kNoFocal, 1>, mapA, mapF64, mapT32, sp01));
+    DYCON_CUDA(cudaLaunchKernelEx(&cfg01, fecl_tc_sweep_kernel<1, kBf16, kNoFocal, 1>, mapA, mapF64, mapT32, sp01));
+  }
   switch (focal_kind(p.sc)) {
-    case kNoFocal: DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kNoFocal>, mapA, mapF2, mapT32, sp)); break;
-    case kFocalG2: DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kFocalG2>, mapA, mapF2, mapT32, sp)); break;
-    default: DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kFocalAny>, mapA, mapF2, mapT32, sp)); break;
+    case kNoFocal: DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kNoFocal, 1>, mapA, mapF2, mapT32, sp)); break;
+    case kFocalG2: DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kFocalG2, 1>, mapA, mapF2, mapT32, sp)); break;
+    default: DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 1>, mapA, mapF2, mapT32, sp)); break;
   }
   DYCON_CUDA(cudaGetLastError());
   count_launches(4);
