@@ -217,7 +217,7 @@ struct SweepParams {
 };
 
 struct SweepMisc {
-  uint64_t a_full;
+  uint64_t a_full[8];      // one per 16 KB K chunk of the (up to two) A tiles: the first MMAs start after 16 + 32 KB
   uint64_t b_full[kSwStages], b_empty[kSwStages];
   uint64_t acc_full[kSwSlots], acc_empty[kSwSlots];
   uint32_t tmem_slot;
@@ -258,7 +258,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
-    mbar_init(&ms.a_full, 1);
+    for (int q = 0; q < 8; ++q) mbar_init(&ms.a_full[q], 1);
     for (int s = 0; s < kSwStages; ++s) mbar_init(&ms.b_full[s], 1), mbar_init(&ms.b_empty[s], 1);
     for (int a = 0; a < kSwSlots; ++a) mbar_init(&ms.acc_full[a], 1), mbar_init(&ms.acc_empty[a], kSwTeamThreads / 32);
     fence_mbar_init();
@@ -285,10 +285,12 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0 && nt > 0) {
-      mbar_expect_tx(&ms.a_full, a_bytes);
-      for (int h = 0; h < kRT; ++h)
-        for (int c = 0; c < KC; ++c)
-          tma_load_2d(sA + h * a_tile + c * kChunk128, &mapA, c * 64, b * p.Npad + i0 + h * kTM, &ms.a_full);
+      // first the K chunk the first MMA needs, then the first B sub-tile, then the rest of A
+      auto load_a = [&](int h, int c) {
+        mbar_expect_tx(&ms.a_full[h * 4 + c], kChunk128);
+        tma_load_2d(sA + h * a_tile + c * kChunk128, &mapA, c * 64, b * p.Npad + i0 + h * kTM, &ms.a_full[h * 4 + c]);
+      };
+      load_a(0, 0);
       for (int t = 0; t < nt; ++t) {
         const int s = t % kStages, row = b * p.Npad + (jt0 + t) * tcols;
         uint8_t* dst = sStage + s * stage_bytes;
@@ -297,6 +299,10 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         for (int c = 0; c < KC; ++c) {
           tma_load_2d(dst + c * kChunk64, &mapF, c * 64, row, &ms.b_full[s]);       // box: 64 rows, or 32 with a teacher
           if (teacher_on) tma_load_2d(dst + c * kChunk64 + kChunk32, &mapT, c * 64, row, &ms.b_full[s]);
+        }
+        if (t == 0) {
+          for (int h = 0; h < kRT; ++h)
+            for (int c = (h == 0 ? 1 : 0); c < KC; ++c) load_a(h, c);
         }
       }
     }
@@ -307,8 +313,8 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     if (lane == 0 && nt > 0) {
       const uint32_t idesc = umma_idesc_16(128, 64, false, false, kBf16);
       const uint64_t a_desc0 = umma_desc_kmajor(smem_u32(sA));
-      mbar_wait_relaxed(&ms.a_full, 0);
       for (int t = warp - 1; t < nt; t += 3) {
+        const bool first = t == warp - 1;         // this issuer's first sub-tile: the A chunks may still be in flight
         const int s = t % kStages, a = t & (kSwSlots - 1);
         const uint64_t b_desc0 = umma_desc_kmajor(smem_u32(sStage + s * stage_bytes));
         mbar_wait_relaxed(&ms.b_full[s], (t / kStages) & 1);
@@ -319,6 +325,10 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
           for (int c = 0; c < 4; ++c) {
             if (c < KC) {
+              if (first) {
+                mbar_wait_relaxed(&ms.a_full[h * 4 + c], 0);
+                tcgen05_after_sync();
+              }
 #pragma unroll
               for (int k = 0; k < 4; ++k)
                 umma_bf16(tmem + a * kSlotCols + h * 64, desc_advance(a_desc0, h * a_tile + c * kChunk128 + k * 32),
@@ -583,7 +593,7 @@ struct BwdParams {
 };
 
 struct BwdMisc {
-  uint64_t a_full;
+  uint64_t a_full[4];      // one per 16 KB K chunk of the A tile
   uint64_t b_full[kBwdStages], b_empty[kBwdStages];
   uint64_t sc_full[2], sc_empty[2];      // per team: S / CS accumulators of its sub-tile
   uint64_t h_full[2], h_free[2];         // per team: its column half of sH / sG
@@ -662,7 +672,7 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
-    mbar_init(&ms.a_full, 1);
+    for (int q = 0; q < 4; ++q) mbar_init(&ms.a_full[q], 1);
     for (int s = 0; s < kBwdStages; ++s) {
       mbar_init(&ms.b_full[s], 1);
       mbar_init(&ms.b_empty[s], 1);
@@ -690,8 +700,11 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   if (warp == 0) {
     // ================================ TMA producer ================================
     if (lane == 0 && nt > 0) {
-      mbar_expect_tx(&ms.a_full, a_bytes);
-      for (int c = 0; c < KC; ++c) tma_load_2d(sA + c * kChunk128, &mapA, c * 64, b * p.Npad + i0, &ms.a_full);
+      auto load_a = [&](int c) {
+        mbar_expect_tx(&ms.a_full[c], kChunk128);
+        tma_load_2d(sA + c * kChunk128, &mapA, c * 64, b * p.Npad + i0, &ms.a_full[c]);
+      };
+      load_a(0);
       for (int t = 0; t < nt; ++t) {
         const int s = t % kBwdStages, row = b * p.Npad + (t0 + t) * 32;
         uint8_t* dst = sStage + s * stage_bytes;
@@ -701,6 +714,9 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           tma_load_2d(dst + c * kChunk64, &mapF, c * 64, row, &ms.b_full[s]);
           if (teacher) tma_load_2d(dst + c * kChunk64 + kChunk32, &mapT, c * 64, row, &ms.b_full[s]);
         }
+        if (t == 0) {
+          for (int c = 1; c < KC; ++c) load_a(c);
+        }
       }
     }
   } else if (warp == 1 || warp == 3) {
@@ -709,8 +725,8 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       // one MMA per K step computes S | CS side by side (N = 64: the F and T rows of a chunk are contiguous)
       const uint32_t idesc_s = umma_idesc_16(128, teacher ? 64 : 32, false, false, kBf16);
       const uint64_t a_desc0 = umma_desc_kmajor(smem_u32(sA));
-      mbar_wait_relaxed(&ms.a_full, 0);
       for (int t = warp >> 1; t < nt; t += 2) {
+        const bool first = t == (warp >> 1);      // this issuer's first sub-tile: the A chunks may still be in flight
         const int s = t % kBwdStages, g = t & 1;
         const uint64_t b_desc0 = umma_desc_kmajor(smem_u32(sStage + s * stage_bytes));
         mbar_wait_relaxed(&ms.b_full[s], (t / kBwdStages) & 1);
@@ -719,6 +735,10 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           if (c < KC) {
+            if (first) {
+              mbar_wait_relaxed(&ms.a_full[c], 0);
+              tcgen05_after_sync();
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k)
               umma_bf16(tm_sc + g * 64, desc_advance(a_desc0, c * kChunk128 + k * 32),
