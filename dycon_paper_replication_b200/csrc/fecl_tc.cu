@@ -197,6 +197,7 @@ struct SweepParams {
   int splits;          // column splits: grid.y CTAs share a row block, each sweeps 1/splits of the sub-tiles
   int splits1;         // the split count of the P1 launch (P2 adds up that many partial n_i per row)
   float* npart;        // kMaxSplits planes of B*N floats: P1's per-split partial n_i (summed in split order by P2)
+  float* apart;        // kMaxSplits planes: P2's per-split partial A_i (summed in split order by the backward)
   FeclScalars sc;
   float c1;            // inv_tau * log2(e)
   float inv_rows;
@@ -208,7 +209,6 @@ struct SweepParams {
   float* stat_m;       // zero-filled before the sweeps; split CTAs combine with atomicMax / atomicAdd (<= 2
   float* stat_p;       // contributors per address, so the float sums are order-independent: a+b == b+a)
   float* stat_n;
-  float* stat_a;
   float* stat_kappa;
   unsigned int* ticket;
   double* partials;
@@ -231,10 +231,11 @@ struct SweepMisc {
 // Grid (row blocks, column splits, samples).  Three launches instead of one fused sweep: n_i needs all m_k
 // and d_ij needs the complete n_i, i.e. two grid-wide dependencies, and splitting the columns of a row
 // block over several CTAs (so that small batches still fill 148 SMs) adds a third.
-// kRT = row tiles per CTA.  P0 / P1 have almost no epilogue work and are bound by the TMA delivery of the B
-// operand (~30 B/clk/SM): with kRT = 2 a CTA keeps TWO 128-row A tiles resident and every B sub-tile feeds two
-// MMAs, which halves the operand bytes per flop (ring of 3 stages, 128 TMEM columns per sub-tile; an epilogue
-// thread then owns one of 256 rows and all 64 columns).  P2 is epilogue bound and stays at kRT = 1.
+// kRT = row tiles per CTA.  With kRT = 2 a CTA keeps TWO 128-row A tiles resident and every B sub-tile feeds
+// two MMAs (ring of 3 stages, 128 TMEM columns per sub-tile; an epilogue thread then owns one of 256 rows and
+// all columns of the sub-tile).  That halves the operand bytes per flop for P0 / P1, and -- what matters for
+// the epilogue-bound P2 -- it lets the grid be (row blocks / 2) x (up to 8 column splits): 140 of the 148 SMs
+// at the BraTS19 shape instead of the 112 that 128-row blocks x 2 splits reach.
 template <int kMode, bool kBf16, int kFocal, int kRT>
 __global__ void __launch_bounds__(kSwThreads, 1)
 fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapF,
@@ -242,7 +243,6 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KC = p.KC;
-  static_assert(kRT == 1 || kMode != 2, "the 256-row tile is for P0 / P1");
   constexpr int kStages = kRT == 2 ? 3 : kSwStages;
   constexpr int kSlotCols = 64 * kRT;
   const uint32_t a_tile = (uint32_t)KC * kChunk128, a_bytes = a_tile * kRT, stage_bytes = (uint32_t)KC * kChunk64;
@@ -265,7 +265,10 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     prefetch_tmap(&mapA);
     prefetch_tmap(&mapF);
     if (teacher_on) prefetch_tmap(&mapT);
-    if (kMode == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) p.hdr[0] = p.hscale;
+    if (kMode == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+      p.hdr[0] = p.hscale;
+      p.hdr[1] = (float)p.splits;       // how many partial A_i planes the backward has to add up
+    }
   }
   if (warp == 1) tmem_alloc(&ms.tmem_slot, kSwSlots * kSlotCols);
   tcgen05_before_sync();
@@ -379,12 +382,20 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     if (kMode == 2) {
       // n_i = the P1 launch's per-split partial sums, added in split order (deterministic for any split count);
       // the total is also what the backward reads
-      for (int q = 0; q < p.splits1; ++q) n_row += __ldg(p.npart + (size_t)q * gridDim.z * p.N + g);
-      if (split == 0 && team == 0 && chalf == 0 && row_ok) p.stat_n[g] = n_row;
+      {
+        float part[kMaxSplits];
+#pragma unroll
+        for (int q = 0; q < kMaxSplits; ++q)        // all loads in flight at once
+          part[q] = q < p.splits1 ? __ldg(p.npart + (size_t)q * gridDim.z * p.N + g) : 0.f;
+#pragma unroll
+        for (int q = 0; q < kMaxSplits; ++q) n_row += part[q];
+      }
+      const bool row_writer = split == 0 && team == 0 && (kRT == 2 || chalf == 0) && row_ok;   // one thread per row
+      if (row_writer) p.stat_n[g] = n_row;
       // kappa_i = r_i c_i / (B N),  c_i = 1/(P_i - 1 + 1e-18)   (dycon_losses.py:192; P from the P1 launch)
       const float rw = p.row_weight ? __ldg(p.row_weight + g) : 1.f;
       kappa = rw / ((__ldg(p.stat_p + g) - 1.f) + kTiny) * p.inv_rows;
-      if (split == 0 && team == 0 && chalf == 0 && row_ok) p.stat_kappa[g] = kappa;
+      if (row_writer) p.stat_kappa[g] = kappa;
     }
 
     if (team < nt) publish(0, fetch(jt0 + team));
@@ -456,44 +467,51 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           }
         }
       } else {
-        // teacher mode (kMode == 2): 16 columns of S and the same 16 columns of CS
-        const float* cy = &ms.col[team][slot][0][cbase];
-        const float* cm = &ms.col[team][slot][1][cbase];
-        const int rdiag = i - j0 - cbase;         // chunk-local column of the diagonal pair, if in range
-        float v[16], w[16];
-        tmem_ld16(tmem + lane_base + a * 64 + cbase, v);
-        tmem_ld16(tmem + lane_base + a * 64 + 32 + cbase, w);
-        tmem_ld_wait();
-        tcgen05_before_sync();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&ms.acc_empty[a]);
-        const int w0 = i0 + quarter * 32 - j0 - cbase;
-        const bool diag_here = w0 + 31 >= 0 && w0 < 16;
-        float cprod = 1.f;         // product of (1 - cs) over this chunk's hard negatives: one log per 16 pairs
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
-          const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
-          const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int c = q * 4 + k;
-            const float tl = fmaf(v[c], p.c1, -m2[k]);
-            float phi2, at;
-            pos_fwd<kFocal>(tl, ex2_approx(tl), n_row, p.sc.gamma, phi2, at);
-            const bool same = ys[k] == yi;
-            const bool pos = diag_here ? same && (c != rdiag) : same;
-            acc0 += pos ? phi2 : 0.f;
-            acc1 += pos ? at : 0.f;
-            // cross term: -log(1 - cs + 1e-18) over labels differ && cs > thresh (dycon_losses.py:217-229);
-            // ordered != so that padding (y = NaN) is never a hard negative
-            const float cs = w[c];
-            const bool hard = (ys[k] < yi || ys[k] > yi) && cs > p.sc.cross_thresh;
-            cprod *= hard ? (1.f - cs) + kTiny : 1.f;
-            acc3 += hard ? 1.f : 0.f;
+        // teacher mode (kMode == 2): chunks of 16 columns of S and the same 16 columns of CS (kRT = 1: one chunk,
+        // this warp group's half of the 32-column sub-tile; kRT = 2: both halves, one after the other)
+#pragma unroll 1
+        for (int ch = 0; ch < kRT; ++ch) {
+          const int cb = kRT == 2 ? ch * 16 : cbase;
+          const float* cy = &ms.col[team][slot][0][cb];
+          const float* cm = &ms.col[team][slot][1][cb];
+          const int rdiag = i - j0 - cb;          // chunk-local column of the diagonal pair, if in range
+          float v[16], w[16];
+          tmem_ld16(tmem + lane_base + a * kSlotCols + rh * 64 + cb, v);
+          tmem_ld16(tmem + lane_base + a * kSlotCols + rh * 64 + 32 + cb, w);
+          tmem_ld_wait();
+          if (ch == kRT - 1) {
+            tcgen05_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&ms.acc_empty[a]);
           }
+          const int w0 = i0 + rh * kTM + quarter * 32 - j0 - cb;
+          const bool diag_here = w0 + 31 >= 0 && w0 < 16;
+          float cprod = 1.f;       // product of (1 - cs) over this chunk's hard negatives: one log per 16 pairs
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
+            const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
+            const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              const int c = q * 4 + k;
+              const float tl = fmaf(v[c], p.c1, -m2[k]);
+              float phi2, at;
+              pos_fwd<kFocal>(tl, ex2_approx(tl), n_row, p.sc.gamma, phi2, at);
+              const bool same = ys[k] == yi;
+              const bool pos = diag_here ? same && (c != rdiag) : same;
+              acc0 += pos ? phi2 : 0.f;
+              acc1 += pos ? at : 0.f;
+              // cross term: -log(1 - cs + 1e-18) over labels differ && cs > thresh (dycon_losses.py:217-229);
+              // ordered != so that padding (y = NaN) is never a hard negative
+              const float cs = w[c];
+              const bool hard = (ys[k] < yi || ys[k] > yi) && cs > p.sc.cross_thresh;
+              cprod *= hard ? (1.f - cs) + kTiny : 1.f;
+              acc3 += hard ? 1.f : 0.f;
+            }
+          }
+          acc2 += lg2_approx(cprod);     // NaN for cs > 1, like the reference's log of a negative number
         }
-        acc2 += lg2_approx(cprod);       // NaN for cs > 1, like the reference's log of a negative number
       }
       publish(slot ^ 1, nxt);
       sw_team_barrier(team);
@@ -522,7 +540,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           p.npart[(size_t)split * gridDim.z * p.N + g] = acc0;           // summed in split order by P2 (deterministic)
           atomicAdd(p.stat_p + g, acc1);                                  // integer-valued: exact in any order
         } else {
-          atomicAdd(p.stat_a + g, acc1);
+          p.apart[(size_t)split * gridDim.z * p.N + g] = acc1;           // summed in split order by the backward
           red[0] = (double)(kappa * (-kLn2 * acc0));                      // kappa_i = r_i c_i inv_rows
           red[1] = (double)(-kLn2 * acc2);
           red[2] = (double)acc3;
@@ -583,7 +601,7 @@ struct BwdParams {
   const float* labels;
   const float* stat_m;
   const float* stat_n;
-  const float* stat_a;
+  const float* apart;  // P2's per-split partial A_i (hdr[1] planes of B*N floats)
   const float* stat_kappa;
   const float* hdr;
   const double* cross_cnt;
@@ -791,7 +809,19 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const float m2i = __ldg(p.stat_m + off + ic) * kLog2e;
     const float ni = __ldg(p.stat_n + off + ic);
     const float ki = row_ok ? __ldg(p.stat_kappa + off + ic) * h_mul : 0.f;
-    const float Pi = -ki * __ldg(p.stat_a + off + ic);
+    const size_t bn = (size_t)gridDim.z * p.N;      // plane stride of the statistics
+    const int splits2 = (int)__ldg(p.hdr + 1);
+    auto a_of = [&](size_t g) {                     // A = P2's per-split partials, added in split order
+      float part[kMaxSplits];
+#pragma unroll
+      for (int q = 0; q < kMaxSplits; ++q)          // all loads in flight at once (one L2 round trip, not eight)
+        part[q] = q < splits2 ? __ldg(p.apart + (size_t)q * bn + g) : 0.f;
+      float acc = part[0];
+#pragma unroll
+      for (int q = 1; q < kMaxSplits; ++q) acc += part[q];
+      return acc;
+    };
+    const float Pi = -ki * a_of(off + ic);
     const float gcs = (teacher && row_ok) ? hscale * p.sc.lambda_cross / ((float)(*p.cross_cnt) + kTiny) : 0.f;
     const float gl = p.sc.gamma * kLn2;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
@@ -809,7 +839,7 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       if (st == 1) return __ldg(p.stat_m + g) * kLog2e;
       if (st == 2) return __ldg(p.stat_n + g);
       const float kh = __ldg(p.stat_kappa + g) * h_mul;
-      return st == 3 ? -kh * __ldg(p.stat_a + g) : kh;
+      return st == 3 ? -kh * a_of(g) : kh;
     };
     auto publish = [&](int slot, float v) {
       if (tt < 160) ms.col[team][slot][tt >> 5][tt & 31] = v;
@@ -940,8 +970,8 @@ constexpr size_t kHdrBytes = 1024;   // keeps the operand arrays 1024-B aligned 
 inline int npad_of(int N) { return (N + 127) / 128 * 128; }
 inline int dpad_of(int D) { return (D + 63) / 64 * 64; }
 size_t operand_bytes(int B, int N, int D) { return align_up((size_t)B * npad_of(N) * dpad_of(D) * 2, 1024); }
-// kNumStats planes of row statistics + kMaxSplits planes of P1's per-split partial n_i
-size_t stats_bytes(int B, int N) { return align_up((size_t)(kNumStats + kMaxSplits) * B * N * sizeof(float), 128); }
+// kNumStats planes of row statistics + kMaxSplits planes each of P1's partial n_i and P2's partial A_i
+size_t stats_bytes(int B, int N) { return align_up((size_t)(kNumStats + 2 * kMaxSplits) * B * N * sizeof(float), 128); }
 TcState carve(void* state, int B, int N, int D, int has_teacher) {
   char* p = reinterpret_cast<char*>(state);
   TcState s;
@@ -1036,17 +1066,18 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   ReduceWorkspace ws = carve_reduce_workspace(a.workspace);
   SweepParams sp;
   sp.N = N; sp.Npad = Npad; sp.KC = KC; sp.has_teacher = p.has_teacher;
-  sp.splits = pick_splits(Npad / 128, B);
-  // P0 / P1: 256-row tiles when the sample has at least two 128-row blocks, and as many column splits (<= 8,
-  // at least one 64-column sub-tile each) as fit one wave of SMs
+  // all three sweeps: 256-row tiles when the sample has at least two 128-row blocks, and as many column splits
+  // (<= 8, at least one 64-column sub-tile each) as fit one wave of SMs
   const int rt01 = Npad / 128 >= 2 ? 2 : 1;
   const int rb01 = (Npad / 128 + rt01 - 1) / rt01;
   int splits01 = sm_count() / (rb01 * B);
   if (splits01 > kMaxSplits) splits01 = kMaxSplits;
   if (splits01 > (N + 63) / 64) splits01 = (N + 63) / 64;
   if (splits01 < 1) splits01 = 1;
+  sp.splits = splits01;
   sp.splits1 = splits01;
   sp.npart = s.stats + (size_t)kNumStats * plane;
+  sp.apart = s.stats + (size_t)(kNumStats + kMaxSplits) * plane;
   sp.sc = p.sc;
   sp.c1 = p.sc.inv_tau * kLog2e;
   sp.inv_rows = (float)p.inv_rows;
@@ -1055,25 +1086,26 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   sp.hdr = s.hdr;
   sp.labels = a.labels; sp.row_weight = a.row_weight;
   sp.stat_m = s.stats + kStatM * plane; sp.stat_n = s.stats + kStatN * plane;
-  sp.stat_a = s.stats + kStatA * plane; sp.stat_kappa = s.stats + kStatKappa * plane;
+  sp.stat_kappa = s.stats + kStatKappa * plane;
   sp.stat_p = s.stats + kStatP * plane;
   sp.ticket = ws.ticket; sp.partials = ws.partials; sp.sums_out = a.sums_out; sp.loss_out = a.loss_out;
   // >= 120 KB of dynamic smem also pins one CTA per SM
-  size_t smem = (size_t)KC * kChunk128 + (size_t)kSwStages * KC * kChunk64 + sizeof(SweepMisc);
-  size_t smem01 = rt01 == 2 ? (size_t)2 * KC * kChunk128 + (size_t)3 * KC * kChunk64 + sizeof(SweepMisc) : smem;
+  size_t smem = rt01 == 2 ? (size_t)2 * KC * kChunk128 + (size_t)3 * KC * kChunk64 + sizeof(SweepMisc)
+                          : (size_t)KC * kChunk128 + (size_t)kSwStages * KC * kChunk64 + sizeof(SweepMisc);
   if (smem < 120 * 1024) smem = 120 * 1024;
-  if (smem01 < 120 * 1024) smem01 = 120 * 1024;
   static const int once = set_smem(fecl_tc_sweep_kernel<0, kBf16, kNoFocal, 1>) |
                           set_smem(fecl_tc_sweep_kernel<1, kBf16, kNoFocal, 1>) |
-                          set_smem(fecl_tc_sweep_kernel<0, kBf16, kNoFocal, 2>) |
-                          set_smem(fecl_tc_sweep_kernel<1, kBf16, kNoFocal, 2>) |
                           set_smem(fecl_tc_sweep_kernel<2, kBf16, kNoFocal, 1>) |
                           set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2, 1>) |
-                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 1>);
+                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 1>) |
+                          set_smem(fecl_tc_sweep_kernel<0, kBf16, kNoFocal, 2>) |
+                          set_smem(fecl_tc_sweep_kernel<1, kBf16, kNoFocal, 2>) |
+                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kNoFocal, 2>) |
+                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2, 2>) |
+                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 2>);
   if (once) return once;
-  DYCON_REQUIRE(smem <= 227 * 1024 && smem01 <= 227 * 1024, DYCON_ERR_UNSUPPORTED,
-                "FeCL tensor-core fwd: %zu / %zu bytes of shared memory needed", smem, smem01);
-  dim3 grid(Npad / 128, sp.splits, B), grid01(rb01, splits01, B);
+  DYCON_REQUIRE(smem <= 227 * 1024, DYCON_ERR_UNSUPPORTED, "FeCL tensor-core fwd: %zu bytes of shared memory needed", smem);
+  dim3 grid(rb01, splits01, B);
   const CUtensorMap& mapF2 = p.has_teacher ? mapF32 : mapF64;      // mode 2 walks 32-column sub-tiles with a teacher
   cudaLaunchAttribute pdl_attr[1];
   pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -1086,23 +1118,20 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   cfg.attrs = pdl_attr;
   cfg.numAttrs = no_pdl ? 0 : 1;
   sp.pdl = no_pdl ? 0 : 1;
-  SweepParams sp01 = sp;             // P0 / P1 run on their own grid: 256-row tiles, up to 8 column splits
-  sp01.splits = splits01;
-  cudaLaunchConfig_t cfg01 = cfg;
-  cfg01.gridDim = grid01;
-  cfg01.dynamicSmemBytes = smem01;
-  if (rt01 == 2) {
-    DYCON_CUDA(cudaLaunchKernelEx(&cfg01, fecl_tc_sweep_kernel<0, kBf16, kNoFocal, 2>, mapA, mapF64, mapT32, sp01));
-    DYCON_CUDA(cudaLaunchKernelEx(&cfg01, fecl_tc_sweep_kernel<1, kBf16, kNoFocal, 2>, mapA, mapF64, mapT32, sp01));
-  } else {
-    DYCON_CUDA(cudaLaunchKernelEx(&cfg01, fecl_tc_sweep_kernel<0, kBf16, kNoFocal, 1>, mapA, mapF64, mapT32, sp01));
-    DYCON_CUDA(cudaLaunchKernelEx(&cfg01, fecl_tc_sweep_kernel<1, kBf16, kNoFocal, 1>, mapA, mapF64, mapT32, sp01));
-  }
-  switch (focal_kind(p.sc)) {
-    case kNoFocal: DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kNoFocal, 1>, mapA, mapF2, mapT32, sp)); break;
-    case kFocalG2: DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kFocalG2, 1>, mapA, mapF2, mapT32, sp)); break;
-    default: DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 1>, mapA, mapF2, mapT32, sp)); break;
-  }
+  const int fk = focal_kind(p.sc);
+#define DYCON_SWEEPS(RT)                                                                                             \
+  do {                                                                                                               \
+    DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<0, kBf16, kNoFocal, RT>, mapA, mapF64, mapT32, sp));     \
+    DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<1, kBf16, kNoFocal, RT>, mapA, mapF64, mapT32, sp));     \
+    if (fk == kNoFocal)                                                                                              \
+      DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kNoFocal, RT>, mapA, mapF2, mapT32, sp));    \
+    else if (fk == kFocalG2)                                                                                         \
+      DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kFocalG2, RT>, mapA, mapF2, mapT32, sp));    \
+    else                                                                                                             \
+      DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kFocalAny, RT>, mapA, mapF2, mapT32, sp));   \
+  } while (0)
+  if (rt01 == 2) DYCON_SWEEPS(2); else DYCON_SWEEPS(1);
+#undef DYCON_SWEEPS
   DYCON_CUDA(cudaGetLastError());
   count_launches(4);
   return DYCON_OK;
@@ -1127,7 +1156,8 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
   bp.c1 = p.sc.inv_tau * kLog2e;
   bp.labels = a.labels;
   bp.stat_m = s.stats + kStatM * plane; bp.stat_n = s.stats + kStatN * plane;
-  bp.stat_a = s.stats + kStatA * plane; bp.stat_kappa = s.stats + kStatKappa * plane;
+  bp.apart = s.stats + (size_t)(kNumStats + kMaxSplits) * plane;
+  bp.stat_kappa = s.stats + kStatKappa * plane;
   bp.hdr = s.hdr;
   bp.cross_cnt = a.cross_cnt; bp.grad_out = a.grad_out; bp.grad_feat = a.grad_feat;
   bp.g_sb = a.g_sb; bp.g_sn = a.g_sn; bp.g_sd = a.g_sd;
