@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--global-negatives", action="store_true",
+                    help="BASELINE config 5: FeCL contrasts every row against the rows of all samples of all ranks")
     return ap.parse_args()
 
 
@@ -284,7 +286,8 @@ def run_ours(args):
     n_gpus = world
     precision = args.precision or dycon_losses.default_fecl_precision()
     gb = args.batch * world
-    fecl = FeCLoss(dev, precision=precision, process_group=group, global_batch=gb if world > 1 else None, **CTOR)
+    fecl = FeCLoss(dev, precision=precision, process_group=group, global_batch=gb if world > 1 else None,
+                   cross_gpu_negatives=args.global_negatives, **CTOR)
     uncl = UnCLoss(process_group=group, global_batch=gb if world > 1 else None)
 
     # rotating input sets, resident in HBM before the timed region (different seeds per rank and set)
@@ -368,7 +371,7 @@ def run_ours(args):
     # (rotating input sets, queued behind a GPU-side sleep) between ONE pair of events -- the average launch
     # duration without the ~2-4 us that an event pair around a single short call adds.  This is the figure the
     # roofline uses; the single-call figures are kept beside it.
-    fam_ms = family_times(torch, _lib, dev, sets, precision, BETA)
+    fam_ms = {} if args.global_negatives else family_times(torch, _lib, dev, sets, precision, BETA)
     if world > 1:
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -498,8 +501,9 @@ def run_ours(args):
     single = {k: statistics.median(v) for k, v in calls.items()}
     avg = dict(single)
     avg.update(fam_ms)
-    flops_fwd = 4.0 * B * N * N * D            # S (2) + cross (2)         SURVEY.md 8(d)
-    flops_bwd = 6.0 * B * N * N * D            # (G+G^T)F (4) + Gc T (2)
+    pairs = float(B * N) * (B * N * world) if args.global_negatives else float(B) * N * N     # (i, j) pairs per rank
+    flops_fwd = 4.0 * pairs * D                # S (2) + cross (2)         SURVEY.md 8(d)
+    flops_bwd = 6.0 * pairs * D                # (G+G^T)F (4) + Gc T (2)
     of = pk["source"]
     fam = {
         "uncl_fwd": {"bound": "hbm", "algorithmic": 16.0 * voxels, "moved": 20.0 * voxels},
@@ -551,7 +555,9 @@ def run_ours(args):
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32" if precision == "fp32" else f"{precision} MMA operands, f32 accumulate/epilogue",
             "data": "synthetic",
-            "config": {"workload": workload_name(args, n_gpus), "fecl_precision": precision,
+            "config": {"workload": workload_name(args, n_gpus) + (", FeCL with global negatives (extension)"
+                                                                   if args.global_negatives else ""),
+                       "fecl_precision": precision,
                        "l2": f"rotating {args.sets} input sets of {set_bytes / 1e6:.0f} MB each (> 126 MB L2), no flush",
                        "launch": "CUDA-graph replay of the step (one graph per input set)" if use_graph else "eager",
                        "loss_check": final_loss},

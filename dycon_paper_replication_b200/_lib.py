@@ -41,6 +41,12 @@ PROTOTYPES = {
     "dycon_fecl_fwd": (_i, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, _p, _i, _i, _i,
                             _f, _f, _i, _f, _f, _d, _i, _p, _sz, _p, _p, _p, _sz, _p]),
     "dycon_fecl_bwd": (_i, [_p, _sz, _p, _i, _i, _i, _i, _f, _f, _i, _i, _f, _f, _i, _p, _p, _p, _i64, _i64, _i64, _p]),
+    "dycon_fecl_gn_state_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "dycon_fecl_gn_layout": (_i, [_i, _i, _i, _i, _i, _p]),
+    "dycon_fecl_gn_fwd": (_i, [_i, _p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, _p, _i, _i, _i, _f, _f, _i, _f, _f,
+                               _i, _p, _sz, _i, _i, _p, _p, _sz, _p]),
+    "dycon_fecl_gn_bwd": (_i, [_p, _sz, _p, _i, _i, _i, _i, _f, _f, _i, _i, _f, _f, _i, _i, _i, _p, _p, _p,
+                               _i64, _i64, _i64, _p]),
     "dycon_ema_multi": (_i, [_p, _p, _p, _i, _f, _f, _p]),
     "dycon_exchange_inbox_bytes": (_sz, []),
     "dycon_exchange_enable_peer": (_i, [_i]),

@@ -72,4 +72,78 @@ int dycon_fecl_bwd(const void* state, size_t state_bytes, const float* labels, i
   return precision != DYCON_FECL_FP32 ? fecl_tc_bwd(p, a, as_stream(stream)) : fecl_simt_bwd(p, a, as_stream(stream));
 }
 
+// ---- global negatives: the merged batch as ONE sample, rows split over ranks (include/dycon_b200.h) -------
+size_t dycon_fecl_gn_state_bytes(int B_all, int N, int D, int has_teacher, int precision) {
+  if (B_all <= 0 || N <= 0 || D <= 0 || precision == DYCON_FECL_FP32) return 0;
+  return fecl_tc_state_bytes(1, B_all * N, D, has_teacher);
+}
+
+int dycon_fecl_gn_layout(int B_all, int N, int D, int has_teacher, int precision, size_t* out6) {
+  DYCON_REQUIRE(out6 && B_all > 0 && N > 0 && D > 0, DYCON_ERR_ARG, "FeCL gn layout: bad arguments");
+  DYCON_REQUIRE(precision == DYCON_FECL_BF16 || precision == DYCON_FECL_FP16, DYCON_ERR_UNSUPPORTED,
+                "FeCL global negatives run on the tensor-core path only (precision fp16 / bf16)");
+  fecl_tc_layout(1, B_all * N, D, has_teacher, out6);
+  return DYCON_OK;
+}
+
+int dycon_fecl_gn_fwd(int phase_mask, const float* feat_all, int64_t f_sb, int64_t f_sn, int64_t f_sd,
+                      const float* teacher_all, int64_t t_sb, int64_t t_sn, int64_t t_sd, const float* labels_all,
+                      const float* row_weight_all, int B_all, int N, int D, float inv_tau, float gamma, int use_focal,
+                      float cross_thresh, float lambda_cross, int precision, void* state, size_t state_bytes,
+                      int row_lo, int row_hi, double* sums_out, void* workspace, size_t workspace_bytes,
+                      dycon_stream_t stream) {
+  if (int rc = check_shape(B_all, N, D, precision)) return rc;
+  DYCON_REQUIRE(precision == DYCON_FECL_BF16 || precision == DYCON_FECL_FP16, DYCON_ERR_UNSUPPORTED,
+                "FeCL global negatives run on the tensor-core path only (precision fp16 / bf16)");
+  const long long M = (long long)B_all * N;
+  DYCON_REQUIRE(M < (1LL << 30), DYCON_ERR_UNSUPPORTED, "FeCL gn: %lld merged rows", M);
+  DYCON_REQUIRE(phase_mask > 0 && phase_mask < 16, DYCON_ERR_ARG, "FeCL gn: phase_mask=%d", phase_mask);
+  DYCON_REQUIRE(0 <= row_lo && row_lo < row_hi && row_hi <= M, DYCON_ERR_ARG, "FeCL gn: rows [%d, %d) of %lld", row_lo,
+                row_hi, M);
+  DYCON_REQUIRE(feat_all && labels_all && state && workspace && ((phase_mask & 8) == 0 || sums_out), DYCON_ERR_ARG,
+                "FeCL gn fwd: NULL feat/labels/state/workspace/sums_out");
+  DYCON_REQUIRE(aligned(state, 128) && aligned(sums_out, 8) && aligned(workspace, 16), DYCON_ERR_ARG,
+                "FeCL gn fwd: misaligned pointer");
+  const int has_teacher = teacher_all != nullptr;
+  DYCON_REQUIRE(state_bytes >= dycon_fecl_gn_state_bytes(B_all, N, D, has_teacher, precision), DYCON_ERR_WORKSPACE,
+                "FeCL gn fwd: state %zu < %zu bytes", state_bytes,
+                dycon_fecl_gn_state_bytes(B_all, N, D, has_teacher, precision));
+  DYCON_REQUIRE(workspace_bytes >= fecl_tc_workspace_bytes(1, (int)M, D), DYCON_ERR_WORKSPACE,
+                "FeCL gn fwd: workspace too small");
+  FeclProblem p{1, (int)M, D, has_teacher,
+                FeclScalars{inv_tau, gamma, cross_thresh, lambda_cross, (use_focal && row_weight_all == nullptr) ? 1 : 0},
+                1.0 / (double)M, precision};
+  FeclFwdArgs a{feat_all, f_sb, f_sn, f_sd, teacher_all, t_sb, t_sn, t_sd, labels_all, row_weight_all, state, sums_out,
+                nullptr, workspace};
+  a.merge_B = B_all;
+  a.phase_mask = phase_mask;
+  a.row_lo = row_lo;
+  a.row_hi = row_hi;
+  return fecl_tc_fwd(p, a, as_stream(stream));
+}
+
+int dycon_fecl_gn_bwd(const void* state, size_t state_bytes, const float* labels_all, int B_all, int N, int D,
+                      int has_teacher, float inv_tau, float gamma, int use_focal, int has_row_weight, float cross_thresh,
+                      float lambda_cross, int precision, int row_lo, int row_hi, const double* cross_cnt,
+                      const float* grad_out, float* grad_feat, int64_t g_sb, int64_t g_sn, int64_t g_sd,
+                      dycon_stream_t stream) {
+  if (int rc = check_shape(B_all, N, D, precision)) return rc;
+  DYCON_REQUIRE(precision == DYCON_FECL_BF16 || precision == DYCON_FECL_FP16, DYCON_ERR_UNSUPPORTED,
+                "FeCL global negatives run on the tensor-core path only (precision fp16 / bf16)");
+  const long long M = (long long)B_all * N;
+  DYCON_REQUIRE(0 <= row_lo && row_lo < row_hi && row_hi <= M && (row_hi - row_lo) % N == 0, DYCON_ERR_ARG,
+                "FeCL gn bwd: rows [%d, %d) must be whole samples of %d rows", row_lo, row_hi, N);
+  DYCON_REQUIRE(state && labels_all && grad_out && grad_feat && (!has_teacher || cross_cnt), DYCON_ERR_ARG,
+                "FeCL gn bwd: NULL argument");
+  DYCON_REQUIRE(state_bytes >= dycon_fecl_gn_state_bytes(B_all, N, D, has_teacher, precision), DYCON_ERR_WORKSPACE,
+                "FeCL gn bwd: state too small");
+  FeclProblem p{1, (int)M, D, has_teacher ? 1 : 0,
+                FeclScalars{inv_tau, gamma, cross_thresh, lambda_cross, (use_focal && !has_row_weight) ? 1 : 0}, 0.0, precision};
+  FeclBwdArgs a{state, labels_all, cross_cnt, grad_out, grad_feat, g_sb, g_sn, g_sd};
+  a.row_lo = row_lo;
+  a.row_hi = row_hi;
+  a.grad_rows = N;
+  return fecl_tc_bwd(p, a, as_stream(stream));
+}
+
 }  // extern "C"

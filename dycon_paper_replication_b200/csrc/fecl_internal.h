@@ -25,6 +25,12 @@ struct FeclFwdArgs {
   double* sums_out;
   float* loss_out;
   void* workspace;
+  // global-negatives mode (tensor-core path only): feat / teacher / labels hold merge_B samples of N / merge_B
+  // rows that are contrasted as ONE sample of N rows; this call runs the phases in phase_mask (1 pack, 2 P0,
+  // 4 P1, 8 P2) for the rows [row_lo, row_hi) -- the caller all-gathers the row statistics between phases
+  int merge_B = 0;
+  int phase_mask = 15;
+  int row_lo = 0, row_hi = -1;
 };
 
 struct FeclBwdArgs {
@@ -34,6 +40,8 @@ struct FeclBwdArgs {
   const float* grad_out;
   float* grad_feat;
   int64_t g_sb, g_sn, g_sd;   // element strides of grad_feat
+  int row_lo = 0, row_hi = -1;   // global-negatives mode: the rows this rank owns ...
+  int grad_rows = 0;             // ... and the rows per sample of its (local) grad_feat
 };
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -53,5 +61,7 @@ size_t fecl_tc_state_bytes(int B, int N, int D, int has_teacher);
 size_t fecl_tc_workspace_bytes(int B, int N, int D);
 int fecl_tc_fwd(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st);
 int fecl_tc_bwd(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st);
+// byte offsets inside the tensor-core state: {hdr, m, n, kappa, A partial plane 0, plane stride}
+void fecl_tc_layout(int B, int N, int D, int has_teacher, size_t out[6]);
 
 }  // namespace dycon

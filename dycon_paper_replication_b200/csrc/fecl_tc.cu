@@ -104,6 +104,8 @@ struct PackParams {
   float* stats;        // kNumStats planes of B*N floats, zero-filled here
   int B, N, D, Npad, Dpad;
   int pdl;
+  int merge;           // global-negatives mode: the B samples become ONE sample of B*N rows (row b*N + n, no
+                       // per-sample padding; the caller zero-fills the tail rows of the state once)
 };
 
 template <bool kBf16>
@@ -154,17 +156,17 @@ pack16_kernel(const PackParams p) {
 #pragma unroll 4
     for (int r = ry; r < 64; r += 8) {
       const int n = n0 + r;
-      if (n < p.Npad)
-        *reinterpret_cast<uint32_t*>(dst + ((size_t)b * p.Npad + n) * p.Dpad + d0 + 2 * kx) =
+      if (p.merge ? n < p.N : n < p.Npad)
+        *reinterpret_cast<uint32_t*>(dst + ((size_t)b * (p.merge ? p.N : p.Npad) + n) * p.Dpad + d0 + 2 * kx) =
             Cvt<kBf16>::two(tile[2 * kx][r], tile[2 * kx + 1][r]);
     }
   } else {         // any other layout (d contiguous or generic): lanes along d for both
     const int tx = tid & 63, ty = tid >> 6;
     for (int r = ty; r < 64; r += 4) {
       const int n = n0 + r, d = d0 + tx;
-      if (n < p.Npad) {
+      if (p.merge ? n < p.N : n < p.Npad) {
         const float v = (n < p.N && d < p.D) ? __ldg(s + (int64_t)n * sn + (int64_t)d * sd) : 0.f;
-        dst[((size_t)b * p.Npad + n) * p.Dpad + d] = Cvt<kBf16>::one(v);
+        dst[((size_t)b * (p.merge ? p.N : p.Npad) + n) * p.Dpad + d] = Cvt<kBf16>::one(v);
       }
     }
   }
@@ -194,6 +196,8 @@ __device__ __forceinline__ void sw_epi_barrier() { asm volatile("bar.sync 3, 512
 struct SweepParams {
   int N, Npad, KC, has_teacher;
   int pdl;             // launched with programmatic stream serialization: griddepcontrol.wait / launch_dependents
+  int rb_lo;           // first row block of this launch and the rows it owns, [row_lo, row_hi): the whole sample
+  int row_lo, row_hi;  // normally; one rank's share of the merged batch in global-negatives mode
   int splits;          // column splits: grid.y CTAs share a row block, each sweeps 1/splits of the sub-tiles
   int splits1;         // the split count of the P1 launch (P2 adds up that many partial n_i per row)
   float* npart;        // kMaxSplits planes of B*N floats: P1's per-split partial n_i (summed in split order by P2)
@@ -249,7 +253,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   uint8_t* const sA = smem;
   uint8_t* const sStage = smem + a_bytes;
   SweepMisc& ms = *reinterpret_cast<SweepMisc*>(sStage + kStages * stage_bytes);
-  const int b = blockIdx.z, i0 = blockIdx.x * kTM * kRT, split = blockIdx.y;
+  const int b = blockIdx.z, i0 = (blockIdx.x + p.rb_lo) * kTM * kRT, split = blockIdx.y;
   const bool teacher_on = kMode == 2 && p.has_teacher;
   const int tcols = teacher_on ? 32 : 64;                  // columns per sub-tile
   const int nt_all = (p.N + tcols - 1) / tcols;            // sub-tiles that hold at least one real column
@@ -352,7 +356,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     // 128-row tiles and every thread walks all 64 columns in two chunks
     const int rh = kRT == 2 ? chalf : 0;
     const int r = rh * kTM + quarter * 32 + lane, i = i0 + r;
-    const bool row_ok = i < p.N;
+    const bool row_ok = i >= p.row_lo && i < p.row_hi;
     const size_t off = (size_t)b * p.N;
     const size_t g = off + (row_ok ? i : 0);
     const float* yb = p.labels + off;
@@ -608,6 +612,8 @@ struct BwdParams {
   const float* grad_out;
   float* grad_feat;
   int64_t g_sb, g_sn, g_sd;
+  int rb_lo, row_lo, row_hi;   // row blocks / rows of this launch (see SweepParams)
+  int grad_rows;               // rows per sample of grad_feat in global-negatives mode (0: row i of sample b)
 };
 
 struct BwdMisc {
@@ -682,7 +688,7 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   uint8_t* const sH = sStage + kBwdStages * stage_bytes;     // [128 i][64 j] 16-bit, K-major SW128
   uint8_t* const sG = sH + kChunk128;
   BwdMisc& ms = *reinterpret_cast<BwdMisc*>(sG + kChunk128);
-  const int b = blockIdx.z, i0 = blockIdx.x * kTM, split = blockIdx.y;
+  const int b = blockIdx.z, i0 = (blockIdx.x + p.rb_lo) * kTM, split = blockIdx.y;
   const int nt_all = (p.N + 31) / 32;           // sub-tiles that hold at least one real column
   const int t0 = (int)((long long)split * nt_all / p.splits), t1 = (int)((long long)(split + 1) * nt_all / p.splits);
   const int nt = t1 - t0;                       // this CTA's 32-column sub-tiles: t0 .. t1-1
@@ -797,7 +803,7 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const int tt = threadIdx.x - 128 - team * kBwdTeamThreads;   // 0..255 inside the team
     const int quarter = warp & 3, chalf = ((warp - 4) >> 2) & 1;
     const int r = quarter * 32 + lane, i = i0 + r;
-    const bool row_ok = i < p.N;
+    const bool row_ok = i >= p.row_lo && i < p.row_hi;
     const size_t off = (size_t)b * p.N;
     const int ic = row_ok ? i : p.N - 1;
     const float qnan = __int_as_float(0x7fc00000);
@@ -920,7 +926,11 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       tmem_ld16(tm_df + lane_base + c0, v);
       tmem_ld_wait();
       if (row_ok) {
-        float* dst = p.grad_feat + (int64_t)b * p.g_sb + (int64_t)i * p.g_sn + (int64_t)c0 * p.g_sd;
+        // global-negatives mode: row i of the merged batch is row (i - row_lo) % grad_rows of local sample
+        // (i - row_lo) / grad_rows of this rank's gradient tensor
+        const int il = i - p.row_lo;
+        const int gb = p.grad_rows ? il / p.grad_rows : b, gn = p.grad_rows ? il - gb * p.grad_rows : i;
+        float* dst = p.grad_feat + (int64_t)gb * p.g_sb + (int64_t)gn * p.g_sn + (int64_t)c0 * p.g_sd;
         if (p.g_sd == 1 && ((p.g_sn | p.g_sb) & 3) == 0) {       // rows contiguous: 16-byte stores
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -1010,6 +1020,15 @@ size_t fecl_tc_state_bytes(int B, int N, int D, int has_teacher) {
   return kHdrBytes + operand_bytes(B, N, D) * (has_teacher ? 2 : 1) + stats_bytes(B, N);
 }
 size_t fecl_tc_workspace_bytes(int, int, int) { return 16 + sizeof(double) * 3 * kMaxPartials; }
+void fecl_tc_layout(int B, int N, int D, int has_teacher, size_t out[6]) {
+  const size_t stats = kHdrBytes + operand_bytes(B, N, D) * (has_teacher ? 2 : 1), plane = (size_t)B * N * sizeof(float);
+  out[0] = 0;
+  out[1] = stats + kStatM * plane;
+  out[2] = stats + kStatN * plane;
+  out[3] = stats + kStatKappa * plane;
+  out[4] = stats + (size_t)(kNumStats + kMaxSplits) * plane;
+  out[5] = plane;
+}
 
 namespace {
 
@@ -1048,6 +1067,11 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   pk.src[0] = a.feat; pk.sb[0] = a.f_sb; pk.sn[0] = a.f_sn; pk.sd[0] = a.f_sd; pk.dst[0] = s.F;
   pk.src[1] = a.teacher; pk.sb[1] = a.t_sb; pk.sn[1] = a.t_sn; pk.sd[1] = a.t_sd; pk.dst[1] = s.T;
   pk.stats = s.stats; pk.B = B; pk.N = N; pk.D = D; pk.Npad = Npad; pk.Dpad = Dpad;
+  pk.merge = 0;
+  if (a.merge_B > 0) {       // global negatives: merge_B samples of N / merge_B rows -> one sample of N rows
+    pk.B = a.merge_B; pk.N = N / a.merge_B; pk.Npad = npad_of(pk.N); pk.merge = 1;
+  }
+  const int row_lo = a.row_lo, row_hi = a.row_hi < 0 ? N : a.row_hi;
   // DYCON_NO_PDL=1 launches the forward kernels fully serialised and without any griddepcontrol instruction
   // (ncu's kernel replay of a --set full capture does not get along with programmatic dependent launches)
   static const bool no_pdl = [] {
@@ -1055,8 +1079,8 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
     return e && e[0] == '1';
   }();
   pk.pdl = no_pdl ? 0 : 1;
-  dim3 pgrid(Npad / 64, Dpad / 64, B * (p.has_teacher ? 2 : 1));
-  pack16_kernel<kBf16><<<pgrid, 256, 0, st>>>(pk);
+  dim3 pgrid(pk.Npad / 64, Dpad / 64, pk.B * (p.has_teacher ? 2 : 1));
+  if (a.phase_mask & 1) pack16_kernel<kBf16><<<pgrid, 256, 0, st>>>(pk);
   // boxes: 128 rows (A tile), 64 rows (a sub-tile of F alone), 32 rows (F | T interleaved in teacher mode)
   CUtensorMap mapA, mapF64, mapF32, mapT32;
   if (int rc = make_tmap_16_2d(&mapA, s.F, (uint64_t)B * Npad, Dpad, 128, kBf16)) return rc;
@@ -1069,13 +1093,15 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   // all three sweeps: 256-row tiles when the sample has at least two 128-row blocks, and as many column splits
   // (<= 8, at least one 64-column sub-tile each) as fit one wave of SMs
   const int rt01 = Npad / 128 >= 2 ? 2 : 1;
-  const int rb01 = (Npad / 128 + rt01 - 1) / rt01;
+  const int rb_lo = row_lo / (128 * rt01);                                   // row blocks that hold rows of this launch
+  const int rb01 = (row_hi + 128 * rt01 - 1) / (128 * rt01) - rb_lo;
   int splits01 = sm_count() / (rb01 * B);
   if (splits01 > kMaxSplits) splits01 = kMaxSplits;
   if (splits01 > (N + 63) / 64) splits01 = (N + 63) / 64;
   if (splits01 < 1) splits01 = 1;
   sp.splits = splits01;
   sp.splits1 = splits01;
+  sp.rb_lo = rb_lo; sp.row_lo = row_lo; sp.row_hi = row_hi;
   sp.npart = s.stats + (size_t)kNumStats * plane;
   sp.apart = s.stats + (size_t)(kNumStats + kMaxSplits) * plane;
   sp.sc = p.sc;
@@ -1121,8 +1147,11 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   const int fk = focal_kind(p.sc);
 #define DYCON_SWEEPS(RT)                                                                                             \
   do {                                                                                                               \
-    DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<0, kBf16, kNoFocal, RT>, mapA, mapF64, mapT32, sp));     \
-    DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<1, kBf16, kNoFocal, RT>, mapA, mapF64, mapT32, sp));     \
+    if (a.phase_mask & 2)                                                                                            \
+      DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<0, kBf16, kNoFocal, RT>, mapA, mapF64, mapT32, sp));   \
+    if (a.phase_mask & 4)                                                                                            \
+      DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<1, kBf16, kNoFocal, RT>, mapA, mapF64, mapT32, sp));   \
+    if (!(a.phase_mask & 8)) break;                                                                                  \
     if (fk == kNoFocal)                                                                                              \
       DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kNoFocal, RT>, mapA, mapF2, mapT32, sp));    \
     else if (fk == kFocalG2)                                                                                         \
@@ -1133,7 +1162,7 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   if (rt01 == 2) DYCON_SWEEPS(2); else DYCON_SWEEPS(1);
 #undef DYCON_SWEEPS
   DYCON_CUDA(cudaGetLastError());
-  count_launches(4);
+  count_launches((a.phase_mask & 1) + ((a.phase_mask >> 1) & 1) + ((a.phase_mask >> 2) & 1) + ((a.phase_mask >> 3) & 1));
   return DYCON_OK;
 }
 
@@ -1150,8 +1179,12 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
   BwdParams bp;
   bp.N = N; bp.Npad = Npad; bp.KC = KC; bp.D = D; bp.has_teacher = p.has_teacher;
   // column splits accumulate into a zero-filled gradient: only for a dense layout (memset of B*N*D floats)
-  const bool dense = a.g_sb == (int64_t)N * D && ((a.g_sn == D && a.g_sd == 1) || (a.g_sn == 1 && a.g_sd == N));
-  bp.splits = dense ? pick_splits(Npad / 128, B) : 1;
+  const int row_lo = a.row_lo, row_hi = a.row_hi < 0 ? N : a.row_hi;
+  const int gn = a.grad_rows > 0 ? a.grad_rows : N;          // rows per sample of grad_feat
+  const int rb_lo = row_lo / 128, rbs = (row_hi + 127) / 128 - rb_lo;
+  const bool dense = a.g_sb == (int64_t)gn * D && ((a.g_sn == D && a.g_sd == 1) || (a.g_sn == 1 && a.g_sd == gn));
+  bp.splits = dense ? pick_splits(rbs, B) : 1;
+  bp.rb_lo = rb_lo; bp.row_lo = row_lo; bp.row_hi = row_hi; bp.grad_rows = a.grad_rows;
   bp.sc = p.sc;
   bp.c1 = p.sc.inv_tau * kLog2e;
   bp.labels = a.labels;
@@ -1167,8 +1200,9 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
                           set_smem(fecl_tc_bwd_kernel<kBf16, kFocalAny>);
   if (once) return once;
   DYCON_REQUIRE(smem <= 227 * 1024, DYCON_ERR_UNSUPPORTED, "FeCL tensor-core bwd: %zu bytes of shared memory needed", smem);
-  if (bp.splits > 1) DYCON_CUDA(cudaMemsetAsync(a.grad_feat, 0, (size_t)B * N * D * sizeof(float), st));
-  dim3 grid(Npad / 128, bp.splits, B);
+  if (bp.splits > 1)
+    DYCON_CUDA(cudaMemsetAsync(a.grad_feat, 0, (size_t)B * (row_hi - row_lo) * D * sizeof(float), st));
+  dim3 grid(rbs, bp.splits, B);
   switch (focal_kind(p.sc)) {
     case kNoFocal: fecl_tc_bwd_kernel<kBf16, kNoFocal><<<grid, kBwdThreads, smem, st>>>(mapA, mapF, mapT, bp); break;
     case kFocalG2: fecl_tc_bwd_kernel<kBf16, kFocalG2><<<grid, kBwdThreads, smem, st>>>(mapA, mapF, mapT, bp); break;

@@ -287,6 +287,91 @@ class _FeCLFunction(torch.autograd.Function):
         return (grad,) + (None,) * 11
 
 
+class _FeCLGlobalFunction(torch.autograd.Function):
+    """FeCL with global negatives: the samples of ALL ranks are contrasted as one sample of B_all*N rows (the
+    reference FeCLoss on feat.reshape(1, B_all*N, D)); every rank owns the rows of its local samples.  See
+    include/dycon_b200.h, "FeCL with global negatives", for the phase protocol."""
+
+    @staticmethod
+    def forward(ctx, feat, labels, teacher, row_weight, inv_tau, gamma, use_focal, cross_thresh, lambda_cross,
+                precision, process_group):
+        dev = feat.device
+        B, N, D = feat.shape
+        world, rank = sharded.group_size_rank(process_group)
+        B_all, M = B * world, B * world * N
+        has_teacher = teacher is not None
+        gather = lambda x: sharded.all_gather_rows(x.contiguous(), process_group)
+        feat_all = gather(feat.detach())                        # (B_all, N, D) row-major
+        teacher_all = gather(teacher) if has_teacher else None
+        labels_all = gather(labels)
+        rw_all = gather(row_weight) if row_weight is not None else None
+        lo, hi = rank * B * N, (rank + 1) * B * N
+        with torch.cuda.device(dev):
+            _lib.require_b200(dev.index)
+            L = _lib.lib()
+            sbytes = L.dycon_fecl_gn_state_bytes(B_all, N, D, int(has_teacher), precision)
+            if sbytes == 0:
+                raise RuntimeError("FeCLoss(cross_gpu_negatives=True) needs precision 'fp16' or 'bf16' and D % 4 == 0, D <= 256")
+            off = (ctypes.c_size_t * 6)()
+            _lib.check(L.dycon_fecl_gn_layout(B_all, N, D, int(has_teacher), precision, off), "dycon_fecl_gn_layout")
+            state = torch.zeros(sbytes, dtype=torch.uint8, device=dev)
+            plane = lambda k: state[off[k]:off[k] + 4 * M].view(torch.float32)
+            ws = _workspace(dev, f"fecl{precision}", L.dycon_fecl_workspace_bytes(1, M, D, precision))
+            sums = torch.empty(3, dtype=torch.float64, device=dev)
+            ts = teacher_all.stride() if has_teacher else (0, 0, 0)
+
+            def phases(mask):
+                _lib.check(L.dycon_fecl_gn_fwd(mask, _ptr(feat_all), *feat_all.stride(), _ptr(teacher_all), *ts,
+                                               _ptr(labels_all), _ptr(rw_all), B_all, N, D, inv_tau, gamma,
+                                               int(use_focal), cross_thresh, lambda_cross, precision, _ptr(state),
+                                               state.numel(), lo, hi, _ptr(sums), _ptr(ws), ws.numel(),
+                                               _stream_ptr(dev)), "dycon_fecl_gn_fwd")
+
+            t0 = _tick()
+            phases(1 | 2)                                       # pack, row max of the own rows
+            m = plane(1)
+            m.copy_(sharded.all_gather_rows(m[lo:hi].clone(), process_group))
+            phases(4 | 8)                                       # negative sums, loss terms of the own rows
+            _tock("fecl_fwd", t0)
+            loss = sharded.reduce_fecl(sums, 1.0 / M, lambda_cross, has_teacher, process_group)
+            if ctx.needs_input_grad[0]:
+                # the backward reads n, kappa and A of EVERY row (the transposed term): consolidate the own rows'
+                # split partials of A into plane 0 (fixed order), then all-gather the three planes
+                a_planes = state[off[4]:off[4] + 8 * 4 * M].view(torch.float32).view(8, M)
+                own = torch.stack([plane(2)[lo:hi], plane(3)[lo:hi], a_planes[:, lo:hi].sum(dim=0)])
+                full = sharded.all_gather_rows(own.unsqueeze(0), process_group)      # (world, 3, B*N)
+                plane(2).copy_(full[:, 0].reshape(-1))
+                plane(3).copy_(full[:, 1].reshape(-1))
+                a_planes[0].copy_(full[:, 2].reshape(-1))
+                state[off[0]:off[0] + 8].view(torch.float32)[1] = 1.0                 # header: one A plane
+        ctx.save_for_backward(state, labels_all, sums)
+        ctx.cfg = (B, N, D, B_all, has_teacher, inv_tau, gamma, int(use_focal), row_weight is not None, cross_thresh,
+                   lambda_cross, precision, lo, hi)
+        ctx.grad_strides = _dense_strides(feat)
+        return loss
+
+    @staticmethod
+    def backward(ctx, go):
+        state, labels_all, sums = ctx.saved_tensors
+        (B, N, D, B_all, has_teacher, inv_tau, gamma, use_focal, has_rw, cross_thresh, lambda_cross, precision, lo,
+         hi) = ctx.cfg
+        dev = state.device
+        if ctx.grad_strides is None:
+            grad = torch.empty((B, N, D), dtype=torch.float32, device=dev)
+        else:
+            grad = torch.empty_strided((B, N, D), ctx.grad_strides, dtype=torch.float32, device=dev)
+        go = _scalar_grad(go)
+        with torch.cuda.device(dev):
+            t0 = _tick()
+            _lib.check(_lib.lib().dycon_fecl_gn_bwd(_ptr(state), state.numel(), _ptr(labels_all), B_all, N, D,
+                                                    int(has_teacher), inv_tau, gamma, use_focal, int(has_rw),
+                                                    cross_thresh, lambda_cross, precision, lo, hi,
+                                                    ctypes.c_void_p(sums.data_ptr() + 16), _ptr(go), _ptr(grad),
+                                                    *grad.stride(), _stream_ptr(dev)), "dycon_fecl_gn_bwd")
+            _tock("fecl_bwd", t0)
+        return (grad,) + (None,) * 10
+
+
 class FeCLoss(nn.Module):
     """Feature contrastive loss with focal positives and the teacher hard-negative branch
     (reference: dycon_losses.py:120-235; constructor :141-148, forward :150-235).
@@ -298,7 +383,8 @@ class FeCLoss(nn.Module):
     """
 
     def __init__(self, device, temperature=0.6, gamma=2.0, use_focal=False, rampup_epochs=2000,
-                 lambda_cross=1.0, *, precision=None, process_group=None, global_batch=None):
+                 lambda_cross=1.0, *, precision=None, process_group=None, global_batch=None,
+                 cross_gpu_negatives=False):
         super().__init__()
         self.device = device
         self.temperature = temperature
@@ -311,6 +397,8 @@ class FeCLoss(nn.Module):
             raise ValueError(f"precision must be one of {sorted(_PRECISIONS)}")
         self.process_group = process_group
         self.global_batch = global_batch
+        # extension (BASELINE config 5): contrast every row against the rows of ALL samples of ALL ranks
+        self.cross_gpu_negatives = bool(cross_gpu_negatives)
 
     def forward(self, feat, mask, teacher_feat=None, gambling_uncertainty=None, epoch=0):
         _require_cuda_fp32("feat", feat)
@@ -341,6 +429,10 @@ class FeCLoss(nn.Module):
             rw = gambling_uncertainty.detach().reshape(B, N).to(device=feat.device, dtype=torch.float32).contiguous()
         # host scalars, recomputed every call like the reference (:199-200, :222)
         cross_thresh = sigmoid_rampup(epoch, self.rampup_epochs, min_threshold=0.3, max_threshold=0.5)
+        if self.cross_gpu_negatives:
+            return _FeCLGlobalFunction.apply(feat, labels, teacher_feat, rw, 1.0 / float(self.temperature),
+                                             float(self.gamma), bool(self.use_focal), float(cross_thresh),
+                                             float(self.lambda_cross), _PRECISIONS[self.precision], self.process_group)
         return _FeCLFunction.apply(feat, labels, teacher_feat, rw, 1.0 / float(self.temperature), float(self.gamma),
                                    bool(self.use_focal), float(cross_thresh), float(self.lambda_cross),
                                    _PRECISIONS[self.precision], self.process_group, self.global_batch)

@@ -160,6 +160,23 @@ def _exchange_for(sums, group):
     return None
 
 
+def group_size_rank(group):
+    """(world size, rank) of `group`; (1, 0) without an initialised process group."""
+    if group is not None and dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def all_gather_rows(x: torch.Tensor, group=None) -> torch.Tensor:
+    """Concatenation over ranks (rank order) of the equally shaped, contiguous `x` along dim 0."""
+    world, _ = group_size_rank(group)
+    if world == 1:
+        return x
+    out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(out, x.contiguous(), group=group)
+    return out
+
+
 def shard_bounds(global_batch: int, rank: int, world_size: int):
     """Contiguous sample range of `rank`; requires world_size <= global_batch (else: replicas only)."""
     if world_size > global_batch:

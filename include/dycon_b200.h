@@ -122,6 +122,36 @@ int dycon_fecl_bwd(const void* state, size_t state_bytes, const float* labels, i
                    const float* grad_out, float* grad_feat, int64_t g_sb, int64_t g_sn, int64_t g_sd,
                    dycon_stream_t stream);
 
+/* ------------------------------------------------------------------ FeCL with global negatives
+ * Extension for batches sharded over ranks (BASELINE config 5; not in the reference, whose contrast is per
+ * sample): every row is contrasted against the rows of ALL B_all samples of the global batch.  The result is
+ * the reference FeCLoss evaluated on feat.reshape(1, B_all*N, D), mask.reshape(1, 1, B_all*N) (that is the
+ * oracle).  Every rank all-gathers the embeddings (feat_all / teacher_all: (B_all, N, D) fp32 with element
+ * strides, labels_all: B_all*N fp32) and owns the rows [row_lo, row_hi) of the merged batch -- whole samples.
+ * dycon_fecl_gn_fwd runs the phases of phase_mask for those rows: 1 pack (+ zero the statistics; the state
+ * must have been ZERO-FILLED once by the caller), 2 row max m, 4 negative sums, 8 loss terms.  Between the
+ * phases the caller all-gathers the row statistics, which live in `state` at the byte offsets returned by
+ * dycon_fecl_gn_layout: out6 = {header, m plane, n plane, kappa plane, A plane 0, plane stride}; a plane holds
+ * B_all*N floats.  Protocol: fwd(1|2) -> all-gather m -> fwd(4|8) -> all-reduce sums_out (3 doubles, as in
+ * dycon_fecl_fwd; the loss is sums[0]/(B_all*N) + lambda*sums[1]/(sums[2]+1e-18)) -> [for the backward: add the
+ * 8 A planes of the own rows into A plane 0, store 1.0f at header float 1, all-gather n, kappa, A plane 0]
+ * -> dycon_fecl_gn_bwd, which writes the gradient of the OWN rows: grad_feat is the rank's local
+ * ((row_hi-row_lo)/N, N, D) tensor with element strides.  Tensor-core precisions only.
+ */
+size_t dycon_fecl_gn_state_bytes(int B_all, int N, int D, int has_teacher, int precision);
+int dycon_fecl_gn_layout(int B_all, int N, int D, int has_teacher, int precision, size_t* out6);
+int dycon_fecl_gn_fwd(int phase_mask, const float* feat_all, int64_t f_sb, int64_t f_sn, int64_t f_sd,
+                      const float* teacher_all, int64_t t_sb, int64_t t_sn, int64_t t_sd, const float* labels_all,
+                      const float* row_weight_all, int B_all, int N, int D, float inv_tau, float gamma, int use_focal,
+                      float cross_thresh, float lambda_cross, int precision, void* state, size_t state_bytes,
+                      int row_lo, int row_hi, double* sums_out, void* workspace, size_t workspace_bytes,
+                      dycon_stream_t stream);
+int dycon_fecl_gn_bwd(const void* state, size_t state_bytes, const float* labels_all, int B_all, int N, int D,
+                      int has_teacher, float inv_tau, float gamma, int use_focal, int has_row_weight, float cross_thresh,
+                      float lambda_cross, int precision, int row_lo, int row_hi, const double* cross_cnt,
+                      const float* grad_out, float* grad_feat, int64_t g_sb, int64_t g_sn, int64_t g_sd,
+                      dycon_stream_t stream);
+
 /* ------------------------------------------------------------------ EMA
  * For every tensor k:  ema[k] = fma(one_minus_alpha, param[k], rn(ema[k]*alpha))  -- the
  * rounding order of ema.mul_(alpha).add_(param, alpha=1-alpha)

@@ -6,7 +6,8 @@
 1. the NVLink peer-memory exchange (dycon_exchange_sums) against NCCL all_reduce: eager back-to-back
    calls (slot reuse) and CUDA-graph replays;
 2. the sharded FeCL + UnCL modules (process_group=, global_batch=) against the float64 closed-form oracle on
-   the concatenated batch: every rank must obtain the single-process loss and its own slice of the gradient.
+   the concatenated batch: every rank must obtain the single-process loss and its own slice of the gradient;
+3. FeCL with global negatives (cross_gpu_negatives=True) against the reference on the merged batch.
 """
 import os
 import sys
@@ -104,9 +105,27 @@ def main():
             assert abs(ul.item() - ru["loss"]) <= 1e-5 * abs(ru["loss"]), (ul.item(), ru["loss"])
             assert np.abs(f.grad.cpu().numpy() - rf["grad"][lo:hi]).max() <= 1e-5 * np.abs(rf["grad"]).max()
             assert np.abs(s.grad.cpu().numpy() - ru["grad"][lo:hi]).max() <= 1e-5 * np.abs(ru["grad"]).max()
+    # ---- 3. global negatives (BASELINE config 5): every rank's rows against the rows of ALL ranks ----------
+    crit = FeCLoss(dev, precision="fp16", process_group=g, cross_gpu_negatives=True, temperature=0.6, gamma=2.0,
+                   use_focal=True, rampup_epochs=1500)
+    f.grad = None
+    gl = crit(f, inp.mask[lo:hi].to(dev), inp.teacher[lo:hi].to(dev), None, 100)
+    (0.5 * gl).backward()
+    Bn, Nn, Dn = inp.feat.shape
+    thr = torch_port.ramp_threshold(100, 1500, 0.3, 0.5)
+    rg = closed_form.fecl(inp.feat.reshape(1, Bn * Nn, Dn).numpy(), inp.mask.reshape(1, 1, Bn * Nn).numpy(),
+                          inp.teacher.reshape(1, Bn * Nn, Dn).numpy(), None, inv_tau=1 / 0.6, gamma=2.0, use_focal=True,
+                          cross_thresh=thr, go=0.5, ambiguity=5e-4)
+    assert abs(gl.item() - rg["loss"]) <= 2e-3 * abs(rg["loss"]), (gl.item(), rg["loss"])
+    full = [torch.empty_like(f.grad.contiguous()) for _ in range(world)]
+    dist.all_gather(full, f.grad.contiguous(), group=g)
+    got = torch.cat(full).cpu().numpy().reshape(rg["grad"].shape)
+    gerr = closed_form.fecl_grad_error(got, rg, inp.teacher.reshape(1, Bn * Nn, Dn).numpy())
+    assert gerr <= 2e-3, gerr
     dist.barrier()
     if rank == 0:
-        print(f"multi_gpu_check ok: world={world} peer_exchange={used_peer} sharded-vs-unsharded max err={worst:.2e}", flush=True)
+        print(f"multi_gpu_check ok: world={world} peer_exchange={used_peer} sharded-vs-unsharded max err={worst:.2e} "
+              f"global-negatives grad err={gerr:.1e}", flush=True)
     os._exit(0)      # skip the NCCL teardown (it can hang once graphs captured NCCL work)
 
 
