@@ -343,7 +343,7 @@ class _FeCLGlobalFunction(torch.autograd.Function):
                 plane(2).copy_(full[:, 0].reshape(-1))
                 plane(3).copy_(full[:, 1].reshape(-1))
                 a_planes[0].copy_(full[:, 2].reshape(-1))
-                state[off[0]:off[0] + 8].view(torch.float32)[1] = 1.0                 # header: one A plane
+                state[off[0] + 4:off[0] + 8].view(torch.float32).fill_(1.0)           # header: one A plane (no H2D copy: graph capturable)
         ctx.save_for_backward(state, labels_all, sums)
         ctx.cfg = (B, N, D, B_all, has_teacher, inv_tau, gamma, int(use_focal), row_weight is not None, cross_thresh,
                    lambda_cross, precision, lo, hi)
