@@ -506,10 +506,11 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
               const bool pos = diag_here ? same && (c != rdiag) : same;
               acc0 += pos ? phi2 : 0.f;
               acc1 += pos ? at : 0.f;
-              // cross term: -log(1 - cs + 1e-18) over labels differ && cs > thresh (dycon_losses.py:217-229);
-              // ordered != so that padding (y = NaN) is never a hard negative
+              // cross term: -log(1 - cs + 1e-18) over labels differ && cs > thresh (dycon_losses.py:217-229).
+              // Padded columns (y = NaN, so !same) have cs == 0 exactly (zero teacher rows) and the host
+              // guarantees thresh >= 0, so they are never hard negatives; padded rows are dropped at the end.
               const float cs = w[c];
-              const bool hard = (ys[k] < yi || ys[k] > yi) && cs > p.sc.cross_thresh;
+              const bool hard = !same && cs > p.sc.cross_thresh;
               cprod *= hard ? (1.f - cs) + kTiny : 1.f;
               acc3 += hard ? 1.f : 0.f;
             }
@@ -667,7 +668,8 @@ __device__ __forceinline__ void bwd_pair(float x, float cs, float yi, float m2i,
   const bool same = yj == yi;                                    // NaN labels (padding) compare unequal
   h = same ? gpos : gneg;                                        // select: the unused branch may be NaN
   if (kTeacher) {
-    const bool hard = (yj < yi || yj > yi) && cs > thresh;       // ordered !=: never true for padding
+    // padded columns have cs == 0 exactly (zero teacher rows) and thresh >= 0 (host check): never hard
+    const bool hard = !same && cs > thresh;
     g = hard ? gcs * rom : 0.f;
   } else {
     g = 0.f;
@@ -995,6 +997,14 @@ TcState carve(void* state, int B, int N, int D, int has_teacher) {
   return s;
 }
 
+// The kernels treat zero-padded columns as "cs == 0 <= thresh": a negative threshold would turn them into hard
+// negatives.  The reference's schedule is sigmoid_rampup(.., 0.3, 0.5) >= 0.3 (dycon_losses.py:222).
+int check_tc_thresh(const FeclProblem& p) {
+  DYCON_REQUIRE(!p.has_teacher || p.sc.cross_thresh >= 0.f, DYCON_ERR_UNSUPPORTED,
+                "FeCL tensor-core path: cross_thresh=%g < 0 (use precision fp32)", (double)p.sc.cross_thresh);
+  return DYCON_OK;
+}
+
 int check_tc_shape(int B, int N, int D) {
   DYCON_REQUIRE(D % 4 == 0 && D <= 256, DYCON_ERR_UNSUPPORTED,
                 "FeCL bf16: D=%d must be a multiple of 4 and <= 256 (the reference projection head has D=256)", D);
@@ -1217,11 +1227,13 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
 
 int fecl_tc_fwd(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   if (int rc = check_tc_shape(p.B, p.N, p.D)) return rc;
+  if (int rc = check_tc_thresh(p)) return rc;
   return p.precision == DYCON_FECL_BF16 ? tc_fwd_impl<true>(p, a, st) : tc_fwd_impl<false>(p, a, st);
 }
 
 int fecl_tc_bwd(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
   if (int rc = check_tc_shape(p.B, p.N, p.D)) return rc;
+  if (int rc = check_tc_thresh(p)) return rc;
   return p.precision == DYCON_FECL_BF16 ? tc_bwd_impl<true>(p, a, st) : tc_bwd_impl<false>(p, a, st);
 }
 

@@ -71,5 +71,14 @@ def test_argument_validation_happens_before_any_launch(so_path):
     assert rc == -1
     rc = L.dycon_fecl_bwd(None, 0, None, 1, 8, 8, 0, 1.0, 2.0, 0, 0, 0.3, 1.0, 7, None, None, None, 64, 8, 1, None)
     assert rc == -1 and b"precision" in L.dycon_last_error()
+    # the tensor-core kernels rely on cross_thresh >= 0 (zero padding must not look like a hard negative)
+    import ctypes
+    buf = (ctypes.c_char * 4096)()
+    addr = (ctypes.addressof(buf) + 255) // 256 * 256
+    ptr = ctypes.c_void_p(addr)
+    big = 1 << 30
+    rc = L.dycon_fecl_fwd(ptr, 64, 8, 1, ptr, 64, 8, 1, ptr, None, 1, 8, 8, 1.0, 2.0, 1, -0.1, 1.0, 0.125,
+                          _lib.FECL_FP16, ptr, big, ptr, None, ptr, big, None)
+    assert rc == -2 and b"cross_thresh" in L.dycon_last_error()
     assert L.dycon_ema_multi(None, None, None, 0, 0.5, 0.5, None) == 0      # empty list is a no-op
     assert L.dycon_ema_multi(None, None, None, 3, 0.5, 0.5, None) == -1
