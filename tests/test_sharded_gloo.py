@@ -51,6 +51,19 @@ def _worker(rank, world, port, out):
         uloss = sharded.uncl_loss_from_sum(tot, 1.0 / (Bu * V))
         assert abs(uloss.item() - float(urec["loss64"])) <= 1e-6 * abs(float(urec["loss64"]))
         assert normwise(ul["grad"], urec["grad64"][ulo:uhi]) <= 1e-10
+        # ---------------- host helpers of the global-negatives protocol (all-gather in rank order; the reduced
+        #                  loss helpers fall back to the backend all-reduce for CPU tensors)
+        assert sharded.group_size_rank(dist.group.WORLD) == (world, rank)
+        rows = torch.arange(6, dtype=torch.float32).reshape(3, 2) + 100 * rank
+        full = sharded.all_gather_rows(rows, dist.group.WORLD)
+        want = torch.cat([torch.arange(6, dtype=torch.float32).reshape(3, 2) + 100 * r for r in range(world)])
+        assert torch.equal(full, want)
+        s3 = torch.tensor([1.0 + rank, 2.0, 4.0 * (rank + 1)], dtype=torch.float64)
+        red = sharded.reduce_fecl(s3, 0.5, 2.0, True, dist.group.WORLD)
+        tot3 = [sum(1.0 + r for r in range(world)), 2.0 * world, sum(4.0 * (r + 1) for r in range(world))]
+        assert abs(red.item() - (tot3[0] * 0.5 + 2.0 * tot3[1] / tot3[2])) < 1e-6
+        u1 = sharded.reduce_uncl(torch.tensor([3.0 * (rank + 1)], dtype=torch.float64), 0.25, dist.group.WORLD)
+        assert abs(u1.item() - 0.25 * sum(3.0 * (r + 1) for r in range(world))) < 1e-6
         out.put((rank, "ok"))
     except Exception as exc:       # noqa: BLE001 - report to the parent
         out.put((rank, repr(exc)))
