@@ -38,7 +38,9 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-eager-gpu"],
+                    help="ours | reference (the op chain on the host CPU; the driver's reference arm) | "
+                         "reference-eager-gpu (the same op chain as eager PyTorch on cuda:0, informational)")
     ap.add_argument("--shape", default="brats19")
     ap.add_argument("--batch", type=int, default=4, help="samples per GPU")
     ap.add_argument("--dim", type=int, default=256)
@@ -173,6 +175,54 @@ def cpu_time_reference(args, steps, warmup, budget_s=150.0):
     sample = (f"{steps} timed steps (after {warmup} warm-up) of UnCL+FeCL fwd+bwd on B={batch} of the "
               f"{args.batch}-sample {args.shape} batch, fp32, {torch.get_num_threads()} torch threads, median")
     return inp.voxels / med, med * 1e3, sample, torch.get_num_threads()
+
+
+def run_reference_eager_gpu(args):
+    """the reference's op chain (oracle/torch_port.py) as eager PyTorch on the same
+    B200 -- what a user of the reference runs today.  Informational: not the driver's reference arm."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    import torch
+    from dycon_paper_replication_b200.synthetic import make_inputs
+    from oracle import torch_port
+    dev = torch.device("cuda", 0)
+    sets = []
+    for k in range(args.sets):
+        inp = make_inputs(args.shape, batch=args.batch, dim=args.dim, seed=1337 + k)
+        sets.append([x.to(dev) if x is not None else None
+                     for x in (inp.s_logits, inp.t_logits, inp.feat, inp.mask, inp.teacher)])
+    voxels = inp.voxels
+
+    def one(k):
+        s0, t0, f0, m0, tf0 = sets[k % len(sets)]
+        s = s0.clone().requires_grad_(True)
+        f = f0.clone().requires_grad_(True)
+        fl = torch_port.fecl_loss(f, m0, tf0, None, EPOCH, **CTOR)
+        ul = torch_port.uncl_loss(s, t0, BETA)
+        (U_WEIGHT * (fl + ul)).backward()
+        return fl + ul
+
+    for k in range(max(3, args.warmup)):
+        one(k)
+    torch.cuda.synchronize(dev)
+    torch.cuda.reset_peak_memory_stats(dev)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    ev[0].record()
+    for k in range(args.steps):
+        loss = one(k)
+        ev[k + 1].record()
+    torch.cuda.synchronize(dev)
+    times = sorted(ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps))
+    total = ev[0].elapsed_time(ev[-1]) / args.steps
+    pick = lambda q: times[min(len(times) - 1, int(q * len(times)))]
+    line = {"impl": "reference-eager-gpu", "metric": METRIC, "value": voxels / (total * 1e-3), "unit": "voxels/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": total,
+            "ms_p10_p50_p90": [pick(0.1), pick(0.5), pick(0.9)], "higher_is_better": True, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": workload_name(args, 1),
+                                            "arm": "oracle/torch_port.py op chain, eager PyTorch on cuda:0, "
+                                                   "inputs resident, includes the chain's own host syncs"},
+            "peak_mem_mb": torch.cuda.max_memory_allocated(dev) / 2**20, "loss_check": float(loss.detach())}
+    print(json.dumps(line), flush=True)
 
 
 def run_reference(args):
@@ -598,5 +648,7 @@ if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
         run_reference(a)
+    elif a.impl == "reference-eager-gpu":
+        run_reference_eager_gpu(a)
     else:
         run_ours(a)
