@@ -178,6 +178,27 @@ def test_isles22_size_properties(mode):
     assert abs(0.5 * (la + lb) - lab) <= 1e-5 * abs(lab)
 
 
+@pytest.mark.parametrize("shape", [(4, 1728, 256), (1, 700, 64), (3, 257, 128), (2, 2352, 256), (5, 100, 64)])
+def test_backward_work_split_is_reproducible_and_exact(shape):
+    """Few row blocks (fewer than SMs): the backward splits a row block's columns over several CTAs and adds
+    their partial dF onto a zero-filled gradient.  Shapes with one to many row blocks per sample, odd N, five
+    samples: the gradient must be bit-identical run to run and meet the 16-bit bound against the float64
+    closed form of dycon_losses.py:150-235."""
+    skip_unavailable("fp16")
+    b, n, d = shape
+    g = torch.Generator().manual_seed(n)
+    mask = (torch.rand(b, 1, n, generator=g) < 0.2).float()
+    f = torch.nn.functional.normalize(torch.randn(b, n, d, generator=g) + 0.5, dim=-1)
+    t = torch.nn.functional.normalize(f + 0.3 * torch.randn(b, n, d, generator=g) / d ** 0.5, dim=-1)
+    ctor = dict(temperature=0.6, gamma=2.0, use_focal=True, rampup_epochs=1500)
+    runs = [run(f, mask, t, None, 100, 0.5, "fp16", **ctor) for _ in range(3)]
+    for loss, grad in runs[1:]:
+        assert loss == runs[0][0] and np.array_equal(grad, runs[0][1])
+    ref = reference(f, mask, t, 100, 0.5, ambiguity=AMBIGUITY["fp16"], **ctor)
+    assert abs(runs[0][0] - ref["loss"]) <= TOL["fp16"] * abs(ref["loss"])
+    assert grad_error(runs[0][1], ref, t) <= grad_tol("fp16")
+
+
 @pytest.mark.parametrize("mode", ["fp32", "fp16"])
 def test_unnormalised_features(mode):
     """The reference's own smoke block feeds un-normalised randn features (dycon_losses.py:244-252): logits of
