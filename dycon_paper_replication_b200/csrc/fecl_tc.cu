@@ -601,6 +601,7 @@ __device__ __forceinline__ void bwd_team_barrier(int team) {
 struct BwdParams {
   int N, Npad, KC, D, has_teacher;
   int splits;          // column splits; with > 1 the partial dF are summed with red.global.add onto zeros
+  int pdl;             // the zero fill of grad_feat may still be running: griddepcontrol.wait before the first RED
   FeclScalars sc;
   float c1;
   const float* labels;
@@ -673,6 +674,21 @@ __device__ __forceinline__ void bwd_pair(float x, float cs, float yi, float m2i,
     g = hard ? gcs * rom : 0.f;
   } else {
     g = 0.f;
+  }
+}
+
+// Zero fill of the gradient for the split backward.  It releases its dependent at once: the backward is
+// launched with programmatic stream serialization, runs its whole main loop next to this grid and only waits
+// for it (griddepcontrol.wait) before its first red.global.add.
+__global__ void __launch_bounds__(256) zero_fill_kernel(float* dst, size_t n, int pdl) {
+  if (pdl) pdl_trigger();
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (size_t q = tid; q < n / 4; q += nth) d4[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (size_t q = (n & ~(size_t)3) + tid; q < n; q += nth) dst[q] = 0.f;
+  } else {
+    for (size_t q = tid; q < n; q += nth) dst[q] = 0.f;
   }
 }
 
@@ -920,6 +936,7 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     // ---- dF (TMEM) * go -> grad_feat: the 16 epilogue warps split the Dpad columns four ways ----
     mbar_wait(&ms.df_full, 0);
     tcgen05_after_sync();
+    if (p.pdl) pdl_wait();                          // the zero fill of grad_feat is complete and visible
     const float go = __ldg(p.grad_out) / hscale;
     const int cgrp = (warp - 4) >> 2;               // 0..3
     const int dq = Dpad / 4;                         // columns per column group (multiple of 16)
@@ -1210,13 +1227,33 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
                           set_smem(fecl_tc_bwd_kernel<kBf16, kFocalAny>);
   if (once) return once;
   DYCON_REQUIRE(smem <= 227 * 1024, DYCON_ERR_UNSUPPORTED, "FeCL tensor-core bwd: %zu bytes of shared memory needed", smem);
-  if (bp.splits > 1)
-    DYCON_CUDA(cudaMemsetAsync(a.grad_feat, 0, (size_t)B * (row_hi - row_lo) * D * sizeof(float), st));
-  dim3 grid(rbs, bp.splits, B);
+  static const bool no_pdl = [] {
+    const char* e = getenv("DYCON_NO_PDL");
+    return e && e[0] == '1';
+  }();
+  bp.pdl = 0;
+  if (bp.splits > 1) {
+    bp.pdl = no_pdl ? 0 : 1;
+    const size_t n = (size_t)B * (row_hi - row_lo) * D;
+    const unsigned zgrid = (unsigned)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)sm_count() * 8);
+    zero_fill_kernel<<<zgrid, 256, 0, st>>>(a.grad_feat, n, bp.pdl);
+    DYCON_CUDA(cudaGetLastError());
+    count_launches(1);
+  }
+  cudaLaunchAttribute pdl_attr[1];
+  pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(rbs, bp.splits, B);
+  cfg.blockDim = dim3(kBwdThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cfg.attrs = pdl_attr;
+  cfg.numAttrs = bp.pdl ? 1 : 0;
   switch (focal_kind(p.sc)) {
-    case kNoFocal: fecl_tc_bwd_kernel<kBf16, kNoFocal><<<grid, kBwdThreads, smem, st>>>(mapA, mapF, mapT, bp); break;
-    case kFocalG2: fecl_tc_bwd_kernel<kBf16, kFocalG2><<<grid, kBwdThreads, smem, st>>>(mapA, mapF, mapT, bp); break;
-    default: fecl_tc_bwd_kernel<kBf16, kFocalAny><<<grid, kBwdThreads, smem, st>>>(mapA, mapF, mapT, bp); break;
+    case kNoFocal: DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_bwd_kernel<kBf16, kNoFocal>, mapA, mapF, mapT, bp)); break;
+    case kFocalG2: DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_bwd_kernel<kBf16, kFocalG2>, mapA, mapF, mapT, bp)); break;
+    default: DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_bwd_kernel<kBf16, kFocalAny>, mapA, mapF, mapT, bp)); break;
   }
   DYCON_CUDA(cudaGetLastError());
   count_launches(1);
