@@ -127,6 +127,37 @@ class ClockSampler:
                 "reasons": reasons + note, "samples": len(inside), "power_w_max": max(power) if power else None}
 
 
+class near_gpu:
+    """Context manager: run the enclosed host allocations on the CPUs of the GPU's NUMA node (pinned pages are
+    placed by first touch; a buffer on the far socket can cost most of the PCIe bandwidth).  No-op when sysfs
+    does not say where the GPU sits or none of those CPUs is allowed."""
+
+    def __init__(self, torch, dev):
+        self.old, self.node = None, None
+        try:
+            pr = torch.cuda.get_device_properties(dev)
+            bus = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            self.node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+            cpus = set()
+            for part in open(f"/sys/devices/system/node/node{self.node}/cpulist").read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            self.cpus = cpus & os.sched_getaffinity(0)
+        except Exception:
+            self.cpus = set()
+
+    def __enter__(self):
+        if self.cpus:
+            self.old = os.sched_getaffinity(0)
+            os.sched_setaffinity(0, self.cpus)
+        return self
+
+    def __exit__(self, *exc):
+        if self.old is not None:
+            os.sched_setaffinity(0, self.old)
+        return False
+
+
 def physical_gpu_index(local_index):
     vis = os.environ.get("CUDA_VISIBLE_DEVICES")
     if vis:
@@ -434,17 +465,29 @@ def run_ours(args):
     if not args.no_e2e:
         h = host_sets[0]
         pin = lambda x: x.contiguous().pin_memory()
-        hs, ht = pin(h.s_logits), pin(h.t_logits)
-        hf, htf = pin(h.feat.transpose(1, 2)), pin(h.teacher.transpose(1, 2))      # (B,D,N) storage order
-        hm = pin(h.mask)
+        numa = near_gpu(torch, dev)
+        with numa:
+            hs, ht = pin(h.s_logits), pin(h.t_logits)
+            hf, htf = pin(h.feat.transpose(1, 2)), pin(h.teacher.transpose(1, 2))      # (B,D,N) storage order
+            hm = pin(h.mask)
         # Three streams, two buffer sets: the H2D copies of step k+1 and the D2H copies of step k-1 overlap the
         # kernels of step k (PCIe is full duplex).  Every step still copies all of its inputs in and its loss and
         # both gradients out inside the timed region; the pipeline only hides the copies behind each other.
         dbuf = [dict(s=torch.empty_like(hs, device=dev), t=torch.empty_like(ht, device=dev),
                      f=torch.empty_like(hf, device=dev), tf=torch.empty_like(htf, device=dev),
                      m=torch.empty_like(hm, device=dev)) for _ in range(2)]
-        obuf = [dict(gs=torch.empty_like(hs).pin_memory(), gf=torch.empty((B, N, D)).pin_memory(),
-                     loss=torch.empty(()).pin_memory()) for _ in range(2)]
+        with numa:
+            obuf = [dict(gs=torch.empty_like(hs).pin_memory(), gf=torch.empty((B, N, D)).pin_memory(),
+                         loss=torch.empty(()).pin_memory()) for _ in range(2)]
+        # what this box's PCIe link gives a plain pinned copy (explains e2e, which is copy-bound)
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dbuf[0]["s"].copy_(hs, non_blocking=True)
+        pe0.record()
+        for _ in range(4):
+            dbuf[0]["s"].copy_(hs, non_blocking=True)
+        pe1.record()
+        torch.cuda.synchronize()
+        h2d_gbs = 4 * hs.numel() * 4 / (pe0.elapsed_time(pe1) * 1e-3) / 1e9
         h2d = sum(x.numel() * 4 for x in (hs, ht, hf, htf, hm))
         d2h = (obuf[0]["gs"].numel() + obuf[0]["gf"].numel() + 1) * 4
         st_in, st_out = torch.cuda.Stream(), torch.cuda.Stream()
@@ -506,6 +549,7 @@ def run_ours(args):
             ms_e2e = float(t)
         e2e = {"value": voxels * world / (ms_e2e / args.steps * 1e-3), "unit": "voxels/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
+               "h2d_gbs_plain_copy": h2d_gbs, "gpu_numa_node": numa.node,
                "note": "pinned host inputs copied in, loss + both gradients copied out, every step; copies of "
                        "neighbouring steps overlap the kernels (3 streams, 2 buffer sets)"}
 

@@ -9,7 +9,7 @@ $B > gpurun_out/plain_$tag.log 2>&1 || { tail -20 gpurun_out/plain_$tag.log; exi
 ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_$tag.csv $B > gpurun_out/ncu_l_$tag.log 2>&1
 # DYCON_NO_PDL=1: ncu serialises kernels anyway, and its kernel replay is happier without programmatic launches
 DYCON_NO_PDL=1 ncu --set full --clock-control none --import-source on -k regex:"fecl_tc_sweep" -s 15 -c 3 -o gpurun_out/prof_${tag}_sweeps $B > gpurun_out/ncu_f_${tag}_sweeps.log 2>&1
-DYCON_NO_PDL=1 ncu --set full --clock-control none --import-source on -k regex:"fecl_tc_bwd|uncl_|pack16" -s 12 -c 4 -o gpurun_out/prof_${tag}_rest $B > gpurun_out/ncu_f_${tag}_rest.log 2>&1
+DYCON_NO_PDL=1 ncu --set full --clock-control none --import-source on -k regex:"fecl_tc_bwd|uncl_|pack16|zero_fill" -s 15 -c 5 -o gpurun_out/prof_${tag}_rest $B > gpurun_out/ncu_f_${tag}_rest.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"ema_" -s 3 -c 1 -o gpurun_out/prof_${tag}_ema $B > gpurun_out/ncu_e_$tag.log 2>&1
 grep -h "ERROR\|passes" gpurun_out/ncu_f_${tag}_*.log gpurun_out/ncu_e_$tag.log | head
 tail -c 400 gpurun_out/bench_$tag.json

@@ -3,6 +3,7 @@
 
     python tools/ncu_summary.py launches gpurun_out/launches.csv            > profiles/rNN_launches.md
     python tools/ncu_summary.py full     gpurun_out/prof.ncu-rep [regex]    > profiles/rNN_<kernel>.md
+    python tools/ncu_summary.py traffic  a.ncu-rep b.ncu-rep ...            > profiles/rNN_traffic.json
 
 `launches` reads the CSV written by `ncu --metrics gpu__time_duration.sum --csv --log-file ...`;
 `full` reads a `--set full` report through `ncu -i ... --page raw/source --csv` (no GPU needed).
@@ -97,8 +98,33 @@ def full(rep, regex=None):
         print()
 
 
+def traffic(reps):
+    """DRAM bytes read / written and duration of the first captured launch of every kernel (JSON)."""
+    import json
+    out = collections.OrderedDict()
+    for rep in reps:
+        rows = ncu_csv(rep, "raw")
+        h, units = rows[0], rows[1]
+        ki = h.index("Kernel Name")
+        col = {m: h.index(m) for m in ("dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__time_duration.sum")}
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "nsecond": 1e-3, "us": 1.0,
+                 "usecond": 1.0, "ms": 1e3, "msecond": 1e3}
+        val = lambda r, m: float(r[col[m]].replace(",", "")) * scale[units[col[m]]]
+        for r in rows[2:]:
+            name = re.sub(r"^.*>::", "", short(r[ki]))
+            if name not in out:
+                out[name] = {"dram_read_bytes": val(r, "dram__bytes_read.sum"),
+                             "dram_write_bytes": val(r, "dram__bytes_write.sum"),
+                             "duration_us": round(val(r, "gpu__time_duration.sum"), 3)}
+    print(json.dumps({"source": "ncu --set full, B200, BraTS19 shape B=4 N=1728 D=256 fp16, one launch per kernel, caches "
+                                "flushed by ncu between replays (see the step_kernels / ema summaries next to this file)",
+                      "kernels": out}, indent=1))
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2])
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2:])
     else:
         full(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
