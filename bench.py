@@ -49,18 +49,33 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--profile-ranges", action="store_true",
+                    help="only run the per-family launch loops, each inside a cudaProfilerStart/Stop range (for "
+                         "`ncu --replay-mode range`: DRAM bytes per family including the write-backs); prints no bench line")
+    ap.add_argument("--no-parity", action="store_true",
+                    help="N > 1: skip the multi-rank parity block (CPU oracle on the concatenated batch, rank 0)")
     ap.add_argument("--global-negatives", action="store_true",
                     help="BASELINE config 5: FeCL contrasts every row against the rows of all samples of all ranks")
     return ap.parse_args()
 
 
-def peaks():
+def peaks(clocks=None):
+    """Roofline denominators: MEASURED_PEAKS.json (driver-written) or the profiling recipe's fallback.  The tensor
+    peak is the BURST figure when the SM clock sampled during the timed region sat at (>= 95 % of) its maximum --
+    a step of ~0.1 ms never reaches the power cap -- and the sustained figure otherwise; `tensor_kind` says which."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         p = json.load(open(path))
-        return {"hbm": p["hbm_gbs"], "tensor_burst": p["bf16_tflops"],
-                "tensor": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
-    return {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor": 1400.0, "source": "fallback"}
+        pk = {"hbm": p["hbm_gbs"], "tensor_burst": p["bf16_tflops"],
+              "tensor_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    else:
+        pk = {"hbm": 6650.0, "tensor_burst": 1590.0, "tensor_sustained": 1400.0, "source": "fallback"}
+    at_max = True
+    if clocks and clocks.get("sm_mhz") and clocks.get("sm_max_mhz"):
+        at_max = clocks["sm_mhz"] >= 0.95 * clocks["sm_max_mhz"]
+    pk["tensor_kind"] = "burst" if at_max else "sustained"
+    pk["tensor"] = pk["tensor_burst"] if at_max else pk["tensor_sustained"]
+    return pk
 
 
 def workload_name(args, n_gpus):
@@ -170,19 +185,34 @@ def physical_gpu_index(local_index):
 
 # ----------------------------------------------------------------------------------------- CPU arm
 def cpu_time_reference(args, steps, warmup, budget_s=150.0):
-    """Times the oracle port (oracle/torch_port.py: the reference's op chain + autograd) on the host
-    cores.  Returns (voxels_per_s, ms_per_step, sample description, cores)."""
+    """Times the reference's own CPU implementation of the path on the host cores: the UNMODIFIED
+    code/utils/dycon_losses.py (from /root/reference here, from the git-ignored copy under baseline/_ref on the
+    GPU box; kind "reference"), else the oracle port (oracle/torch_port.py: the same op chain + autograd; kind
+    "port").  Returns (voxels_per_s, ms_per_step, sample description, cores, kind)."""
     import torch
     from dycon_paper_replication_b200.synthetic import make_inputs
-    from oracle import torch_port
+    from oracle import ref_loader, torch_port
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    kind = "port"
+    fecl_fn = lambda f, m, t: torch_port.fecl_loss(f, m, t, None, EPOCH, **CTOR)
+    uncl_fn = lambda s, t: torch_port.uncl_loss(s, t, BETA)
+    if ref_loader.available():
+        try:
+            ref = ref_loader.dycon_losses()
+            fecl_mod = ref.FeCLoss(device="cpu", **CTOR)
+            uncl_mod = ref.UnCLoss()
+            fecl_fn = lambda f, m, t: fecl_mod(feat=f, mask=m, teacher_feat=t, gambling_uncertainty=None, epoch=EPOCH)
+            uncl_fn = lambda s, t: uncl_mod(s, t, BETA)
+            kind = "reference"
+        except Exception as err:       # keep the arm alive: fall back to the port and say so
+            sys.stderr.write(f"bench.py: reference module unusable ({type(err).__name__}: {err}); timing the port\n")
 
     def one(inp):
         s = inp.s_logits.clone().requires_grad_(True)
         f = inp.feat.clone().requires_grad_(True)
-        fl = torch_port.fecl_loss(f, inp.mask, inp.teacher, None, EPOCH, **CTOR)
-        ul = torch_port.uncl_loss(s, inp.t_logits, BETA)
+        fl = fecl_fn(f, inp.mask, inp.teacher)
+        ul = uncl_fn(s, inp.t_logits)
         (U_WEIGHT * (fl + ul)).backward()
         return float((fl + ul).detach())
 
@@ -203,9 +233,11 @@ def cpu_time_reference(args, steps, warmup, budget_s=150.0):
         one(inp)
         times.append(time.perf_counter() - t0)
     med = statistics.median(times)
+    what = ("the unmodified reference modules (code/utils/dycon_losses.py)" if kind == "reference"
+            else "the oracle port of the reference op chain")
     sample = (f"{steps} timed steps (after {warmup} warm-up) of UnCL+FeCL fwd+bwd on B={batch} of the "
-              f"{args.batch}-sample {args.shape} batch, fp32, {torch.get_num_threads()} torch threads, median")
-    return inp.voxels / med, med * 1e3, sample, torch.get_num_threads()
+              f"{args.batch}-sample {args.shape} batch, {what}, fp32, {torch.get_num_threads()} torch threads, median")
+    return inp.voxels / med, med * 1e3, sample, torch.get_num_threads(), kind
 
 
 def run_reference_eager_gpu(args):
@@ -260,20 +292,104 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    vps, ms, sample, cores = cpu_time_reference(args, args.steps, args.warmup)
+    vps, ms, sample, cores, kind = cpu_time_reference(args, args.steps, args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": vps, "unit": "voxels/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args, 1), "arm": "host CPU only; GPUs idle"},
-            "cpu_baseline": {"value": vps, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": vps, "unit": "voxels/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": vps, "unit": "voxels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
+# ----------------------------------------------------------------------------------------- N > 1 parity
+def multi_rank_parity(args, world, precision, seeds, loss_f, loss_u, grads_f, grads_s, check_ranks):
+    """Rank 0, after the timed region: the fp64 closed-form oracle (oracle/closed_form.py, pinned to the
+    unmodified reference by tests/test_oracle_golden.py) on the CONCATENATED batch of all ranks -- regenerated on
+    the host from the per-rank seeds -- against what the sharded CUDA path returned: the global losses and the
+    gradient slices of `check_ranks`.  FeCL with global negatives: the reference on feat.reshape(1, B_all*N, D)."""
+    import numpy as np
+    from dycon_paper_replication_b200.synthetic import make_inputs
+    from oracle import closed_form, torch_port
+    t_start = time.time()
+    thr = torch_port.ramp_threshold(EPOCH, CTOR["rampup_epochs"], 0.3, 0.5)
+    kw = dict(inv_tau=1.0 / CTOR["temperature"], gamma=CTOR["gamma"], use_focal=CTOR["use_focal"], cross_thresh=thr,
+              lambda_cross=1.0, go=U_WEIGHT)
+    inps = [make_inputs(args.shape, batch=args.batch, dim=args.dim, seed=sd) for sd in seeds]
+    Bl = args.batch
+    B_all = Bl * world
+    _, N, D = inps[0].feat.shape
+    V = inps[0].s_logits[0, 0].numel()
+    tol_f = 1e-5 if precision == "fp32" else 2e-3
+    amb = {"fp32": 2e-6, "fp16": 5e-4, "bf16": 4e-3}[precision]
+    out = {"oracle": "oracle/closed_form.py (fp64) on the concatenated batch of all ranks", "ranks_checked": list(check_ranks)}
+    # ---- UnCL: per-voxel, so per-rank sums add up
+    u_sum, u_err = 0.0, 0.0
+    for r, inp in enumerate(inps):
+        ref = closed_form.uncl(inp.s_logits.numpy(), inp.t_logits.numpy(), BETA, go=U_WEIGHT, count=B_all * V)
+        u_sum += ref["sum"]
+        if r in check_ranks:
+            g = grads_s[check_ranks.index(r)]
+            u_err = max(u_err, float(np.abs(g - ref["grad"]).max() / np.abs(ref["grad"]).max()))
+    u_ref = u_sum / (B_all * V)
+    out["uncl_loss_rel_err"] = abs(loss_u - u_ref) / abs(u_ref)
+    out["uncl_grad_err"] = u_err
+    # ---- FeCL
+    if args.global_negatives:
+        import torch
+        feat = torch.cat([i.feat for i in inps]).reshape(1, B_all * N, D).numpy()
+        teacher = torch.cat([i.teacher for i in inps]).reshape(1, B_all * N, D).numpy()
+        mask = torch.cat([i.mask for i in inps]).reshape(1, B_all * N).numpy()
+        r0 = check_ranks[0]
+        rows = (r0 * Bl * N, r0 * Bl * N + min(Bl * N, 2048))      # the loss covers all rows; the gradient a slice
+        ref = closed_form.fecl_blocked(feat, mask, teacher, None, grad_rows=rows, block=1024, **kw)
+        got = grads_f[0].reshape(Bl * N, D)[:rows[1] - rows[0]]
+        out["fecl_loss_rel_err"] = abs(loss_f - ref["loss"]) / abs(ref["loss"])
+        out["fecl_grad_err"] = float(np.abs(got - ref["grad"]).max() / np.abs(ref["grad"]).max())
+        out["fecl_grad_rows_checked"] = list(rows)
+        out["fecl_comparator"] = "plain max|dg|/max|g| (no flip tolerance)"
+    else:
+        per = []          # first pass: per-sample sums (the hard-negative count is batch-global, dycon_losses.py:229)
+        for inp in inps:
+            for b in range(Bl):
+                per.append(closed_form.fecl(inp.feat[b:b + 1].numpy(), inp.mask[b:b + 1].numpy(), inp.teacher[b:b + 1].numpy(),
+                                            None, rows_global=B_all * N, **kw))
+        student = sum(p["student_sum"] for p in per)
+        cross, cnt = sum(p["cross_sum"] for p in per), sum(p["cnt"] for p in per)
+        f_ref = student / (B_all * N) + cross / (cnt + 1e-18)
+        out["fecl_loss_rel_err"] = abs(loss_f - f_ref) / abs(f_ref)
+        plain, fitted = 0.0, 0.0
+        gmax = 0.0
+        refs = {}
+        for r in check_ranks:             # second pass with the global count: this rank's gradient slice
+            for b in range(Bl):
+                inp = inps[r]
+                refs[(r, b)] = closed_form.fecl(inp.feat[b:b + 1].numpy(), inp.mask[b:b + 1].numpy(),
+                                                inp.teacher[b:b + 1].numpy(), None, rows_global=B_all * N,
+                                                cnt_global=cnt, ambiguity=amb, **kw)
+                gmax = max(gmax, float(np.abs(refs[(r, b)]["grad"]).max()))
+        for (r, b), ref in refs.items():
+            g = grads_f[check_ranks.index(r)][b:b + 1]
+            scale = float(np.abs(ref["grad"]).max()) / gmax     # errors relative to the max over the checked batch
+            plain = max(plain, float(np.abs(g - ref["grad"]).max() / gmax))
+            # the comparator divides by the sample's own max; rescale.  cnt of the flip bookkeeping is the global one
+            ref = dict(ref, cnt=cnt)
+            fitted = max(fitted, closed_form.fecl_grad_error(g, ref, inps[r].teacher[b:b + 1].numpy()) * scale)
+        out["fecl_grad_err_plain"] = plain
+        out["fecl_grad_err"] = fitted
+        out["fecl_comparator"] = "threshold-boundary pairs (|cs - theta| <= %g) may flip; plain error beside it" % amb
+    out["tol"] = {"uncl": 1e-5, "fecl": tol_f}
+    out["ok"] = bool(out["uncl_loss_rel_err"] <= 1e-5 and out["uncl_grad_err"] <= 1e-5 and
+                     out["fecl_loss_rel_err"] <= tol_f and out["fecl_grad_err"] <= tol_f)
+    out["oracle_seconds"] = time.time() - t_start
+    return out
+
+
 # ----------------------------------------------------------------------------------------- GPU arm
-def family_times(torch, _lib, dev, sets, precision, beta, reps=40):
-    """Average launch duration (ms) of the four kernel families through the C ABI, back-to-back launches."""
+def family_times(torch, _lib, dev, sets, precision, beta, reps=40, profile=False):
+    """Average launch duration (ms) of the four kernel families through the C ABI, back-to-back launches.
+    profile=True: every family's loop runs inside its own cudaProfilerStart/Stop range instead of being timed."""
     import ctypes
     from dycon_paper_replication_b200 import dycon_losses as dl
     L = _lib.lib()
@@ -326,6 +442,14 @@ def family_times(torch, _lib, dev, sets, precision, beta, reps=40):
         for d in per:
             fn(d)
         torch.cuda.synchronize()
+        if profile:
+            torch.cuda.profiler.start()
+            for r in range(reps):
+                fn(per[r % len(per)])
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+            out[name] = reps
+            continue
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda._sleep(int(40e6))
         e0.record()
@@ -398,6 +522,14 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    if args.profile_ranges:
+        for k in range(len(sets)):
+            step(k)
+        torch.cuda.synchronize()
+        order = family_times(torch, _lib, dev, sets, precision, BETA, profile=True)
+        print(json.dumps({"profile_ranges": list(order), "launches_per_range": 40,
+                          "note": "ranges appear in this order in the ncu range-replay report"}), flush=True)
+        return
     sampler = ClockSampler(physical_gpu_index(local)) if rank == 0 else None
     # warm-up (eager) on a side stream, then capture one CUDA graph per rotating input set: the step
     # (~0.3 ms of GPU work in ~12 launches) is otherwise bound by Python/launch overhead, not by the GPU
@@ -453,6 +585,26 @@ def run_ours(args):
     # duration without the ~2-4 us that an event pair around a single short call adds.  This is the figure the
     # roofline uses; the single-call figures are kept beside it.
     fam_ms = {} if args.global_negatives else family_times(torch, _lib, dev, sets, precision, BETA)
+    # ---- N > 1: what the sharded path RETURNS, checked on rank 0 against the oracle on the concatenated batch --
+    parity = None
+    if world > 1 and not args.no_parity:
+        s0, t0_, f0, tf0, m0 = sets[0]
+        s0.grad = None
+        f0.grad = None
+        lf = fecl(feat=f0, mask=m0, teacher_feat=tf0, gambling_uncertainty=None, epoch=EPOCH)
+        lu = uncl(s0, t0_, BETA)
+        (U_WEIGHT * (lf + lu)).backward()
+        check = sorted({0, world - 1})
+        gf_mine, gs_mine = f0.grad.contiguous(), s0.grad.contiguous()
+        gfs = [torch.empty_like(gf_mine) for _ in range(world)] if rank == 0 else None
+        gss = [torch.empty_like(gs_mine) for _ in range(world)] if rank == 0 else None
+        dist.gather(gf_mine, gfs, dst=0)
+        dist.gather(gs_mine, gss, dst=0)
+        torch.cuda.synchronize()
+        if rank == 0:
+            parity = dict(loss_f=float(lf), loss_u=float(lu), gf=[gfs[r].cpu().numpy() for r in check],
+                          gs=[gss[r].cpu().numpy() for r in check], check=check)
+        del gfs, gss
     if world > 1:
         t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -591,7 +743,7 @@ def run_ours(args):
         return
 
     # ---- roofline ------------------------------------------------------------------------------------
-    pk = peaks()
+    pk = peaks(clocks)
     single = {k: statistics.median(v) for k, v in calls.items()}
     avg = dict(single)
     avg.update(fam_ms)
@@ -599,9 +751,12 @@ def run_ours(args):
     flops_fwd = 4.0 * pairs * D                # S (2) + cross (2)         SURVEY.md 8(d)
     flops_bwd = 6.0 * pairs * D                # (G+G^T)F (4) + Gc T (2)
     of = pk["source"]
+    # UnCL: `achieved` counts the bytes the kernels MOVE (fwd 16 B read + 4 B stash write, bwd 4 B read + 8 B
+    # write = 32 B/voxel); SURVEY 8(d)'s 40 B/voxel recompute model credits bytes this design never moves and is
+    # kept beside it as `survey_gbs` / `survey_frac`.
     fam = {
-        "uncl_fwd": {"bound": "hbm", "algorithmic": 16.0 * voxels, "moved": 20.0 * voxels},
-        "uncl_bwd": {"bound": "hbm", "algorithmic": 24.0 * voxels, "moved": 12.0 * voxels},
+        "uncl_fwd": {"bound": "hbm", "algorithmic": 20.0 * voxels, "survey": 16.0 * voxels},
+        "uncl_bwd": {"bound": "hbm", "algorithmic": 12.0 * voxels, "survey": 24.0 * voxels},
         "fecl_fwd": {"bound": "tensor", "algorithmic": flops_fwd},
         "fecl_bwd": {"bound": "tensor", "algorithmic": flops_bwd},
     }
@@ -611,36 +766,36 @@ def run_ours(args):
             continue
         sec = avg[name] * 1e-3
         if spec["bound"] == "hbm":
-            ach, peak, unit = spec["algorithmic"] / sec / 1e9, pk["hbm"], "GB/s"
+            ach, peak, unit, src = spec["algorithmic"] / sec / 1e9, pk["hbm"], "GB/s", f"of {of}"
         else:
             ach, peak, unit = spec["algorithmic"] / sec / 1e12, pk["tensor"], "TFLOP/s"
+            src = f"of {of}, {pk['tensor_kind']} bf16 peak"
         roof_all[name] = {"bound": spec["bound"], "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak,
-                          "traffic": None, "avg_ms": avg[name], "peak_source": f"of {of}",
+                          "traffic": None, "avg_ms": avg[name], "peak_source": src,
                           "timing": "40 back-to-back launches between one CUDA event pair",
                           "avg_ms_single_call": single.get(name)}
-        if "moved" in spec:
-            roof_all[name]["moved_gbs"] = spec["moved"] / sec / 1e9
+        if "survey" in spec:
+            roof_all[name]["survey_gbs"] = spec["survey"] / sec / 1e9
     if "uncl_fwd" in avg and "uncl_bwd" in avg:
         sec = (avg["uncl_fwd"] + avg["uncl_bwd"]) * 1e-3
-        roof_all["uncl_pair"] = {"bound": "hbm", "achieved": 40.0 * voxels / sec / 1e9, "peak": pk["hbm"],
-                                 "unit": "GB/s", "frac": 40.0 * voxels / sec / 1e9 / pk["hbm"], "traffic": None,
-                                 "moved_gbs": 32.0 * voxels / sec / 1e9, "avg_ms": sec * 1e3,
-                                 "note": "40 B/voxel algorithmic (SURVEY 8d); the stash design moves 32 B/voxel"}
+        roof_all["uncl_pair"] = {"bound": "hbm", "achieved": 32.0 * voxels / sec / 1e9, "peak": pk["hbm"],
+                                 "unit": "GB/s", "frac": 32.0 * voxels / sec / 1e9 / pk["hbm"], "traffic": None,
+                                 "survey_gbs": 40.0 * voxels / sec / 1e9,
+                                 "survey_frac": 40.0 * voxels / sec / 1e9 / pk["hbm"], "avg_ms": sec * 1e3,
+                                 "note": "achieved = the 32 B/voxel the stash design moves; survey_* = SURVEY 8(d)'s "
+                                         "40 B/voxel recompute accounting"}
     roof_all["ema"] = {"bound": "hbm", "achieved": 12.0 * n_params / (ema_ms * 1e-3) / 1e9, "peak": pk["hbm"],
                        "unit": "GB/s", "frac": 12.0 * n_params / (ema_ms * 1e-3) / 1e9 / pk["hbm"], "traffic": None,
                        "avg_ms": ema_ms, "params": n_params}
-    # traffic: DRAM bytes per launch (read + write) of each family's kernels, from the committed ncu --set full
-    # capture (profiles/r1_traffic.json) -- not re-measured here (a run under ncu is never a bench run)
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")
+    # traffic: DRAM bytes per launch (read + write) of each family, from the committed ncu RANGE capture of
+    # `bench.py --profile-ranges` (40 rotating launches per range, so write-backs are evicted and counted) --
+    # not re-measured here (a run under ncu is never a bench run)
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")
     if os.path.exists(tpath) and args.shape == "brats19" and args.batch == 4 and args.dim == 256:
-        tk = json.load(open(tpath))["kernels"]
-        tot = lambda pref: sum(v["dram_read_bytes"] + v["dram_write_bytes"] for k, v in tk.items() if k.startswith(pref))
-        fams = {"uncl_fwd": ("uncl_fwd",), "uncl_bwd": ("uncl_bwd",), "fecl_fwd": ("pack16", "fecl_tc_sweep"),
-                "fecl_bwd": ("fecl_tc_bwd",), "ema": ("ema_multi",)}
-        for name, prefs in fams.items():
-            if name in roof_all:
-                t = sum(tot(pf) for pf in prefs)
-                roof_all[name]["traffic"] = t if t > 0 else None
+        tk = json.load(open(tpath)).get("families", {})
+        for name, rec in tk.items():
+            if name in roof_all and rec.get("dram_bytes_per_launch"):
+                roof_all[name]["traffic"] = rec["dram_bytes_per_launch"]
     dominant = max((k for k in fam if k in avg), key=lambda k: avg[k])
     roofline = dict(roof_all[dominant], kernel=dominant,
                     share_of_step=avg[dominant] / sum(avg[k] for k in fam if k in avg))
@@ -659,9 +814,17 @@ def run_ours(args):
             "gpu_launches": int(launches), "clocks": clocks}
     if e2e:
         line["e2e"] = e2e
+    if parity is not None:
+        seeds = [1337 + 101 * r for r in range(world)]
+        try:
+            line["parity"] = multi_rank_parity(args, world, precision, seeds, parity["loss_f"], parity["loss_u"],
+                                               parity["gf"], parity["gs"], parity["check"])
+        except Exception as err:           # never lose the bench line to the checker
+            line["parity"] = {"ok": False, "error": f"{type(err).__name__}: {err}"}
     if n_gpus == 1 and not args.no_cpu_baseline:
-        vps, ms, sample, cores = cpu_time_reference(args, steps=3, warmup=1)
-        line["cpu_baseline"] = {"value": vps, "unit": "voxels/s", "cores": cores, "kind": "port", "sample": sample,
+        # same protocol as the reference arm (bench.py --impl reference), capped so the default run stays short
+        vps, ms, sample, cores, kind = cpu_time_reference(args, steps=min(args.steps, 20), warmup=min(args.warmup, 5))
+        line["cpu_baseline"] = {"value": vps, "unit": "voxels/s", "cores": cores, "kind": kind, "sample": sample,
                                 "ms_per_step": ms}
     print(json.dumps(line), flush=True)
     shutdown(world)

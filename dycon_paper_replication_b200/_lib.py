@@ -15,7 +15,9 @@ SO_PATH = os.path.join(_HERE, "_dycon_b200.so")
 FECL_FP32 = 0
 FECL_BF16 = 1
 FECL_FP16 = 2
+ABI_VERSION = 2
 EXCHANGE_NONE, EXCHANGE_UNCL, EXCHANGE_FECL, EXCHANGE_FECL_TEACHER = 0, 1, 2, 3
+EXCHANGE_CHANNELS = 3
 
 _lock = threading.Lock()
 _lib = None
@@ -50,7 +52,11 @@ PROTOTYPES = {
     "dycon_ema_multi": (_i, [_p, _p, _p, _i, _f, _f, _p]),
     "dycon_exchange_inbox_bytes": (_sz, []),
     "dycon_exchange_enable_peer": (_i, [_i]),
-    "dycon_exchange_sums": (_i, [_p, _i, _p, _p, _i, _i, _p, _i, _d, _d, _p, _p]),
+    "dycon_exchange_error_offset": (_sz, []),
+    "dycon_exchange_sums": (_i, [_p, _i, _p, _p, _i, _i, _p, _i, _d, _d, _p, _d, _p]),
+    "dycon_uncl_fwd_sharded": (_i, [_p, _p, _i64, _i, _i64, _f, _d, _p, _p, _p, _p, _sz, _p, _i, _i, _p, _d, _p]),
+    "dycon_fecl_fwd_sharded": (_i, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, _p, _i, _i, _i,
+                                    _f, _f, _i, _f, _f, _d, _i, _p, _sz, _p, _p, _p, _sz, _p, _i, _i, _p, _d, _p]),
 }
 
 
@@ -74,7 +80,7 @@ def lib():
                 fn = getattr(handle, name)      # AttributeError if the ABI and the header diverge
                 fn.restype = res
                 fn.argtypes = args
-            if handle.dycon_abi_version() != 1:
+            if handle.dycon_abi_version() != ABI_VERSION:
                 raise DyconError("dycon ABI version mismatch")
             _lib = handle
     return _lib

@@ -7,26 +7,21 @@
 // total.  No host involvement: the sequence number lives in device memory and is advanced by the kernel,
 // which keeps the exchange CUDA-graph replayable.
 //
-// Inbox layout (per rank, allocated by the host and shared through CUDA IPC):
-//   [kSlots][kMaxRanks] entries of kEntry doubles: payload[0..6], then the sequence flag (as int64 bits).
-// Two slots alternate with the sequence parity: a peer can only be one call ahead of this rank (it needs this
-// rank's message of call k to finish call k), so the slot of call k is no longer read when call k+2 writes it.
-#include "common.cuh"
+// The protocol (inbox layout, slots, channels, time-out) is in exchange.cuh; the UnCL forward and the FeCL P2
+// sweep run it in their own tail (dycon_uncl_fwd_sharded / dycon_fecl_fwd_sharded), this file is the
+// stand-alone launch for everything else.
+#include "exchange.cuh"
+
+#include <cstdlib>
 
 namespace dycon {
 namespace {
 
-constexpr int kSlots = 2;
-constexpr int kMaxRanks = 16;
-constexpr int kEntry = 8;           // doubles per entry: 7 payload + 1 flag
-constexpr int kMaxPayload = 7;
-
 struct ExchangeParams {
-  double* inbox[kMaxRanks];         // inbox[r] = base of rank r's inbox (peer-mapped device pointers)
+  ExchangeCtx x;
   const double* local;              // n partial sums of this rank
   double* out;                      // n totals
-  unsigned long long* seq;          // device counter, advanced once per call
-  int n, rank, world;
+  int n;
   int kind;                         // DYCON_EXCHANGE_*: which loss to evaluate from the totals (0: none)
   double scale, lambda;             // 1/(B_global V) or 1/(B_global N); lambda_cross
   float* loss_out;
@@ -35,59 +30,56 @@ struct ExchangeParams {
 __global__ void __launch_bounds__(32)
 exchange_sums_kernel(const __grid_constant__ ExchangeParams p) {
   const int lane = threadIdx.x;
-  const unsigned long long seq = *p.seq + 1;                 // every lane reads the same value
-  const int slot = (int)(seq & (kSlots - 1));
-  if (lane < p.world) {
-    // ---- send: my partials into slot[seq][my rank] of peer `lane` (my own inbox included) ----
-    double* dst = p.inbox[lane] + ((size_t)slot * kMaxRanks + p.rank) * kEntry;
-    for (int k = 0; k < p.n; ++k) dst[k] = p.local[k];
-    __threadfence_system();                                  // payload before flag, at system scope
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long*>(dst + kMaxPayload)),
-                 "l"(seq)
-                 : "memory");
-    // ---- receive: wait for peer `lane`'s entry in MY inbox ----
-    const double* src = p.inbox[p.rank] + ((size_t)slot * kMaxRanks + lane) * kEntry;
-    unsigned long long got = 0;
-    unsigned int spins = 0;
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got)
-                   : "l"(reinterpret_cast<const unsigned long long*>(src + kMaxPayload))
-                   : "memory");
-      if (got != seq) {
-        __nanosleep(100);
-        if (++spins > (1u << 27)) __trap();                  // a peer never arrived: fail the launch, do not hang
-      }
-    } while (got != seq);
+  const double acc = exchange_warp(p.x, lane < p.n ? p.local[lane] : 0.0, p.n);
+  if (lane < p.n) p.out[lane] = acc;
+  // the loss from the reduced sums, in the same launch (dycon_losses.py:116-118 / :193,229-234)
+  const double t1 = __shfl_sync(0xffffffffu, acc, 1), t2 = __shfl_sync(0xffffffffu, acc, 2);
+  if (lane == 0 && p.loss_out) {
+    if (p.kind == DYCON_EXCHANGE_UNCL) *p.loss_out = (float)(acc * p.scale);
+    if (p.kind == DYCON_EXCHANGE_FECL) *p.loss_out = (float)(acc * p.scale);
+    if (p.kind == DYCON_EXCHANGE_FECL_TEACHER) *p.loss_out = (float)(acc * p.scale + p.lambda * (t1 / (t2 + 1e-18)));
   }
-  __syncwarp();
-  if (lane < p.n) {                                          // fixed rank order: identical result on every rank
-    double acc = 0.0;
-    for (int r = 0; r < p.world; ++r) {
-      const volatile double* src = p.inbox[p.rank] + ((size_t)slot * kMaxRanks + r) * kEntry;
-      acc += src[lane];
-    }
-    p.out[lane] = acc;
-    // the loss from the reduced sums, in the same launch (dycon_losses.py:116-118 / :193,229-234)
-    const double t1 = __shfl_sync((1u << p.n) - 1u, acc, 1 < p.n ? 1 : 0);
-    const double t2 = __shfl_sync((1u << p.n) - 1u, acc, 2 < p.n ? 2 : 0);
-    if (lane == 0 && p.loss_out) {
-      if (p.kind == DYCON_EXCHANGE_UNCL) *p.loss_out = (float)(acc * p.scale);
-      if (p.kind == DYCON_EXCHANGE_FECL) *p.loss_out = (float)(acc * p.scale);
-      if (p.kind == DYCON_EXCHANGE_FECL_TEACHER) *p.loss_out = (float)(acc * p.scale + p.lambda * (t1 / (t2 + 1e-18)));
-    }
-  }
-  __syncwarp();
-  if (lane == 0) *p.seq = seq;
 }
 
 }  // namespace
+
+int make_exchange_ctx(ExchangeCtx* ctx, void* const* peer_inboxes, int rank, int world, unsigned long long* seq_counters,
+                      int channel, double timeout_s) {
+  for (int r = 0; r < kXMaxRanks; ++r) ctx->inbox[r] = nullptr;
+  ctx->seq = seq_counters;
+  ctx->rank = 0; ctx->world = 1; ctx->channel = channel;
+  ctx->timeout_ns = 0;
+  if (world <= 1 && peer_inboxes == nullptr) return DYCON_OK;
+  DYCON_REQUIRE(peer_inboxes && seq_counters, DYCON_ERR_ARG, "exchange: NULL inbox table / sequence counters");
+  DYCON_REQUIRE(world >= 1 && world <= kXMaxRanks && rank >= 0 && rank < world, DYCON_ERR_ARG,
+                "exchange: rank %d / world %d (at most %d ranks)", rank, world, kXMaxRanks);
+  DYCON_REQUIRE(channel >= 0 && channel < kXChannels, DYCON_ERR_ARG, "exchange: channel %d", channel);
+  for (int r = 0; r < world; ++r) {
+    DYCON_REQUIRE(peer_inboxes[r] && aligned(peer_inboxes[r], 16), DYCON_ERR_ARG, "exchange: inbox of rank %d is NULL / misaligned", r);
+    ctx->inbox[r] = reinterpret_cast<double*>(peer_inboxes[r]);
+  }
+  ctx->rank = rank; ctx->world = world;
+  // A rank that lags by more than the timeout (rank-0-only validation, a data-loader stall) makes its peers give
+  // up: they get NaN sums and an error word instead of a destroyed context.  Negative: DYCON_EXCHANGE_TIMEOUT_S
+  // from the environment, default 600 s; 0: wait for ever, like a blocking collective.
+  if (timeout_s < 0) {
+    const char* e = getenv("DYCON_EXCHANGE_TIMEOUT_S");
+    timeout_s = e ? atof(e) : 600.0;
+    if (timeout_s < 0) timeout_s = 0;
+  }
+  ctx->timeout_ns = (unsigned long long)(timeout_s * 1e9);
+  return DYCON_OK;
+}
+
 }  // namespace dycon
 
 using namespace dycon;
 
 extern "C" {
 
-size_t dycon_exchange_inbox_bytes(void) { return sizeof(double) * kSlots * kMaxRanks * kEntry; }
+size_t dycon_exchange_inbox_bytes(void) { return sizeof(double) * kXInboxDoubles; }
+
+size_t dycon_exchange_error_offset(void) { return sizeof(double) * kXChannels * kXSlots * kXMaxRanks * kXEntry; }
 
 int dycon_exchange_enable_peer(int peer_device) {
   int dev = 0, can = 0;
@@ -105,21 +97,15 @@ int dycon_exchange_enable_peer(int peer_device) {
 }
 
 int dycon_exchange_sums(const double* local, int n, double* out, void* const* peer_inboxes, int rank, int world,
-                        unsigned long long* seq_counter, int kind, double scale, double lambda_cross, float* loss_out,
-                        dycon_stream_t stream) {
-  DYCON_REQUIRE(local && out && peer_inboxes && seq_counter, DYCON_ERR_ARG, "exchange: NULL argument");
-  DYCON_REQUIRE(n >= 1 && n <= kMaxPayload, DYCON_ERR_ARG, "exchange: n=%d outside [1, %d]", n, kMaxPayload);
-  DYCON_REQUIRE(world >= 1 && world <= kMaxRanks && rank >= 0 && rank < world, DYCON_ERR_ARG,
-                "exchange: rank %d / world %d (at most %d ranks)", rank, world, kMaxRanks);
-  ExchangeParams p;
-  for (int r = 0; r < kMaxRanks; ++r) p.inbox[r] = nullptr;
-  for (int r = 0; r < world; ++r) {
-    DYCON_REQUIRE(peer_inboxes[r] && aligned(peer_inboxes[r], 16), DYCON_ERR_ARG, "exchange: inbox of rank %d is NULL / misaligned", r);
-    p.inbox[r] = reinterpret_cast<double*>(peer_inboxes[r]);
-  }
+                        unsigned long long* seq_counters, int kind, double scale, double lambda_cross, float* loss_out,
+                        double timeout_s, dycon_stream_t stream) {
+  DYCON_REQUIRE(local && out && peer_inboxes && seq_counters, DYCON_ERR_ARG, "exchange: NULL argument");
+  DYCON_REQUIRE(n >= 1 && n <= kXMaxPayload, DYCON_ERR_ARG, "exchange: n=%d outside [1, %d]", n, kXMaxPayload);
   DYCON_REQUIRE(kind >= 0 && kind <= DYCON_EXCHANGE_FECL_TEACHER && (kind != DYCON_EXCHANGE_FECL_TEACHER || n >= 3),
                 DYCON_ERR_ARG, "exchange: kind=%d with n=%d", kind, n);
-  p.local = local; p.out = out; p.seq = seq_counter; p.n = n; p.rank = rank; p.world = world;
+  ExchangeParams p;
+  if (int rc = make_exchange_ctx(&p.x, peer_inboxes, rank, world, seq_counters, DYCON_CHANNEL_PLAIN, timeout_s)) return rc;
+  p.local = local; p.out = out; p.n = n;
   p.kind = kind; p.scale = scale; p.lambda = lambda_cross; p.loss_out = loss_out;
   exchange_sums_kernel<<<1, 32, 0, as_stream(stream)>>>(p);
   DYCON_CUDA(cudaGetLastError());

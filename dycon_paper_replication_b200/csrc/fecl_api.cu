@@ -1,5 +1,6 @@
 // C-ABI entry points of FeCL (include/dycon_b200.h): argument validation + dispatch on the
 // similarity arithmetic (fp32 SIMT tiles / bf16 tcgen05 tiles).
+#include "exchange.cuh"
 #include "fecl_internal.h"
 
 using namespace dycon;
@@ -13,6 +14,34 @@ int check_shape(int B, int N, int D, int precision) {
   DYCON_REQUIRE((long long)N * N < (1LL << 40), DYCON_ERR_UNSUPPORTED, "FeCL: N=%d too large", N);
   return DYCON_OK;
 }
+
+
+int fecl_fwd_checked(const float* feat, int64_t f_sb, int64_t f_sn, int64_t f_sd, const float* teacher, int64_t t_sb,
+                   int64_t t_sn, int64_t t_sd, const float* labels, const float* row_weight, int B, int N, int D,
+                   float inv_tau, float gamma, int use_focal, float cross_thresh, float lambda_cross, double inv_rows,
+                   int precision, void* state, size_t state_bytes, double* sums_out, float* loss_out, void* workspace,
+                   size_t workspace_bytes, const ExchangeCtx* xc, dycon_stream_t stream) {
+  if (int rc = check_shape(B, N, D, precision)) return rc;
+  DYCON_REQUIRE(feat && labels && state && sums_out && workspace, DYCON_ERR_ARG,
+                "FeCL fwd: NULL feat/labels/state/sums_out/workspace");
+  DYCON_REQUIRE(aligned(feat, 4) && aligned(teacher, 4) && aligned(labels, 4) && aligned(row_weight, 4) &&
+                    aligned(state, 128) && aligned(sums_out, 8) && aligned(workspace, 16),
+                DYCON_ERR_ARG, "FeCL fwd: misaligned pointer");
+  DYCON_REQUIRE(f_sn > 0 && f_sd > 0 && (teacher == nullptr || (t_sn > 0 && t_sd > 0)), DYCON_ERR_ARG,
+                "FeCL fwd: non-positive strides");
+  const int has_teacher = teacher != nullptr;
+  DYCON_REQUIRE(state_bytes >= dycon_fecl_state_bytes(B, N, D, has_teacher, precision), DYCON_ERR_WORKSPACE,
+                "FeCL fwd: state %zu < %zu bytes", state_bytes, dycon_fecl_state_bytes(B, N, D, has_teacher, precision));
+  DYCON_REQUIRE(workspace_bytes >= dycon_fecl_workspace_bytes(B, N, D, precision), DYCON_ERR_WORKSPACE,
+                "FeCL fwd: workspace %zu < %zu bytes", workspace_bytes, dycon_fecl_workspace_bytes(B, N, D, precision));
+  FeclProblem p{B, N, D, has_teacher,
+                FeclScalars{inv_tau, gamma, cross_thresh, lambda_cross, (use_focal && row_weight == nullptr) ? 1 : 0},
+                inv_rows, precision};
+  FeclFwdArgs a{feat, f_sb, f_sn, f_sd, teacher, t_sb, t_sn, t_sd, labels, row_weight, state, sums_out, loss_out, workspace};
+  a.xc = xc;
+  return precision != DYCON_FECL_FP32 ? fecl_tc_fwd(p, a, as_stream(stream)) : fecl_simt_fwd(p, a, as_stream(stream));
+}
+
 
 }  // namespace
 
@@ -34,24 +63,31 @@ int dycon_fecl_fwd(const float* feat, int64_t f_sb, int64_t f_sn, int64_t f_sd, 
                    float inv_tau, float gamma, int use_focal, float cross_thresh, float lambda_cross, double inv_rows,
                    int precision, void* state, size_t state_bytes, double* sums_out, float* loss_out, void* workspace,
                    size_t workspace_bytes, dycon_stream_t stream) {
-  if (int rc = check_shape(B, N, D, precision)) return rc;
-  DYCON_REQUIRE(feat && labels && state && sums_out && workspace, DYCON_ERR_ARG,
-                "FeCL fwd: NULL feat/labels/state/sums_out/workspace");
-  DYCON_REQUIRE(aligned(feat, 4) && aligned(teacher, 4) && aligned(labels, 4) && aligned(row_weight, 4) &&
-                    aligned(state, 128) && aligned(sums_out, 8) && aligned(workspace, 16),
-                DYCON_ERR_ARG, "FeCL fwd: misaligned pointer");
-  DYCON_REQUIRE(f_sn > 0 && f_sd > 0 && (teacher == nullptr || (t_sn > 0 && t_sd > 0)), DYCON_ERR_ARG,
-                "FeCL fwd: non-positive strides");
-  const int has_teacher = teacher != nullptr;
-  DYCON_REQUIRE(state_bytes >= dycon_fecl_state_bytes(B, N, D, has_teacher, precision), DYCON_ERR_WORKSPACE,
-                "FeCL fwd: state %zu < %zu bytes", state_bytes, dycon_fecl_state_bytes(B, N, D, has_teacher, precision));
-  DYCON_REQUIRE(workspace_bytes >= dycon_fecl_workspace_bytes(B, N, D, precision), DYCON_ERR_WORKSPACE,
-                "FeCL fwd: workspace %zu < %zu bytes", workspace_bytes, dycon_fecl_workspace_bytes(B, N, D, precision));
-  FeclProblem p{B, N, D, has_teacher,
-                FeclScalars{inv_tau, gamma, cross_thresh, lambda_cross, (use_focal && row_weight == nullptr) ? 1 : 0},
-                inv_rows, precision};
-  FeclFwdArgs a{feat, f_sb, f_sn, f_sd, teacher, t_sb, t_sn, t_sd, labels, row_weight, state, sums_out, loss_out, workspace};
-  return precision != DYCON_FECL_FP32 ? fecl_tc_fwd(p, a, as_stream(stream)) : fecl_simt_fwd(p, a, as_stream(stream));
+  return fecl_fwd_checked(feat, f_sb, f_sn, f_sd, teacher, t_sb, t_sn, t_sd, labels, row_weight, B, N, D, inv_tau, gamma,
+                          use_focal, cross_thresh, lambda_cross, inv_rows, precision, state, state_bytes, sums_out,
+                          loss_out, workspace, workspace_bytes, nullptr, stream);
+}
+
+int dycon_fecl_fwd_sharded(const float* feat, int64_t f_sb, int64_t f_sn, int64_t f_sd, const float* teacher,
+                           int64_t t_sb, int64_t t_sn, int64_t t_sd, const float* labels, const float* row_weight,
+                           int B, int N, int D, float inv_tau, float gamma, int use_focal, float cross_thresh,
+                           float lambda_cross, double inv_rows, int precision, void* state, size_t state_bytes,
+                           double* sums_out, float* loss_out, void* workspace, size_t workspace_bytes,
+                           void* const* peer_inboxes, int rank, int world, unsigned long long* seq_counters,
+                           double timeout_s, dycon_stream_t stream) {
+  ExchangeCtx xc;
+  if (int rc = make_exchange_ctx(&xc, peer_inboxes, rank, world, seq_counters, DYCON_CHANNEL_FECL, timeout_s)) return rc;
+  if (xc.world == 1 || precision != DYCON_FECL_FP32)      // the tensor-core loss sweep exchanges in its own tail
+    return fecl_fwd_checked(feat, f_sb, f_sn, f_sd, teacher, t_sb, t_sn, t_sd, labels, row_weight, B, N, D, inv_tau,
+                            gamma, use_focal, cross_thresh, lambda_cross, inv_rows, precision, state, state_bytes,
+                            sums_out, loss_out, workspace, workspace_bytes, xc.world > 1 ? &xc : nullptr, stream);
+  if (int rc = fecl_fwd_checked(feat, f_sb, f_sn, f_sd, teacher, t_sb, t_sn, t_sd, labels, row_weight, B, N, D, inv_tau,
+                                gamma, use_focal, cross_thresh, lambda_cross, inv_rows, precision, state, state_bytes,
+                                sums_out, nullptr, workspace, workspace_bytes, nullptr, stream))
+    return rc;
+  return dycon_exchange_sums(sums_out, 3, sums_out, peer_inboxes, rank, world, seq_counters,
+                             teacher ? DYCON_EXCHANGE_FECL_TEACHER : DYCON_EXCHANGE_FECL, inv_rows, lambda_cross, loss_out,
+                             timeout_s, stream);
 }
 
 int dycon_fecl_bwd(const void* state, size_t state_bytes, const float* labels, int B, int N, int D, int has_teacher,

@@ -6,6 +6,8 @@
 
 namespace dycon {
 
+struct ExchangeCtx;   // exchange.cuh
+
 struct FeclProblem {
   int B, N, D;
   int has_teacher;
@@ -31,6 +33,7 @@ struct FeclFwdArgs {
   int merge_B = 0;
   int phase_mask = 15;
   int row_lo = 0, row_hi = -1;
+  const ExchangeCtx* xc = nullptr;   // sharded batch: exchange the three sums in the tail of the loss sweep
 };
 
 struct FeclBwdArgs {

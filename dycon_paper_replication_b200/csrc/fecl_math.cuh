@@ -35,6 +35,7 @@ template <bool kFast>
 __device__ __forceinline__ float f_pow(float x, float g) {
   if (g == 2.f) return x * x;
   if (g == 1.f) return x;
+  if (g == 0.f) return 1.f;      // torch.pow(0., 0.) = 1; __powf(0, 0) would be NaN
   if (g == 3.f) return x * x * x;
   return kFast ? __powf(x, g) : powf(x, g);
 }
@@ -46,7 +47,7 @@ __device__ __forceinline__ void fecl_pos_fwd(float e, float n, const FeclScalars
   const float d = e * rT;
   const float logd = f_log<kFast>(d + kTiny);
   if (sc.focal) {
-    const float omd = 1.f - d;
+    const float omd = fmaxf(1.f - d, 0.f);               // a row without negatives has d = 1 (+ ulp): (1-1)^gamma = 0
     const float w1 = f_pow<kFast>(omd, sc.gamma - 1.f);  // (1-d)^(gamma-1)
     const float w = w1 * omd;
     phi = -logd * w;
@@ -61,7 +62,7 @@ __device__ __forceinline__ void fecl_pos_fwd(float e, float n, const FeclScalars
 template <bool kFast>
 __device__ __forceinline__ float fecl_pos_bwd(float e, float n, const FeclScalars& sc) {
   const float d = e * f_div<kFast>(1.f, e + n + kTiny);
-  const float omd = 1.f - d;
+  const float omd = fmaxf(1.f - d, 0.f);
   if (sc.focal) {
     const float logd = f_log<kFast>(d + kTiny);
     const float w1 = f_pow<kFast>(omd, sc.gamma - 1.f);

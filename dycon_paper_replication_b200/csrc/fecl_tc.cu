@@ -21,7 +21,9 @@
 //                                 MN-major operands from the very stage that produced S | CS.
 // The four forward kernels are chained with programmatic dependent launch.
 #include <cstdlib>
+#include <mutex>
 
+#include "exchange.cuh"
 #include "fecl_internal.h"
 #include "tc_common.cuh"
 
@@ -47,6 +49,14 @@ enum { kNoFocal = 0, kFocalG2 = 1, kFocalAny = 2 };
 //   T = e + n, d = e/T, log2 d = t - log2 T.
 // fwd returns phi2 with phi(d) = -ln2 * phi2 (the -ln2 is applied once per row) and the A-summand
 // phi'(d) d / T;  bwd returns phi'(d) d (1-d).
+// (1-d)^(gamma-1) for any gamma.  A row without negatives (n_i = 0: a single-class sample) has d = 1 (or 1 + ulp),
+// where the reference evaluates (1-1)^gamma = 0: clamp 1-d to >= 0 and take the logarithm of a positive floor, so
+// that gamma > 1 gives 0, gamma == 1 gives 1 (torch.pow(0., 0.) = 1) and nothing turns into NaN.
+__device__ __forceinline__ float pow_gm1(float& omd, float gamma) {
+  omd = fmaxf(omd, 0.f);
+  return ex2_approx((gamma - 1.f) * lg2_approx(fmaxf(omd, 1e-30f)));
+}
+
 template <int kFocal>
 __device__ __forceinline__ void pos_fwd(float t, float e, float n, float gamma, float& phi2, float& a_term) {
   const float T = e + n;
@@ -56,8 +66,9 @@ __device__ __forceinline__ void pos_fwd(float t, float e, float n, float gamma, 
     phi2 = tL;
     a_term = -rT;
   } else {
-    const float d = e * rT, omd = 1.f - d;
-    const float w1 = kFocal == kFocalG2 ? omd : ex2_approx((gamma - 1.f) * lg2_approx(omd));
+    const float d = e * rT;
+    float omd = 1.f - d;
+    const float w1 = kFocal == kFocalG2 ? omd : pow_gm1(omd, gamma);
     const float w = w1 * omd;
     phi2 = tL * w;
     a_term = fmaf(gamma * kLn2 * w1 * d, tL, -w) * rT;
@@ -66,10 +77,11 @@ __device__ __forceinline__ void pos_fwd(float t, float e, float n, float gamma, 
 template <int kFocal>
 __device__ __forceinline__ float pos_bwd(float t, float e, float n, float gamma) {
   const float T = e + n;
-  const float d = e * rcp_approx(T), omd = 1.f - d;
+  const float d = e * rcp_approx(T);
+  float omd = 1.f - d;
   if (kFocal == kNoFocal) return -omd;
   const float tL = t - lg2_approx(T);
-  const float w1 = kFocal == kFocalG2 ? omd : ex2_approx((gamma - 1.f) * lg2_approx(omd));
+  const float w1 = kFocal == kFocalG2 ? omd : pow_gm1(omd, gamma);
   return w1 * omd * fmaf(gamma * kLn2 * d, tL, -omd);
 }
 
@@ -218,6 +230,7 @@ struct SweepParams {
   double* partials;
   double* sums_out;
   float* loss_out;
+  ExchangeCtx x;       // sharded batch (x.world > 1): P2's last block exchanges the three sums with the peers
 };
 
 struct SweepMisc {
@@ -490,12 +503,16 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           }
           const int w0 = i0 + rh * kTM + quarter * 32 - j0 - cb;
           const bool diag_here = w0 + 31 >= 0 && w0 < 16;
-          float cprod = 1.f;       // product of (1 - cs) over this chunk's hard negatives: one log per 16 pairs
+          // one log per FOUR hard negatives (product of their 1 - cs): a factor is 1e-18 (cs == 1 exactly), or
+          // >= 2^-24 (the fp32 spacing below 1), or negative (cs > 1: NaN, like the reference's log of a negative
+          // number), so four regular factors cannot underflow; a group that does falls back to one log per pair
+          float cmin = 1.f;        // smallest factor of the chunk: an even number of negative factors must not cancel
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
             const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
             const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
+            float fac[4];
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               const int c = q * 4 + k;
@@ -511,11 +528,17 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
               // guarantees thresh >= 0, so they are never hard negatives; padded rows are dropped at the end.
               const float cs = w[c];
               const bool hard = !same && cs > p.sc.cross_thresh;
-              cprod *= hard ? (1.f - cs) + kTiny : 1.f;
+              fac[k] = hard ? (1.f - cs) + kTiny : 1.f;
+              cmin = fminf(cmin, fac[k]);
               acc3 += hard ? 1.f : 0.f;
             }
+            const float gp = (fac[0] * fac[1]) * (fac[2] * fac[3]);
+            if (gp < 1e-30f)         // rare: several cs == 1 pairs (or a negative factor) in one group
+              acc2 += (lg2_approx(fac[0]) + lg2_approx(fac[1])) + (lg2_approx(fac[2]) + lg2_approx(fac[3]));
+            else
+              acc2 += lg2_approx(gp);
           }
-          acc2 += lg2_approx(cprod);     // NaN for cs > 1, like the reference's log of a negative number
+          if (cmin < 0.f) acc2 = qnan;
         }
       }
       publish(slot ^ 1, nxt);
@@ -561,14 +584,25 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
     const unsigned int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     if (grid_sum_last_block<3>(red, total_, p.ticket, p.partials, nblocks, bid, scratch, reinterpret_cast<int*>(sStage + 12288)) &&
-        threadIdx.x == 0) {
-      const double student = total_[0] / p.inv_rows_d;
-      p.sums_out[0] = student;
-      p.sums_out[1] = total_[1];
-      p.sums_out[2] = total_[2];
-      if (p.loss_out) {
-        const double cross = p.has_teacher ? total_[1] / (total_[2] + 1e-18) : 0.0;
-        *p.loss_out = (float)(student * p.inv_rows_d + (double)p.sc.lambda_cross * cross);
+        warp == 0) {
+      // totals are in thread 0; with a sharded batch warp 0 runs the exchange (rank-ordered sums of all ranks)
+      double t0 = __shfl_sync(0xffffffffu, total_[0], 0), t1 = __shfl_sync(0xffffffffu, total_[1], 0),
+             t2 = __shfl_sync(0xffffffffu, total_[2], 0);
+      if (p.x.world > 1) {
+        const double tot = exchange_warp(p.x, lane == 0 ? t0 : lane == 1 ? t1 : t2, 3);
+        t0 = __shfl_sync(0xffffffffu, tot, 0);
+        t1 = __shfl_sync(0xffffffffu, tot, 1);
+        t2 = __shfl_sync(0xffffffffu, tot, 2);
+      }
+      if (lane == 0) {
+        const double student = t0 / p.inv_rows_d;
+        p.sums_out[0] = student;
+        p.sums_out[1] = t1;
+        p.sums_out[2] = t2;
+        if (p.loss_out) {
+          const double cross = p.has_teacher ? t1 / (t2 + 1e-18) : 0.0;
+          *p.loss_out = (float)(student * p.inv_rows_d + (double)p.sc.lambda_cross * cross);
+        }
       }
     }
   }
@@ -653,15 +687,17 @@ __device__ __forceinline__ void bwd_pair(float x, float cs, float yi, float m2i,
     pji = fmaf(eji, rji, -1.f);
   } else {
     const float dij = eij * rij, dji = eji * rji;
-    const float oij = fmaf(-eij, rij, 1.f), oji = fmaf(-eji, rji, 1.f);
+    float oij = fmaf(-eij, rij, 1.f), oji = fmaf(-eji, rji, 1.f);
     const float Lij = tij - lg2_approx(Tij), Lji = tji - lg2_approx(Tji);   // log2 d
-    const float aij = fmaf(gl, dij * Lij, -oij), aji = fmaf(gl, dji * Lji, -oji);
     if (kFocal == kFocalG2) {
+      const float aij = fmaf(gl, dij * Lij, -oij), aji = fmaf(gl, dji * Lji, -oji);
       pij = oij * oij * aij;
       pji = oji * oji * aji;
     } else {
-      pij = ex2_approx((gamma - 1.f) * lg2_approx(oij)) * oij * aij;
-      pji = ex2_approx((gamma - 1.f) * lg2_approx(oji)) * oji * aji;
+      const float wij = pow_gm1(oij, gamma), wji = pow_gm1(oji, gamma);     // clamps oij / oji to >= 0
+      const float aij = fmaf(gl, dij * Lij, -oij), aji = fmaf(gl, dji * Lji, -oji);
+      pij = wij * oij * aij;
+      pji = wji * oji * aji;
     }
   }
   const float gpos = fmaf(ki, pij, kj * pji);
@@ -950,7 +986,8 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         const int il = i - p.row_lo;
         const int gb = p.grad_rows ? il / p.grad_rows : b, gn = p.grad_rows ? il - gb * p.grad_rows : i;
         float* dst = p.grad_feat + (int64_t)gb * p.g_sb + (int64_t)gn * p.g_sn + (int64_t)c0 * p.g_sd;
-        if (p.g_sd == 1 && ((p.g_sn | p.g_sb) & 3) == 0) {       // rows contiguous: 16-byte stores
+        if (p.g_sd == 1 && ((p.g_sn | p.g_sb) & 3) == 0 &&
+            (reinterpret_cast<uintptr_t>(p.grad_feat) & 15) == 0) {  // rows contiguous and 16-byte aligned: vector stores
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float o0 = go * v[q * 4], o1 = go * v[q * 4 + 1], o2 = go * v[q * 4 + 2], o3 = go * v[q * 4 + 3];
@@ -1037,6 +1074,20 @@ int set_smem(K kernel) {
   DYCON_CUDA(cudaFuncGetAttributes(&attr, kernel));
   DYCON_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   227 * 1024 - (int)attr.sharedSizeBytes));
+  return DYCON_OK;
+}
+
+// cudaFuncSetAttribute applies to the CURRENT device: run `f` once per device (a process may drive several GPUs).
+template <typename F>
+int once_per_device(F f) {
+  static std::mutex mu;
+  static uint64_t done = 0;      // bit d: device d is set up (devices >= 64 are set up on every call)
+  int dev = 0;
+  DYCON_CUDA(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lock(mu);
+  if (dev < 64 && ((done >> dev) & 1)) return DYCON_OK;
+  if (int rc = f()) return rc;
+  if (dev < 64) done |= uint64_t(1) << dev;
   return DYCON_OK;
 }
 
@@ -1142,21 +1193,19 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   sp.stat_kappa = s.stats + kStatKappa * plane;
   sp.stat_p = s.stats + kStatP * plane;
   sp.ticket = ws.ticket; sp.partials = ws.partials; sp.sums_out = a.sums_out; sp.loss_out = a.loss_out;
+  if (a.xc) sp.x = *a.xc; else make_exchange_ctx(&sp.x, nullptr, 0, 1, nullptr, DYCON_CHANNEL_FECL, 0.0);
   // >= 120 KB of dynamic smem also pins one CTA per SM
   size_t smem = rt01 == 2 ? (size_t)2 * KC * kChunk128 + (size_t)3 * KC * kChunk64 + sizeof(SweepMisc)
                           : (size_t)KC * kChunk128 + (size_t)kSwStages * KC * kChunk64 + sizeof(SweepMisc);
   if (smem < 120 * 1024) smem = 120 * 1024;
-  static const int once = set_smem(fecl_tc_sweep_kernel<0, kBf16, kNoFocal, 1>) |
-                          set_smem(fecl_tc_sweep_kernel<1, kBf16, kNoFocal, 1>) |
-                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kNoFocal, 1>) |
-                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2, 1>) |
-                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 1>) |
-                          set_smem(fecl_tc_sweep_kernel<0, kBf16, kNoFocal, 2>) |
-                          set_smem(fecl_tc_sweep_kernel<1, kBf16, kNoFocal, 2>) |
-                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kNoFocal, 2>) |
-                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2, 2>) |
-                          set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 2>);
-  if (once) return once;
+  if (int rc = once_per_device([] {
+        return set_smem(fecl_tc_sweep_kernel<0, kBf16, kNoFocal, 1>) | set_smem(fecl_tc_sweep_kernel<1, kBf16, kNoFocal, 1>) |
+               set_smem(fecl_tc_sweep_kernel<2, kBf16, kNoFocal, 1>) | set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2, 1>) |
+               set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 1>) | set_smem(fecl_tc_sweep_kernel<0, kBf16, kNoFocal, 2>) |
+               set_smem(fecl_tc_sweep_kernel<1, kBf16, kNoFocal, 2>) | set_smem(fecl_tc_sweep_kernel<2, kBf16, kNoFocal, 2>) |
+               set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2, 2>) | set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 2>);
+      }))
+    return rc;
   DYCON_REQUIRE(smem <= 227 * 1024, DYCON_ERR_UNSUPPORTED, "FeCL tensor-core fwd: %zu bytes of shared memory needed", smem);
   dim3 grid(rb01, splits01, B);
   const CUtensorMap& mapF2 = p.has_teacher ? mapF32 : mapF64;      // mode 2 walks 32-column sub-tiles with a teacher
@@ -1223,9 +1272,11 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
   bp.g_sb = a.g_sb; bp.g_sn = a.g_sn; bp.g_sd = a.g_sd;
   size_t smem = (size_t)KC * kChunk128 + (size_t)kBwdStages * 2 * KC * kChunk32 + 2 * kChunk128 + sizeof(BwdMisc);
   if (smem < 120 * 1024) smem = 120 * 1024;
-  static const int once = set_smem(fecl_tc_bwd_kernel<kBf16, kNoFocal>) | set_smem(fecl_tc_bwd_kernel<kBf16, kFocalG2>) |
-                          set_smem(fecl_tc_bwd_kernel<kBf16, kFocalAny>);
-  if (once) return once;
+  if (int rc = once_per_device([] {
+        return set_smem(fecl_tc_bwd_kernel<kBf16, kNoFocal>) | set_smem(fecl_tc_bwd_kernel<kBf16, kFocalG2>) |
+               set_smem(fecl_tc_bwd_kernel<kBf16, kFocalAny>);
+      }))
+    return rc;
   DYCON_REQUIRE(smem <= 227 * 1024, DYCON_ERR_UNSUPPORTED, "FeCL tensor-core bwd: %zu bytes of shared memory needed", smem);
   static const bool no_pdl = [] {
     const char* e = getenv("DYCON_NO_PDL");

@@ -11,6 +11,7 @@
 // Sums are two-stage and fixed-order (bit-reproducible); the last block to finish reduces the
 // per-block partials, so there is no second launch and no float atomics.
 #include "common.cuh"
+#include "exchange.cuh"
 #include "tc_common.cuh"
 
 namespace dycon {
@@ -119,8 +120,11 @@ __device__ __forceinline__ void set_elem(float& v, int, float x) { v = x; }
 // Block + grid reduction tail of the C == 2 forward.  Warps 1.. leave their partial in shared memory and
 // retire at once (bar.arrive); only warp 0 waits for them, publishes the block partial and takes the
 // ticket, so no warp idles behind the L2 round trip of the atomic.  Fixed order -> bit-reproducible.
+// Sharded batch (x.world > 1): the same warp then runs the partial-sum exchange with the peers (exchange.cuh), so
+// sum_out / loss_out hold the GLOBAL sum / loss and the step has no extra launch for it.
 __device__ __forceinline__ void uncl_finish(float acc, unsigned int* ticket, double* partials, double inv_count,
-                                            double* __restrict__ sum_out, float* __restrict__ loss_out) {
+                                            double* __restrict__ sum_out, float* __restrict__ loss_out,
+                                            const ExchangeCtx& x) {
   __shared__ float warp_part[kThreads / 32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const float w = warp_sum(acc);
@@ -147,10 +151,11 @@ __device__ __forceinline__ void uncl_finish(float acc, unsigned int* ticket, dou
   double tot = 0.0;
   for (unsigned int k = lane; k < nblocks; k += 32) tot += __ldcg(&partials[k]);
   tot = warp_sum(tot);
+  if (lane == 0) *ticket = 0u;
+  if (x.world > 1) tot = exchange_warp(x, tot, 1);
   if (lane == 0) {
     *sum_out = tot;
     if (loss_out) *loss_out = (float)(tot * inv_count);
-    *ticket = 0u;
   }
 }
 
@@ -161,7 +166,7 @@ template <int kVec>
 __global__ void __launch_bounds__(kThreads, 3)
 uncl_fwd_c2_kernel(const float* __restrict__ s, const float* __restrict__ t, int64_t B, int64_t V, float beta,
                    double inv_count, float* __restrict__ stash, unsigned int* ticket, double* partials,
-                   double* __restrict__ sum_out, float* __restrict__ loss_out) {
+                   double* __restrict__ sum_out, float* __restrict__ loss_out, const __grid_constant__ ExchangeCtx xc) {
   using P = Pack<kVec>;
   using vec_t = typename P::type;
   const int64_t nvec = V / kVec;
@@ -203,7 +208,7 @@ uncl_fwd_c2_kernel(const float* __restrict__ s, const float* __restrict__ t, int
       i = nx;
     }
   }
-  uncl_finish(fmaf(beta * kLn2, acc_h, acc), ticket, partials, inv_count, sum_out, loss_out);
+  uncl_finish(fmaf(beta * kLn2, acc_h, acc), ticket, partials, inv_count, sum_out, loss_out, xc);
 }
 
 // ---- C == 2, 16-byte aligned: cp.async pipelined forward ------------------------------------------
@@ -230,7 +235,7 @@ __global__ void __launch_bounds__(kThreads, 4)
 uncl_fwd_c2_pipe_kernel(const float* __restrict__ s, const float* __restrict__ t, int64_t V, int64_t chunks_per_sample,
                         int64_t total_chunks, float beta, double inv_count, float* __restrict__ stash,
                         unsigned int* ticket, double* partials, double* __restrict__ sum_out,
-                        float* __restrict__ loss_out) {
+                        float* __restrict__ loss_out, const __grid_constant__ ExchangeCtx xc) {
   extern __shared__ __align__(16) float4 ring[];          // [kPipeStages][4 streams][kThreads]
   const int tid = threadIdx.x;
   const int step = gridDim.x, cps = (int)chunks_per_sample;
@@ -292,7 +297,7 @@ uncl_fwd_c2_pipe_kernel(const float* __restrict__ s, const float* __restrict__ t
     advance(cur, step);
   }
   cp_async_wait<0>();
-  uncl_finish(fmaf(beta * kLn2, acc_h, acc), ticket, partials, inv_count, sum_out, loss_out);
+  uncl_finish(fmaf(beta * kLn2, acc_h, acc), ticket, partials, inv_count, sum_out, loss_out, xc);
 }
 
 template <int kVec>
@@ -427,6 +432,23 @@ dim3 pick_grid(int64_t B, int64_t work_items_per_sample, int resident) {
   return dim3((unsigned)gx, (unsigned)gy, 1);
 }
 
+// Occupancy of the pipelined forward (per device: a process may drive several GPUs).
+int uncl_pipe_ctas_per_sm(int* out) {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  DYCON_CUDA(cudaGetDevice(&dev));
+  if (dev != cached_dev) {
+    int n = 0;
+    DYCON_CUDA(cudaFuncSetAttribute(uncl_fwd_c2_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPipeSmemBytes));
+    DYCON_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, uncl_fwd_c2_pipe_kernel, kThreads, kPipeSmemBytes));
+    DYCON_REQUIRE(n > 0, DYCON_ERR_DEVICE, "UnCL fwd: cannot place the pipelined kernel (%zu B of shared memory)", kPipeSmemBytes);
+    cached = n;
+    cached_dev = dev;
+  }
+  *out = cached;
+  return DYCON_OK;
+}
+
 int check_common(int64_t B, int C, int64_t V) {
   DYCON_REQUIRE(B > 0 && V > 0, DYCON_ERR_ARG, "UnCL: B=%lld V=%lld must be positive", (long long)B, (long long)V);
   DYCON_REQUIRE(C >= 2 && C <= 1024, DYCON_ERR_UNSUPPORTED, "UnCL: C=%d outside [2, 1024]", C);
@@ -438,13 +460,15 @@ int check_common(int64_t B, int C, int64_t V) {
 
 using namespace dycon;
 
-extern "C" {
+extern "C" size_t dycon_uncl_workspace_bytes(void) { return 16 + sizeof(double) * kMaxPartials; }
 
-size_t dycon_uncl_workspace_bytes(void) { return 16 + sizeof(double) * kMaxPartials; }
+namespace {
 
-int dycon_uncl_fwd(const float* s, const float* t, int64_t B, int C, int64_t V, float beta, double inv_count,
-                   float* stash, double* sum_out, float* loss_out, void* workspace, size_t workspace_bytes,
-                   dycon_stream_t stream) {
+// x == nullptr or x->world == 1: the plain forward.  Otherwise the C == 2 kernels run the exchange of the partial
+// sum in their own tail; the generic-C kernel is followed by the stand-alone exchange launch.
+int uncl_fwd_impl(const float* s, const float* t, int64_t B, int C, int64_t V, float beta, double inv_count,
+                  float* stash, double* sum_out, float* loss_out, void* workspace, size_t workspace_bytes,
+                  const ExchangeCtx& xc, cudaStream_t st) {
   if (int rc = check_common(B, C, V)) return rc;
   DYCON_REQUIRE(s && t && sum_out && workspace, DYCON_ERR_ARG, "UnCL fwd: NULL s/t/sum_out/workspace");
   DYCON_REQUIRE(aligned(s, 4) && aligned(t, 4) && aligned(workspace, 16) && aligned(sum_out, 8), DYCON_ERR_ARG,
@@ -452,33 +476,23 @@ int dycon_uncl_fwd(const float* s, const float* t, int64_t B, int C, int64_t V, 
   DYCON_REQUIRE(workspace_bytes >= dycon_uncl_workspace_bytes(), DYCON_ERR_WORKSPACE,
                 "UnCL fwd: workspace %zu < %zu bytes", workspace_bytes, dycon_uncl_workspace_bytes());
   ReduceWorkspace ws = carve_reduce_workspace(workspace);
-  cudaStream_t st = as_stream(stream);
   if (C == 2) {
     DYCON_REQUIRE(stash && aligned(stash, 4), DYCON_ERR_ARG, "UnCL fwd: C == 2 needs a stash of B*V floats");
     const bool vec = (V % 4 == 0) && aligned(s, 16) && aligned(t, 16) && aligned(stash, 16);
     if (vec) {
-      static const int per_sm = [] {
-        int n = 0;
-        if (cudaFuncSetAttribute(uncl_fwd_c2_pipe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)kPipeSmemBytes) != cudaSuccess ||
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, uncl_fwd_c2_pipe_kernel, kThreads, kPipeSmemBytes) !=
-                cudaSuccess || n < 1)
-          n = 0;
-        return n;
-      }();
-      DYCON_REQUIRE(per_sm > 0, DYCON_ERR_DEVICE, "UnCL fwd: cannot place the pipelined kernel (%zu B of shared memory)",
-                    kPipeSmemBytes);
+      int per_sm = 0;
+      if (int rc = uncl_pipe_ctas_per_sm(&per_sm)) return rc;
       const int64_t cps = (V + kPipeChunk - 1) / kPipeChunk, total = cps * B;
       int64_t grid = (int64_t)per_sm * sm_count();
       if (grid > total) grid = total;
       if (grid > kMaxPartials) grid = kMaxPartials;
       uncl_fwd_c2_pipe_kernel<<<(unsigned)grid, kThreads, kPipeSmemBytes, st>>>(
-          s, t, V, cps, total, beta, inv_count, stash, ws.ticket, ws.partials, sum_out, loss_out);
+          s, t, V, cps, total, beta, inv_count, stash, ws.ticket, ws.partials, sum_out, loss_out, xc);
     } else {
       static const int res = resident_ctas(uncl_fwd_c2_kernel<1>);
       dim3 grid = pick_grid(B, V, res);
       uncl_fwd_c2_kernel<1><<<grid, kThreads, 0, st>>>(s, t, B, V, beta, inv_count, stash, ws.ticket, ws.partials,
-                                                        sum_out, loss_out);
+                                                        sum_out, loss_out, xc);
     }
   } else {
     static const int res = resident_ctas(uncl_fwd_generic_kernel);
@@ -489,6 +503,37 @@ int dycon_uncl_fwd(const float* s, const float* t, int64_t B, int C, int64_t V, 
   DYCON_CUDA(cudaGetLastError());
   count_launches(1);
   return DYCON_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int dycon_uncl_fwd(const float* s, const float* t, int64_t B, int C, int64_t V, float beta, double inv_count,
+                   float* stash, double* sum_out, float* loss_out, void* workspace, size_t workspace_bytes,
+                   dycon_stream_t stream) {
+  ExchangeCtx xc;
+  make_exchange_ctx(&xc, nullptr, 0, 1, nullptr, DYCON_CHANNEL_UNCL, 0.0);
+  return uncl_fwd_impl(s, t, B, C, V, beta, inv_count, stash, sum_out, loss_out, workspace, workspace_bytes, xc,
+                       as_stream(stream));
+}
+
+int dycon_uncl_fwd_sharded(const float* s, const float* t, int64_t B, int C, int64_t V, float beta, double inv_count,
+                           float* stash, double* sum_out, float* loss_out, void* workspace, size_t workspace_bytes,
+                           void* const* peer_inboxes, int rank, int world, unsigned long long* seq_counters,
+                           double timeout_s, dycon_stream_t stream) {
+  ExchangeCtx xc;
+  if (int rc = make_exchange_ctx(&xc, peer_inboxes, rank, world, seq_counters, DYCON_CHANNEL_UNCL, timeout_s)) return rc;
+  if (C == 2 || xc.world == 1)
+    return uncl_fwd_impl(s, t, B, C, V, beta, inv_count, stash, sum_out, loss_out, workspace, workspace_bytes, xc,
+                         as_stream(stream));
+  ExchangeCtx none;
+  make_exchange_ctx(&none, nullptr, 0, 1, nullptr, DYCON_CHANNEL_UNCL, 0.0);
+  if (int rc = uncl_fwd_impl(s, t, B, C, V, beta, inv_count, stash, sum_out, nullptr, workspace, workspace_bytes, none,
+                             as_stream(stream)))
+    return rc;
+  return dycon_exchange_sums(sum_out, 1, sum_out, peer_inboxes, rank, world, seq_counters, DYCON_EXCHANGE_UNCL, inv_count,
+                             0.0, loss_out, timeout_s, stream);
 }
 
 int dycon_uncl_bwd(const float* s, const float* t, const float* stash, int64_t B, int C, int64_t V, float beta,

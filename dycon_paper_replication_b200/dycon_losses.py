@@ -154,7 +154,7 @@ class _UnCLFunction(torch.autograd.Function):
         t = t_logits.detach().contiguous()
         B, Cn = s.shape[0], s.shape[1]
         V = s[0, 0].numel()
-        gb = int(global_batch) if global_batch is not None else B
+        gb = sharded.global_batch_of(B, global_batch, process_group)
         inv_count = 1.0 / (gb * V)
         with torch.cuda.device(dev):
             _lib.require_b200(dev.index)
@@ -163,12 +163,16 @@ class _UnCLFunction(torch.autograd.Function):
             stash = torch.empty(B * V, dtype=torch.float32, device=dev) if Cn == 2 else None
             total = torch.empty(1, dtype=torch.float64, device=dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
+            ex = sharded.fused_exchange(dev, process_group)
             t0 = _tick()
-            _lib.check(L.dycon_uncl_fwd(_ptr(s), _ptr(t), B, Cn, V, float(beta), inv_count, _ptr(stash),
-                                        _ptr(total), _ptr(loss), _ptr(ws), ws.numel(), _stream_ptr(dev)),
-                       "dycon_uncl_fwd")
+            args = (_ptr(s), _ptr(t), B, Cn, V, float(beta), inv_count, _ptr(stash), _ptr(total), _ptr(loss), _ptr(ws),
+                    ws.numel())
+            if ex is not None:      # the exchange of the partial sum runs in the tail of the forward kernel
+                _lib.check(L.dycon_uncl_fwd_sharded(*args, *ex.abi_args(), _stream_ptr(dev)), "dycon_uncl_fwd_sharded")
+            else:
+                _lib.check(L.dycon_uncl_fwd(*args, _stream_ptr(dev)), "dycon_uncl_fwd")
             _tock("uncl_fwd", t0)
-            if process_group is not None:
+            if ex is None and process_group is not None:
                 loss = sharded.reduce_uncl(total, inv_count, process_group)
         ctx.dims = (B, Cn, V, float(beta), inv_count)
         ctx.shape = s_logits.shape
@@ -236,7 +240,7 @@ class _FeCLFunction(torch.autograd.Function):
                 lambda_cross, precision, process_group, global_batch):
         dev = feat.device
         B, N, D = feat.shape
-        gb = int(global_batch) if global_batch is not None else B
+        gb = sharded.global_batch_of(B, global_batch, process_group)
         inv_rows = 1.0 / (gb * N)
         has_teacher = teacher is not None
         with torch.cuda.device(dev):
@@ -249,14 +253,17 @@ class _FeCLFunction(torch.autograd.Function):
             sums = torch.empty(3, dtype=torch.float64, device=dev)
             loss = torch.empty((), dtype=torch.float32, device=dev)
             ts = teacher.stride() if has_teacher else (0, 0, 0)
+            ex = sharded.fused_exchange(dev, process_group)
             t0 = _tick()
-            _lib.check(L.dycon_fecl_fwd(_ptr(feat), *feat.stride(), _ptr(teacher), *ts, _ptr(labels),
-                                        _ptr(row_weight), B, N, D, inv_tau, gamma, int(use_focal), cross_thresh,
-                                        lambda_cross, inv_rows, precision, _ptr(state), state.numel(), _ptr(sums),
-                                        _ptr(loss), _ptr(ws), ws.numel(), _stream_ptr(dev)),
-                       "dycon_fecl_fwd")
+            args = (_ptr(feat), *feat.stride(), _ptr(teacher), *ts, _ptr(labels), _ptr(row_weight), B, N, D, inv_tau, gamma,
+                    int(use_focal), cross_thresh, lambda_cross, inv_rows, precision, _ptr(state), state.numel(), _ptr(sums),
+                    _ptr(loss), _ptr(ws), ws.numel())
+            if ex is not None:      # the three sums are exchanged in the tail of the loss sweep: `sums` / `loss` are global
+                _lib.check(L.dycon_fecl_fwd_sharded(*args, *ex.abi_args(), _stream_ptr(dev)), "dycon_fecl_fwd_sharded")
+            else:
+                _lib.check(L.dycon_fecl_fwd(*args, _stream_ptr(dev)), "dycon_fecl_fwd")
             _tock("fecl_fwd", t0)
-            if process_group is not None:
+            if ex is None and process_group is not None:
                 loss = sharded.reduce_fecl(sums, inv_rows, lambda_cross, has_teacher, process_group)
         ctx.save_for_backward(state, labels, sums)
         ctx.cfg = (B, N, D, has_teacher, inv_tau, gamma, int(use_focal), row_weight is not None, cross_thresh,

@@ -9,7 +9,9 @@ with the GLOBAL denominators baked in (``inv_count``, ``inv_rows``), all-reduces
 from the reduced sums.  The backward needs no communication: the FeCL kernel reads the reduced
 ``cnt`` from device memory and the local gradients are already scaled for a SUM over ranks (the
 loss is the global mean), which is what DDP's gradient all-reduce of the network parameters needs
-once its default averaging is undone (multiply by world size) or ``global_batch`` is left unset.
+once its default averaging is undone (multiply by world size).  With a process group the denominators
+are ALWAYS global: ``global_batch`` defaults to ``B_local * world_size`` (equal shards); pass it
+explicitly for ragged shards.
 
 This module holds only host logic (no kernels) so the N>1 protocol can be tested on CPU with gloo.
 """
@@ -42,7 +44,9 @@ class PeerExchange:
         self.rank = dist.get_rank(group)
         nbytes = _lib.lib().dycon_exchange_inbox_bytes()
         self.inbox = torch.zeros(nbytes // 8, dtype=torch.float64, device=device)
-        self.seq = torch.zeros(1, dtype=torch.int64, device=device)
+        self.seq = torch.zeros(_lib.EXCHANGE_CHANNELS, dtype=torch.int64, device=device)      # one counter per channel
+        self.error_offset = _lib.lib().dycon_exchange_error_offset() // 8
+        self.timeout_s = -1.0          # negative: DYCON_EXCHANGE_TIMEOUT_S from the environment, default 600 s
         torch.cuda.synchronize(device)                 # zero-filled before any peer can learn the handle
         handles = [None] * self.world
         dist.all_gather_object(handles, reduce_tensor(self.inbox), group=group)
@@ -71,9 +75,19 @@ class PeerExchange:
         lptr = ctypes.c_void_p(loss_out.data_ptr()) if loss_out is not None else None
         self.lib.check(self.lib.lib().dycon_exchange_sums(ptr, sums.numel(), ptr, self.table, self.rank, self.world,
                                                           ctypes.c_void_p(self.seq.data_ptr()), int(kind), float(scale),
-                                                          float(lambda_cross), lptr, stream),
+                                                          float(lambda_cross), lptr, self.timeout_s, stream),
                        "dycon_exchange_sums")
         return sums
+
+    def abi_args(self):
+        """(peer_inboxes, rank, world, seq_counters, timeout_s): the trailing arguments of the *_sharded entry points."""
+        import ctypes
+        return (self.table, self.rank, self.world, ctypes.c_void_p(self.seq.data_ptr()), self.timeout_s)
+
+    def timed_out(self) -> bool:
+        """True if a wait of any channel has given up so far (host sync: diagnostics only)."""
+        words = self.inbox[self.error_offset:self.error_offset + self.lib.EXCHANGE_CHANNELS].view(torch.int64)
+        return bool((words != 0).any().item())
 
 
 _exchanges = {}      # (id(group), device index) -> PeerExchange, or None when peer memory is unavailable
@@ -158,6 +172,24 @@ def _exchange_for(sums, group):
             and sums.is_cuda and sums.dtype == torch.float64 and sums.is_contiguous() and sums.numel() <= 7):
         return _peer_exchange(group, sums.device)
     return None
+
+
+def fused_exchange(device, group):
+    """The PeerExchange whose inboxes the *_sharded forward entry points use (the exchange then runs in the tail of
+    the kernel that produces the sums), or None: no group / world of one / no peer memory."""
+    if (group is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+            and device.type == "cuda"):
+        return _peer_exchange(group, device)
+    return None
+
+
+def global_batch_of(local_batch: int, global_batch, group) -> int:
+    """The batch size behind the mean denominators: ``global_batch`` if given, else B_local * world size
+    (so that a sharded call never mixes globally reduced sums with a local denominator)."""
+    if global_batch is not None:
+        return int(global_batch)
+    world, _ = group_size_rank(group)
+    return int(local_batch) * world
 
 
 def group_size_rank(group):

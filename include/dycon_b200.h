@@ -34,7 +34,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden */
 #endif
 
-#define DYCON_ABI_VERSION 1
+#define DYCON_ABI_VERSION 2
 
 #define DYCON_OK 0
 #define DYCON_ERR_ARG (-1)         /* NULL / misaligned / out-of-range argument          */
@@ -166,15 +166,33 @@ int dycon_ema_multi(float* const* ema_ptrs, const float* const* param_ptrs, cons
 /* ------------------------------------------------------------------ sharded batches
  * The path shards over ranks along the batch; the only exchange is the all-reduce of the partial sums above
  * (dycon_uncl_fwd: sum_out; dycon_fecl_fwd: sums_out; the reference has no multi-process mode, its
- * DataParallel gather at train_DyCON_BraTS19.py:180-193 is what this replaces).  dycon_exchange_sums() does it
- * over NVLink peer memory on the caller's stream: every rank owns an inbox of dycon_exchange_inbox_bytes()
- * bytes (ZERO-FILLED once, 16-byte aligned, mapped into every peer, e.g. through CUDA IPC); peer_inboxes is a
- * HOST array of `world` device pointers (entry r = rank r's inbox as mapped in THIS process, entry `rank` the
- * local one).  local / out: n <= 7 doubles on the device (out may alias local).  seq_counter: one device
- * uint64, zero-initialised, private to this exchange object; all ranks must issue the same sequence of calls.
+ * DataParallel gather at train_DyCON_BraTS19.py:180-193 is what this replaces).  It runs over NVLink peer
+ * memory: every rank owns an inbox of dycon_exchange_inbox_bytes() bytes (ZERO-FILLED once, 16-byte aligned,
+ * mapped into every peer, e.g. through CUDA IPC); peer_inboxes is a HOST array of `world` device pointers (entry
+ * r = rank r's inbox as mapped in THIS process, entry `rank` the local one).  seq_counters: DYCON_EXCHANGE_CHANNELS
+ * device uint64, zero-initialised, private to this exchange object (one counter per channel: UnCL, FeCL and the
+ * stand-alone call are independent exchanges); all ranks must issue the same sequence of calls per channel.
  * The totals are added in rank order, so every rank gets bit-identical results.  world <= 16.
+ * timeout_s: how long a rank waits for its peers before it gives up -- the sums (and the loss) then become NaN
+ * and the error word of the channel is raised in the local inbox (dycon_exchange_error_offset()), the launch
+ * itself still completes.  0: wait for ever (a blocking collective); negative: the environment variable
+ * DYCON_EXCHANGE_TIMEOUT_S, default 600.  Ranks may lag behind each other by up to that long (rank-0-only
+ * validation, a data-loader stall) -- the waiting ranks simply spin inside the kernel.
+ *
+ * dycon_uncl_fwd_sharded / dycon_fecl_fwd_sharded: the forward of one rank's shard WITH the exchange in the tail
+ * of the kernel that produces the sums (the last block of the UnCL forward / of the FeCL loss sweep pushes its
+ * sums to the peers and waits for theirs): sum_out / sums_out / loss_out are the GLOBAL sums and loss, and the
+ * step has no extra launch in front of the backward.  inv_count / inv_rows must be the global denominators.
+ * dycon_exchange_sums(): the same exchange as a stand-alone launch (local / out: n <= 7 doubles on the device,
+ * out may alias local), used by the paths that do not fuse it (generic-C UnCL, fp32 FeCL, global negatives).
  */
+#define DYCON_EXCHANGE_CHANNELS 3
+#define DYCON_CHANNEL_PLAIN 0
+#define DYCON_CHANNEL_UNCL 1
+#define DYCON_CHANNEL_FECL 2
 size_t dycon_exchange_inbox_bytes(void);
+/* Byte offset inside an inbox of the DYCON_EXCHANGE_CHANNELS uint64 error words (0: no time-out so far). */
+size_t dycon_exchange_error_offset(void);
 /* Lets kernels of the CURRENT device store into memory of `peer_device` (cudaDeviceEnablePeerAccess; a no-op
  * if already enabled).  Call once per peer before the first exchange. */
 int dycon_exchange_enable_peer(int peer_device);
@@ -186,8 +204,20 @@ int dycon_exchange_enable_peer(int peer_device);
 #define DYCON_EXCHANGE_FECL 2
 #define DYCON_EXCHANGE_FECL_TEACHER 3
 int dycon_exchange_sums(const double* local, int n, double* out, void* const* peer_inboxes, int rank, int world,
-                        unsigned long long* seq_counter, int kind, double scale, double lambda_cross, float* loss_out,
-                        dycon_stream_t stream);
+                        unsigned long long* seq_counters, int kind, double scale, double lambda_cross, float* loss_out,
+                        double timeout_s, dycon_stream_t stream);
+int dycon_uncl_fwd_sharded(const float* s, const float* t, int64_t B, int C, int64_t V, float beta, double inv_count,
+                           float* stash, double* sum_out, float* loss_out, void* workspace, size_t workspace_bytes,
+                           void* const* peer_inboxes, int rank, int world, unsigned long long* seq_counters,
+                           double timeout_s, dycon_stream_t stream);
+int dycon_fecl_fwd_sharded(const float* feat, int64_t f_sb, int64_t f_sn, int64_t f_sd,
+                           const float* teacher, int64_t t_sb, int64_t t_sn, int64_t t_sd,
+                           const float* labels, const float* row_weight, int B, int N, int D,
+                           float inv_tau, float gamma, int use_focal, float cross_thresh, float lambda_cross,
+                           double inv_rows, int precision, void* state, size_t state_bytes,
+                           double* sums_out, float* loss_out, void* workspace, size_t workspace_bytes,
+                           void* const* peer_inboxes, int rank, int world, unsigned long long* seq_counters,
+                           double timeout_s, dycon_stream_t stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

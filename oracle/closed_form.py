@@ -128,7 +128,7 @@ def fecl(feat, mask, teacher=None, row_weight=None, *, inv_tau, gamma=2.0, use_f
     return {"loss": loss, "grad": go * grad, "m": m, "n": nsum, "A": a, "kappa": kappa,
             "student_sum": student_sum, "cross_sum": cross_sum, "cnt": cnt,
             "grad_student": go * grad_student, "cross_unnorm": cross_unnorm, "ambiguous": ambiguous,
-            "go": go, "lambda_cross": lambda_cross}
+            "go": go, "lambda_cross": lambda_cross, "labels": y}
 
 
 def fecl_grad_error(grad, ref, teacher, max_per_row=14):
@@ -169,6 +169,180 @@ def fecl_grad_error(grad, ref, teacher, max_per_row=14):
         u[b, i] = u[b, i] + bits[best] @ contrib
         net += float(bits[best] @ signs)
     return min(plain, err(ref["grad_student"] + k * u / (cnt + net + EPS_FECL)))
+
+
+def fecl_blocked(feat, mask, teacher=None, row_weight=None, *, inv_tau, gamma=2.0, use_focal=False,
+                 cross_thresh=0.5, lambda_cross=1.0, go=1.0, rows_global=None, cnt_global=None, block=1024,
+                 grad_rows=None):
+    """The same value and gradient as ``fecl`` for ONE sample (feat (N,D) or (1,N,D)) without ever holding an
+    (N,N) array: four sweeps over row blocks (row max; negative sums; loss and A; gradient), the transposed
+    gradient term G_ji evaluated from the per-row statistics of row j -- the structure the kernels use.  For
+    shapes where ``fecl`` does not fit (ISLES22 N=9216, merged batches of config 5).  ``grad_rows`` = (lo, hi)
+    restricts the gradient sweep to those rows (the loss always covers all rows).  float64 throughout, on torch
+    CPU tensors so that the element-wise passes use all host cores.  dycon_losses.py:150-235."""
+    import torch
+    f = torch.as_tensor(np.asarray(feat, np.float64)).reshape(-1, np.asarray(feat).shape[-1])
+    n = f.shape[0]
+    y = torch.as_tensor(np.asarray(mask, np.float64)).reshape(n)
+    tf = None if teacher is None else torch.as_tensor(np.asarray(teacher, np.float64)).reshape(n, -1)
+    r = torch.ones(n, dtype=torch.float64) if row_weight is None else torch.as_tensor(np.asarray(row_weight, np.float64)).reshape(n)
+    rows = float(rows_global if rows_global is not None else n)
+    focal = bool(use_focal) and row_weight is None
+    blocks = [(a, min(a + block, n)) for a in range(0, n, block)]
+    idx = torch.arange(n)
+
+    def logits(a, b):                                          # rows a..b x all columns, diagonal zeroed (:175-178)
+        lg = (f[a:b] @ f.T) * inv_tau
+        lg[idx[a:b] - a, idx[a:b]] = 0.0
+        return lg
+
+    def dphi_of(d):
+        if focal:
+            return gamma * (1.0 - d) ** (gamma - 1.0) * torch.log(d + EPS_FECL) - (1.0 - d) ** gamma / (d + EPS_FECL)
+        return -1.0 / (d + EPS_FECL)
+
+    m = torch.empty(n, dtype=torch.float64)
+    for a, b in blocks:                                        # :180 column max == row max (the matrix is symmetric)
+        m[a:b] = logits(a, b).max(dim=1).values
+    nsum, pcount = torch.empty(n, dtype=torch.float64), torch.empty(n, dtype=torch.float64)
+    for a, b in blocks:                                        # :183-184
+        pos = y[a:b, None] == y[None, :]
+        e = torch.exp(logits(a, b) - m[None, :])
+        nsum[a:b] = (e * ~pos).sum(-1)
+        pcount[a:b] = pos.sum(-1).double()
+    c = 1.0 / (pcount - 1 + EPS_FECL)                          # :192
+    kappa = r * c / rows
+    amat = torch.empty(n, dtype=torch.float64)
+    student_sum, cross_sum, cnt = 0.0, 0.0, 0.0
+
+    def pair_terms(a, b):
+        pos = y[a:b, None] == y[None, :]
+        pm = pos.clone()
+        pm[idx[a:b] - a, idx[a:b]] = False
+        e = torch.exp(logits(a, b) - m[None, :])
+        tt = e + nsum[a:b, None]
+        d = e / (tt + EPS_FECL)
+        dphi = torch.where(pm, dphi_of(d), torch.zeros((), dtype=torch.float64))
+        return pos, pm, e, tt, d, dphi
+
+    for a, b in blocks:                                        # :186-206 and the backward row scalar A
+        pos, pm, e, tt, d, dphi = pair_terms(a, b)
+        nl = -torch.log(d + EPS_FECL)
+        wgt = (1.0 - d) ** gamma if focal else 1.0
+        student_sum += float((r[a:b] * c[a:b] * (nl * wgt * pm).sum(-1)).sum())
+        amat[a:b] = (dphi * d / (tt + EPS_FECL)).sum(-1)
+        if tf is not None:                                     # :217-229
+            cs = f[a:b] @ tf.T
+            hard = ~pos & (cs > cross_thresh)
+            cnt += float(hard.sum())
+            cross_sum += float((-torch.log(1.0 - cs + EPS_FECL))[hard].sum())
+    cg = float(cnt_global if cnt_global is not None else cnt) if tf is not None else 0.0
+    loss = student_sum / rows + lambda_cross * (cross_sum / (cg + EPS_FECL) if tf is not None else 0.0)
+
+    lo, hi = grad_rows if grad_rows is not None else (0, n)
+    grad = torch.zeros((hi - lo, f.shape[1]), dtype=torch.float64)
+    zero = torch.zeros((), dtype=torch.float64)
+    for a, b in [(max(a, lo), min(b, hi)) for a, b in blocks if min(b, hi) > max(a, lo)]:
+        pos, pm, e, tt, d, dphi = pair_terms(a, b)
+        gij = kappa[a:b, None] * (dphi * d * (1.0 - d) - ~pos * e * amat[a:b, None])
+        # G_ji for the same (i, j): row j's statistics, column max m_i;  l_ji = l_ij
+        eT = torch.exp(logits(a, b) - m[a:b, None])
+        ttT = eT + nsum[None, :]
+        dT = eT / (ttT + EPS_FECL)
+        dphiT = torch.where(pm, dphi_of(dT), zero)
+        gji = kappa[None, :] * (dphiT * dT * (1.0 - dT) - ~pos * eT * amat[None, :])
+        h = (gij + gji) * inv_tau
+        h[idx[a:b] - a, idx[a:b]] = 0.0
+        g = h @ f
+        if tf is not None:
+            cs = f[a:b] @ tf.T
+            hard = ~pos & (cs > cross_thresh)
+            gc = torch.where(hard, 1.0 / ((1.0 - cs + EPS_FECL) * (cg + EPS_FECL)), zero)
+            g = g + lambda_cross * (gc @ tf)
+        grad[a - lo:b - lo] = g
+    return {"loss": loss, "grad": (go * grad).numpy(), "m": m.numpy(), "n": nsum.numpy(), "A": amat.numpy(),
+            "kappa": kappa.numpy(), "student_sum": student_sum, "cross_sum": cross_sum, "cnt": cnt}
+
+
+def round_operand(x, mode):
+    """fp32 array -> the values the 16-bit tensor-core modes feed to the MMA (round to nearest even)."""
+    x = np.asarray(x, np.float32)
+    if mode == "fp16":
+        return x.astype(np.float16).astype(np.float64)
+    if mode == "bf16":
+        u = x.view(np.uint32).astype(np.uint64)
+        u = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+        return u.astype(np.uint32).view(np.float32).astype(np.float64)
+    return x.astype(np.float64)
+
+
+def fecl_grad_error_strict(grad, ref, feat, teacher, mode, cross_thresh, accum_window=3e-6, max_per_row=14):
+    """The teacher-branch comparison WITHOUT fitting the flips to the output: hard-negative membership of the
+    threshold-boundary pairs (``ref["ambiguous"]``) is PREDICTED from cs recomputed on the operands as the kernel
+    rounds them (``round_operand``); only pairs whose rounded-operand cs lies within ``accum_window`` of the
+    threshold (the fp32 accumulation order is the kernel's own) stay free.  Returns
+    dict(err, plain, flipped, free, window_pairs, outside_flips):
+      err            max|grad - predicted oracle| / max|oracle|
+      plain          the same against the fp64 membership
+      flipped        boundary pairs whose predicted membership differs from the fp64 one
+      free           pairs left to the fit (inside the accumulation window)
+      outside_flips  negative pairs OUTSIDE the ambiguity window whose rounded-operand membership differs from
+                     fp64 (must be 0: it validates the window)."""
+    g = np.asarray(grad, np.float64)
+    scale = np.abs(ref["grad"]).max()
+    err = lambda x: float(np.abs(g - x).max() / scale)
+    plain = err(ref["grad"])
+    out = {"err": plain, "plain": plain, "flipped": 0, "free": 0, "window_pairs": len(ref["ambiguous"]), "outside_flips": 0}
+    if teacher is None or ref["cross_unnorm"] is None:
+        return out
+    fq, tq = round_operand(feat, mode), round_operand(teacher, mode)
+    f64, t64 = np.asarray(feat, np.float64), np.asarray(teacher, np.float64)
+    b, n, _ = f64.shape
+    y = None
+    amb = {(bb, ii, jj): (cs, hard) for bb, ii, jj, cs, hard in ref["ambiguous"]}
+    # window validation: every negative pair outside the window keeps its membership under operand rounding
+    labels = ref.get("labels")
+    if labels is not None:
+        for bb in range(b):
+            csq = fq[bb] @ tq[bb].T
+            cs64 = f64[bb] @ t64[bb].T
+            neg = labels[bb][:, None] != labels[bb][None, :]
+            diff = neg & ((csq > cross_thresh) != (cs64 > cross_thresh))
+            for ii, jj in zip(*np.nonzero(diff)):
+                if (bb, int(ii), int(jj)) not in amb:
+                    out["outside_flips"] += 1
+    k = ref["go"] * ref["lambda_cross"]
+    u = ref["cross_unnorm"].copy()
+    cnt, net = ref["cnt"], 0.0
+    rows = {}
+    for (bb, ii, jj), (cs, hard) in amb.items():
+        rows.setdefault((bb, ii), []).append((jj, cs, hard))
+    free_rows = {}
+    for (bb, ii), pairs in rows.items():
+        for jj, cs, hard in pairs:
+            csq = float(fq[bb, ii] @ tq[bb, jj])
+            if abs(csq - cross_thresh) <= accum_window:
+                free_rows.setdefault((bb, ii), []).append((jj, cs, hard))
+                out["free"] += 1
+                continue
+            want = csq > cross_thresh
+            if want != hard:
+                sg = 1.0 if want else -1.0
+                u[bb, ii] += sg * t64[bb, jj] / (1.0 - cs + EPS_FECL)
+                net += sg
+                out["flipped"] += 1
+    for (bb, ii), pairs in free_rows.items():
+        if len(pairs) > max_per_row:
+            continue
+        signs = np.array([-1.0 if hard else 1.0 for _, _, hard in pairs])
+        contrib = np.stack([sg * t64[bb, jj] / (1.0 - cs + EPS_FECL) for sg, (jj, cs, _) in zip(signs, pairs)])
+        bits = ((np.arange(1 << len(pairs))[:, None] >> np.arange(len(pairs))[None, :]) & 1).astype(np.float64)
+        cand = ref["grad_student"][bb, ii][None, :] + k * (u[bb, ii][None, :] + bits @ contrib) / (cnt + net + EPS_FECL)
+        best = int(np.abs(cand - g[bb, ii][None, :]).max(axis=1).argmin())
+        u[bb, ii] = u[bb, ii] + bits[best] @ contrib
+        net += float(bits[best] @ signs)
+    out["err"] = err(ref["grad_student"] + k * u / (cnt + net + EPS_FECL))
+    return out
 
 
 # --------------------------------------------------------------------------- EMA

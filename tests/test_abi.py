@@ -52,7 +52,7 @@ def test_ctypes_prototypes_match_header(so_path):
 def test_size_queries_without_gpu(so_path):
     from dycon_paper_replication_b200 import _lib
     L = _lib.lib()
-    assert L.dycon_abi_version() == 1
+    assert L.dycon_abi_version() == _lib.ABI_VERSION
     assert L.dycon_uncl_workspace_bytes() >= 16
     # fp32 state: student + teacher operand copies + 4 stat planes
     b, n, d = 4, 1728, 256

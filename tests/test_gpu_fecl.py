@@ -219,6 +219,48 @@ def test_unnormalised_features(mode):
     assert normwise(grad, ref["grad"]) <= (1e-5 if mode == "fp32" else 1e-1)
 
 
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("gamma", [3.0, 1.5, 1.0])
+def test_single_class_sample_any_gamma(mode, gamma):
+    """A sample whose rows all carry one label (a tumour-free crop) has no negatives: n_i = 0, d_ij = 1, and the
+    reference returns exactly 0 for those pairs because (1-1)^gamma = 0 (dycon_losses.py:186-202).  The general
+    focal path (gamma != 2) must not turn 1 - d = -ulp into NaN; the second sample has mixed labels."""
+    skip_unavailable(mode)
+    g = torch.Generator().manual_seed(3)
+    b, n, d = 2, 200, 32
+    mask = (torch.rand(b, 1, n, generator=g) < 0.3).float()
+    mask[0] = 1.0
+    f = torch.nn.functional.normalize(torch.randn(b, n, d, generator=g) + 0.7, dim=-1)
+    t = torch.nn.functional.normalize(f + 0.3 * torch.randn(b, n, d, generator=g) / d ** 0.5, dim=-1)
+    ctor = dict(temperature=0.6, gamma=gamma, use_focal=True, rampup_epochs=1500)
+    loss, grad = run(f, mask, t, None, 100, 1.0, mode, **ctor)
+    ref = reference(f, mask, t, 100, 1.0, ambiguity=AMBIGUITY[mode], **ctor)
+    assert np.isfinite(loss) and np.isfinite(grad).all()
+    assert abs(loss - ref["loss"]) <= TOL[mode] * abs(ref["loss"]), (loss, ref["loss"])
+    assert np.abs(grad[0]).max() <= 1e-6 * np.abs(ref["grad"]).max()      # the single-class sample carries no gradient
+    assert grad_error(grad, ref, t) <= (TOL[mode] if mode != "bf16" else 2e-2)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "fp16"])
+def test_near_identical_student_and_teacher(mode):
+    """Collapsed embeddings (early training): every cross similarity is ~0.9975, so a product of sixteen
+    (1 - cs) factors underflows fp32.  The loss must stay finite and close to the reference's per-pair logs
+    (dycon_losses.py:227-229); 16-bit operand rounding moves 1 - cs by a few per cent here, hence the loose bound."""
+    skip_unavailable(mode)
+    g = torch.Generator().manual_seed(17)
+    b, n, d = 2, 256, 64
+    mask = (torch.rand(b, 1, n, generator=g) < 0.5).float()
+    c = torch.nn.functional.normalize(torch.randn(d, generator=g), dim=0)
+    f = torch.nn.functional.normalize(c + 0.00625 * torch.randn(b, n, d, generator=g), dim=-1)
+    t = torch.nn.functional.normalize(f + 0.01 * torch.randn(b, n, d, generator=g) / d ** 0.5, dim=-1)
+    ctor = dict(temperature=0.6, gamma=2.0, use_focal=True, rampup_epochs=1500)
+    loss, grad = run(f, mask, t, None, 100, 1.0, mode, **ctor)
+    ref = reference(f, mask, t, 100, 1.0, **ctor)
+    assert ref["cnt"] > 0.9 * (b * n * n / 2) * 0.9 and np.isfinite(ref["loss"])
+    assert np.isfinite(loss) and np.isfinite(grad).all(), loss
+    assert abs(loss - ref["loss"]) <= (1e-5 if mode == "fp32" else 5e-3) * abs(ref["loss"]), (loss, ref["loss"])
+
+
 def test_bad_arguments_raise():
     from dycon_paper_replication_b200 import FeCLoss
     crit = FeCLoss("cuda", precision="fp32")

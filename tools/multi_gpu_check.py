@@ -105,6 +105,39 @@ def main():
             assert abs(ul.item() - ru["loss"]) <= 1e-5 * abs(ru["loss"]), (ul.item(), ru["loss"])
             assert np.abs(f.grad.cpu().numpy() - rf["grad"][lo:hi]).max() <= 1e-5 * np.abs(rf["grad"]).max()
             assert np.abs(s.grad.cpu().numpy() - ru["grad"][lo:hi]).max() <= 1e-5 * np.abs(ru["grad"]).max()
+    # ---- 2b. the sharded step captured in a CUDA graph (the exchange runs in the tail of the forward kernels):
+    #          replays must reproduce the eager result bit for bit
+    ctor = dict(temperature=0.6, gamma=2.0, use_focal=True, rampup_epochs=1500, precision="fp16")
+    fecl = FeCLoss(dev, process_group=g, global_batch=B, **ctor)
+    uncl = UnCLoss(process_group=g, global_batch=B)
+    mk, tk, tl = inp.mask[lo:hi].to(dev), inp.teacher[lo:hi].to(dev), inp.t_logits[lo:hi].to(dev)
+
+    def sharded_step():
+        f.grad = s.grad = None
+        fl = fecl(f, mk, tk, None, 100)
+        ul = uncl(s, tl, 1.58)
+        (0.5 * (fl + ul)).backward()
+        return fl, ul
+
+    fl, ul = sharded_step()
+    want = (fl.item(), ul.item(), f.grad.clone(), s.grad.clone())
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        sharded_step()
+    torch.cuda.current_stream().wait_stream(side)
+    dist.barrier()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        gfl, gul = sharded_step()
+    for _ in range(10):
+        graph.replay()
+    torch.cuda.synchronize()
+    assert gfl.item() == want[0] and gul.item() == want[1], (gfl.item(), want[0], gul.item(), want[1])
+    assert torch.equal(f.grad, want[2]) and torch.equal(s.grad, want[3])
+    ex = sharded._exchanges.get((id(g), dev.index))
+    assert ex is None or not ex.timed_out()
+
     # ---- 3. global negatives (BASELINE config 5): every rank's rows against the rows of ALL ranks ----------
     crit = FeCLoss(dev, precision="fp16", process_group=g, cross_gpu_negatives=True, temperature=0.6, gamma=2.0,
                    use_focal=True, rampup_epochs=1500)
