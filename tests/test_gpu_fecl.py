@@ -1,11 +1,18 @@
 """FeCL CUDA path (module -> ctypes -> C ABI) vs the oracle.
 
 fp32 mode (SIMT tiles): rtol 1e-5 on the loss, max|dg| <= 1e-5*max|g| on the gradient.
-fp16 mode (tcgen05, the default): 2e-3 on both -- the north-star's bound for the 16-bit tensor-core path.
-bf16 mode (tcgen05): 2e-3 on the loss everywhere and on the gradient at the BASELINE shape with
-trained-like (structured) features; bf16's 8-bit mantissa flips hard-negative membership
-(cs > theta) and costs up to ~1e-2 (0.13 on the D=16 fixture) of max|g| on the small / iid
-fixtures -- measured and emulated in DESIGN.md, which is why fp16 operands are the default."""
+fp16 mode (tcgen05, the product default): 2e-3 on both -- the north-star's bound for the 16-bit tensor-core path.
+bf16 mode (tcgen05, best effort): 2e-3 on the loss; the gradient meets 2e-3 against the closed form evaluated ON
+the bf16-rounded operands (i.e. the kernel's arithmetic is exact to that bound) and 5e-3 against the unrounded
+inputs -- bf16's 8-bit mantissa alone costs 1e-3..3e-3 of max|g| on iid features (measured table:
+tools/parity_report.py), which is why fp16 operands are the default.
+
+Teacher branch: hard-negative membership (cs > theta, dycon_losses.py:223) is a step function, so an
+implementation that rounds cs differently legitimately flips pairs whose similarity sits on the threshold.  The
+comparator is STRICT about it (oracle.closed_form.fecl_grad_error_strict): the flips are PREDICTED by recomputing
+cs from the operands as the mode rounds them -- not fitted to the kernel's output -- only pairs within 3e-6 of the
+threshold after rounding (the fp32 accumulation order) stay free, no pair outside the ambiguity window may flip,
+and on fixtures whose hard-negative count is large (a flip then weighs < 1e-4) the PLAIN error is bounded too."""
 import numpy as np
 import pytest
 import torch
@@ -18,14 +25,10 @@ pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not torch.cuda.is_available(),
 FECL = load_golden("fecl")
 MAIN = sorted(k for k in FECL if k != "legacy_plain")
 TOL = {"fp32": 1e-5, "fp16": 2e-3, "bf16": 2e-3}
-BF16_LOOSE_GRAD = 0.2      # sanity bound for bf16 on the fixtures described above
-# Hard-negative membership (cs > theta, dycon_losses.py:223) is a step function: pairs whose fp64
-# similarity is within this distance of theta may flip under fp32 rounding of the dot product (even
-# torch's own fp32 matmul flips one pair of the BraTS19 fixture).  fp32 parity is therefore stated
-# modulo those boundary pairs (oracle.closed_form.fecl_grad_error); a single flip moves one row of
-# the gradient by ~1/cnt, ~3e-4 of max|g| here.  In bf16 mode flips are part of the 2e-3 budget.
+BF16_UNROUNDED_GRAD = 5e-3     # bf16 vs the UNROUNDED inputs: operand quantisation floor (measured <= 3.1e-3)
 # Window = bound on the rounding error of cs in each mode (fp32 accumulate of 16-bit products:
-# |d cs| <= 2^-10 (fp16) / 2^-7 (bf16) times sum|f_k t_k| <= 1; typical error is ~10x smaller).
+# |d cs| <= 2^-10 (fp16) / 2^-7 (bf16) times sum|f_k t_k| <= 1; typical error is ~10x smaller).  The strict
+# comparator asserts that no pair outside the window changes membership under the mode's operand rounding.
 AMBIGUITY = {"fp32": 2e-6, "fp16": 5e-4, "bf16": 4e-3}
 
 
@@ -40,10 +43,31 @@ def modes():
 MODES = ["fp32", "fp16", "bf16"]
 
 
-def grad_tol(mode, strict_bf16=False):
-    if mode == "bf16" and not strict_bf16:
-        return BF16_LOOSE_GRAD
-    return TOL[mode]
+def grad_tol(mode):
+    return BF16_UNROUNDED_GRAD if mode == "bf16" else TOL[mode]
+
+
+def check_grad(grad, ref, feat, teacher, mode, thr, kw=None, mask=None, unc=None):
+    """All gradient assertions of one case (see the module docstring).  `ref` = closed_form.fecl(...,
+    ambiguity=AMBIGUITY[mode]); kw/mask/unc: the arguments needed to re-evaluate the oracle on rounded operands."""
+    fn = np.asarray(feat)
+    tn = None if teacher is None else np.asarray(teacher)
+    if tn is None:
+        assert normwise(grad, ref["grad"]) <= grad_tol(mode)
+    else:
+        st = closed_form.fecl_grad_error_strict(grad, ref, fn, tn, mode, thr)
+        assert st["outside_flips"] == 0, st                       # the ambiguity window covers every flip
+        assert st["flipped"] + st["free"] <= st["window_pairs"], st
+        assert st["err"] <= grad_tol(mode), st
+        if ref["cnt"] >= 1e4 and mode != "bf16":                  # a single flip weighs < 1e-4: the plain error is bounded too
+            assert st["plain"] <= 2 * TOL[mode], st
+    if mode == "bf16" and kw is not None:
+        # the kernel's own arithmetic: the oracle on the SAME bf16-rounded operands, at the north-star bound
+        fq = closed_form.round_operand(fn, "bf16")
+        tq = None if tn is None else closed_form.round_operand(tn, "bf16")
+        rq = closed_form.fecl(fq, mask, tq, unc, ambiguity=3e-6, **kw)
+        err = closed_form.fecl_grad_error(grad, rq, tq) if tq is not None else normwise(grad, rq["grad"])
+        assert err <= TOL["bf16"], err
 
 
 def skip_unavailable(mode):
@@ -79,18 +103,14 @@ def test_golden(case, mode):
                      **ctor_of(rec))
     tol = TOL[mode]
     assert abs(loss - float(rec["loss64"])) <= tol * abs(float(rec["loss64"]))
-    if "teacher" not in rec:
-        assert normwise(grad, rec["grad64"]) <= grad_tol(mode)
-        return
-    # with a teacher, compare modulo the threshold-boundary pairs: the closed form (pinned to this very
-    # fixture by tests/test_oracle_golden.py) exposes the pieces fecl_grad_error needs
+    # the closed form (pinned to this very fixture by tests/test_oracle_golden.py) exposes what the comparator needs
     kw = ctor_of(rec)
     thr = torch_port.ramp_threshold(int(rec["epoch"]), kw["rampup_epochs"], 0.3, 0.5)
-    ref = closed_form.fecl(rec["feat"], rec["mask"], rec["teacher"], rec.get("unc"), inv_tau=1.0 / kw["temperature"],
-                           gamma=kw["gamma"], use_focal=kw["use_focal"], cross_thresh=thr,
-                           lambda_cross=kw["lambda_cross"], go=float(rec["go"]), ambiguity=AMBIGUITY[mode])
+    okw = dict(inv_tau=1.0 / kw["temperature"], gamma=kw["gamma"], use_focal=kw["use_focal"], cross_thresh=thr,
+               lambda_cross=kw["lambda_cross"], go=float(rec["go"]))
+    ref = closed_form.fecl(rec["feat"], rec["mask"], rec.get("teacher"), rec.get("unc"), ambiguity=AMBIGUITY[mode], **okw)
     assert normwise(ref["grad"], rec["grad64"]) <= 1e-9
-    assert closed_form.fecl_grad_error(grad, ref, rec["teacher"]) <= grad_tol(mode)
+    check_grad(grad, ref, rec["feat"], rec.get("teacher"), mode, thr, okw, rec["mask"], rec.get("unc"))
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -105,16 +125,21 @@ def test_legacy_losses_fecloss(mode):
     assert normwise(f.grad.cpu().numpy(), rec["grad32"]) <= grad_tol(mode)
 
 
-def reference(inp_feat, mask, teacher, epoch, go, ambiguity=0.0, **ctor):
+def oracle_kw(epoch, go, **ctor):
     thr = torch_port.ramp_threshold(epoch, ctor.get("rampup_epochs", 2000), 0.3, 0.5)
+    return dict(inv_tau=1.0 / ctor.get("temperature", 0.6), gamma=ctor.get("gamma", 2.0),
+                use_focal=ctor.get("use_focal", False), cross_thresh=thr, lambda_cross=ctor.get("lambda_cross", 1.0), go=go)
+
+
+def reference(inp_feat, mask, teacher, epoch, go, ambiguity=0.0, **ctor):
     return closed_form.fecl(inp_feat.numpy(), mask.numpy(), None if teacher is None else teacher.numpy(), None,
-                            inv_tau=1.0 / ctor.get("temperature", 0.6), gamma=ctor.get("gamma", 2.0),
-                            use_focal=ctor.get("use_focal", False), cross_thresh=thr,
-                            lambda_cross=ctor.get("lambda_cross", 1.0), go=go, ambiguity=ambiguity)
+                            ambiguity=ambiguity, **oracle_kw(epoch, go, **ctor))
 
 
-def grad_error(grad, ref, teacher):
-    return closed_form.fecl_grad_error(grad, ref, None if teacher is None else teacher.numpy())
+def check(grad, ref, feat, mask, teacher, epoch, go, mode, **ctor):
+    kw = oracle_kw(epoch, go, **ctor)
+    check_grad(grad, ref, feat.numpy(), None if teacher is None else teacher.numpy(), mode, kw["cross_thresh"], kw,
+               mask.numpy())
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -134,8 +159,7 @@ def test_seeded_shapes_vs_oracle(shape, dim, feat_kind, mask_kind, epoch, mode):
     ref = reference(inp.feat, inp.mask, inp.teacher, epoch, 0.5, ambiguity=AMBIGUITY[mode], **ctor)
     tol = TOL[mode]
     assert abs(loss - ref["loss"]) <= tol * abs(ref["loss"]), (loss, ref["loss"])
-    strict = shape == "brats19" and dim == 256 and feat_kind == "structured"
-    assert grad_error(grad, ref, inp.teacher) <= grad_tol(mode, strict_bf16=strict)
+    check(grad, ref, inp.feat, inp.mask, inp.teacher, epoch, 0.5, mode, **ctor)
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -150,7 +174,7 @@ def test_ragged_n_not_multiple_of_tile(mode):
     loss, grad = run(f, mask, t, None, 100, 1.0, mode, **ctor)
     ref = reference(f, mask, t, 100, 1.0, ambiguity=AMBIGUITY[mode], **ctor)
     assert abs(loss - ref["loss"]) <= TOL[mode] * abs(ref["loss"])
-    assert grad_error(grad, ref, t) <= grad_tol(mode)
+    check(grad, ref, f, mask, t, 100, 1.0, mode, **ctor)
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -178,6 +202,25 @@ def test_isles22_size_properties(mode):
     assert abs(0.5 * (la + lb) - lab) <= 1e-5 * abs(lab)
 
 
+def test_isles22_sample_against_the_blocked_oracle():
+    """N = 9216 (ISLES22 grid, train_DyCON_ISLES22.py:70,75) against the ORACLE, not only through properties: one
+    sample, fp64 closed form evaluated in row blocks (oracle.closed_form.fecl_blocked, pinned to closed_form.fecl
+    -- and through it to the unmodified reference -- by tests/test_oracle_properties.py).  fp32 mode at 1e-5,
+    fp16 mode at 2e-3; the fp32 gradient is compared modulo threshold-boundary rows: at cnt ~ 1e7 a flipped pair
+    moves one row by ~1e-7 of max|g|, far below either bound, so the plain error is asserted."""
+    skip_unavailable("fp16")
+    from dycon_paper_replication_b200.synthetic import make_inputs
+    inp = make_inputs("isles22", batch=1, dim=256)
+    ctor = dict(temperature=0.6, gamma=2.0, use_focal=True, rampup_epochs=1500)
+    kw = oracle_kw(100, 0.5, **ctor)
+    ref = closed_form.fecl_blocked(inp.feat.numpy(), inp.mask.numpy(), inp.teacher.numpy(), None, block=1024, **kw)
+    assert ref["cnt"] > 1e6
+    for mode in ("fp32", "fp16"):
+        loss, grad = run(inp.feat, inp.mask, inp.teacher, None, 100, 0.5, mode, **ctor)
+        assert abs(loss - ref["loss"]) <= TOL[mode] * abs(ref["loss"]), (mode, loss, ref["loss"])
+        assert normwise(grad[0], ref["grad"]) <= TOL[mode], (mode, normwise(grad[0], ref["grad"]))
+
+
 @pytest.mark.parametrize("shape", [(4, 1728, 256), (1, 700, 64), (3, 257, 128), (2, 2352, 256), (5, 100, 64)])
 def test_backward_work_split_is_reproducible_and_exact(shape):
     """Few row blocks (fewer than SMs): the backward splits a row block's columns over several CTAs and adds
@@ -196,7 +239,7 @@ def test_backward_work_split_is_reproducible_and_exact(shape):
         assert loss == runs[0][0] and np.array_equal(grad, runs[0][1])
     ref = reference(f, mask, t, 100, 0.5, ambiguity=AMBIGUITY["fp16"], **ctor)
     assert abs(runs[0][0] - ref["loss"]) <= TOL["fp16"] * abs(ref["loss"])
-    assert grad_error(runs[0][1], ref, t) <= grad_tol("fp16")
+    check(runs[0][1], ref, f, mask, t, 100, 0.5, "fp16", **ctor)
 
 
 @pytest.mark.parametrize("mode", ["fp32", "fp16"])
@@ -238,7 +281,7 @@ def test_single_class_sample_any_gamma(mode, gamma):
     assert np.isfinite(loss) and np.isfinite(grad).all()
     assert abs(loss - ref["loss"]) <= TOL[mode] * abs(ref["loss"]), (loss, ref["loss"])
     assert np.abs(grad[0]).max() <= 1e-6 * np.abs(ref["grad"]).max()      # the single-class sample carries no gradient
-    assert grad_error(grad, ref, t) <= (TOL[mode] if mode != "bf16" else 2e-2)
+    check(grad, ref, f, mask, t, 100, 1.0, mode, **ctor)
 
 
 @pytest.mark.parametrize("mode", ["fp32", "fp16"])

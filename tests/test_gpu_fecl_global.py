@@ -35,6 +35,15 @@ def oracle(f, mask, t, epoch, go):
                             cross_thresh=thr, go=go, ambiguity=5e-4)
 
 
+def strict(got, ref, f, t):
+    """Threshold flips predicted from the fp16-rounded operands, never fitted (closed_form.fecl_grad_error_strict)."""
+    b, n, d = f.shape
+    thr = torch_port.ramp_threshold(100, 1500, 0.3, 0.5)
+    st = closed_form.fecl_grad_error_strict(got, ref, f.reshape(1, b * n, d).numpy(), t.reshape(1, b * n, d).numpy(), "fp16", thr)
+    assert st["outside_flips"] == 0 and st["flipped"] + st["free"] <= st["window_pairs"], st
+    assert st["err"] <= 2e-3, st
+
+
 @pytest.mark.parametrize("shape", [(3, 80, 32), (2, 300, 256)])
 def test_module_world_of_one_matches_the_merged_reference(shape):
     from dycon_paper_replication_b200 import FeCLoss
@@ -46,7 +55,7 @@ def test_module_world_of_one_matches_the_merged_reference(shape):
     ref = oracle(f, mask, t, 100, 0.5)
     assert abs(loss.item() - ref["loss"]) <= 2e-3 * abs(ref["loss"])
     got = x.grad.cpu().numpy().reshape(ref["grad"].shape)
-    assert closed_form.fecl_grad_error(got, ref, t.reshape(1, -1, shape[2]).numpy()) <= 2e-3
+    strict(got, ref, f, t)
 
 
 def test_two_virtual_ranks_through_the_c_abi():
@@ -105,4 +114,4 @@ def test_two_virtual_ranks_through_the_c_abi():
     ref = oracle(f, mask, t, 100, 0.5)
     assert abs(loss - ref["loss"]) <= 2e-3 * abs(ref["loss"]), (loss, ref["loss"])
     got = torch.cat(grads).cpu().numpy().reshape(ref["grad"].shape)
-    assert closed_form.fecl_grad_error(got, ref, t.reshape(1, M, D).numpy()) <= 2e-3
+    strict(got, ref, f, t)

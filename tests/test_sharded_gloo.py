@@ -54,6 +54,9 @@ def _worker(rank, world, port, out):
         # ---------------- host helpers of the global-negatives protocol (all-gather in rank order; the reduced
         #                  loss helpers fall back to the backend all-reduce for CPU tensors)
         assert sharded.group_size_rank(dist.group.WORLD) == (world, rank)
+        # with a process group the denominators are always global (never local B with globally reduced sums)
+        assert sharded.global_batch_of(3, None, dist.group.WORLD) == 3 * world
+        assert sharded.global_batch_of(3, 7, dist.group.WORLD) == 7 and sharded.global_batch_of(3, None, None) == 3
         rows = torch.arange(6, dtype=torch.float32).reshape(3, 2) + 100 * rank
         full = sharded.all_gather_rows(rows, dist.group.WORLD)
         want = torch.cat([torch.arange(6, dtype=torch.float32).reshape(3, 2) + 100 * r for r in range(world)])
