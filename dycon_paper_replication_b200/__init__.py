@@ -5,8 +5,8 @@
 ``FeCLoss(device, temperature)`` of ``code/utils/losses.py:221-250``.
 """
 from . import dycon_losses
-from .dycon_losses import (FeCLoss, UnCLoss, adaptive_beta, gambling_softmax, sigmoid_rampup,
-                           update_ema_variables)
+from .dycon_losses import (FeCLoss, StepLosses, UnCLoss, adaptive_beta, gambling_softmax, loss_is_finite_flag,
+                           sgd_clip_ema_step, sigmoid_rampup, update_ema_variables)
 
-__all__ = ["dycon_losses", "UnCLoss", "FeCLoss", "adaptive_beta", "sigmoid_rampup", "gambling_softmax",
-           "update_ema_variables"]
+__all__ = ["dycon_losses", "UnCLoss", "FeCLoss", "StepLosses", "adaptive_beta", "sigmoid_rampup", "gambling_softmax",
+           "update_ema_variables", "sgd_clip_ema_step", "loss_is_finite_flag"]

@@ -49,6 +49,13 @@ PROTOTYPES = {
                                _i, _p, _sz, _i, _i, _p, _p, _sz, _p]),
     "dycon_fecl_gn_bwd": (_i, [_p, _sz, _p, _i, _i, _i, _i, _f, _f, _i, _i, _f, _f, _i, _i, _i, _p, _p, _p,
                                _i64, _i64, _i64, _p]),
+    "dycon_segcons_workspace_bytes": (_sz, []),
+    "dycon_segcons_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i64, _f, _p, _p, _p, _sz, _p]),
+    "dycon_segcons_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i64, _f, _p, _p, _p, _p]),
+    "dycon_grad_norm_workspace_bytes": (_sz, []),
+    "dycon_grad_norm": (_i, [_p, _p, _i, _f, _p, _p, _sz, _p]),
+    "dycon_sgd_ema_step": (_i, [_p, _p, _p, _p, _p, _i, _f, _f, _f, _i, _i, _f, _f, _p, _p, _i, _p]),
+    "dycon_finite_check": (_i, [_p, _i, _p, _p, _p]),
     "dycon_ema_multi": (_i, [_p, _p, _p, _i, _f, _f, _p]),
     "dycon_exchange_inbox_bytes": (_sz, []),
     "dycon_exchange_enable_peer": (_i, [_i]),

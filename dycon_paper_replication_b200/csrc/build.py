@@ -19,8 +19,8 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 SO = os.path.join(PKG, "_dycon_b200.so")
 STAMP = SO + ".hash"
-SOURCES = ["api.cu", "uncl.cu", "ema.cu", "exchange.cu", "fecl_api.cu", "fecl_simt.cu", "fecl_tc.cu", "tc_host.cu"]
-HEADERS = ["common.cuh", "fecl_math.cuh", "fecl_internal.h", "tc_common.cuh", os.path.join(ROOT, "include", "dycon_b200.h")]
+SOURCES = ["api.cu", "uncl.cu", "segcons.cu", "ema.cu", "sgd_ema.cu", "exchange.cu", "fecl_api.cu", "fecl_simt.cu", "fecl_tc.cu", "tc_host.cu"]
+HEADERS = ["common.cuh", "exchange.cuh", "fecl_math.cuh", "fecl_internal.h", "tc_common.cuh", os.path.join(ROOT, "include", "dycon_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--use_fast_math" if False else "-DDYCON_NO_GLOBAL_FAST_MATH",   # fast intrinsics are chosen per call site

@@ -4,8 +4,13 @@
 // exist, so the sharded step has no extra launch in front of the backward.
 //
 // Inbox layout (per rank; allocated and ZERO-FILLED by the host, mapped into every peer through CUDA IPC):
-//   [kChannels][kSlots][kMaxRanks] entries of kEntry doubles: payload[0..6], then the sequence flag (int64 bits)
-//   followed by one int64 error word (non-zero: a wait timed out) per channel.
+//   [kChannels][kSlots][kMaxRanks] entries of 16 64-bit words, then one 64-bit error word per channel
+//   (non-zero: a wait timed out).
+// A double travels as TWO self-validating 64-bit words {32 bits of payload, 32-bit sequence tag} (the "LL"
+// scheme): a 64-bit store is single-copy atomic, so the receiver simply polls every word until its tag equals
+// the sequence number -- no payload / flag ordering, hence no system-scope fence and no second NVLink round trip
+// on the sender's side (the fenced payload-then-flag version cost ~8 us per exchange; this one costs about the
+// one-way latency).
 // Channels are independent exchanges with their own sequence counters (UnCL, FeCL, stand-alone), because the
 // kernels that use them may run in any order or concurrently.  Two slots alternate with the sequence parity: a
 // peer can only be one call ahead of this rank (it needs this rank's message of call k to finish call k), so
@@ -19,7 +24,7 @@ namespace dycon {
 constexpr int kXChannels = 3;        // DYCON_CHANNEL_*
 constexpr int kXSlots = 2;
 constexpr int kXMaxRanks = 16;
-constexpr int kXEntry = 8;           // doubles per entry: 7 payload + 1 flag
+constexpr int kXEntry = 16;          // 64-bit words per entry: two per double
 constexpr int kXMaxPayload = 7;
 constexpr size_t kXInboxDoubles = (size_t)kXChannels * kXSlots * kXMaxRanks * kXEntry + kXChannels;
 
@@ -45,52 +50,46 @@ __device__ __forceinline__ double exchange_warp(const ExchangeCtx& x, double min
   const int lane = threadIdx.x & 31;
   unsigned long long* seqp = x.seq + x.channel;
   const unsigned long long seq = *seqp + 1;                     // every lane reads the same value
+  const unsigned long long tag = (seq & 0xffffffffull) << 32;
   const int slot = (int)(seq & (kXSlots - 1));
   const size_t base = ((size_t)x.channel * kXSlots + slot) * kXMaxRanks;
   bool late = false;
-  // ---- send: my partials into entry [channel][slot][my rank] of every peer (my own inbox included) ----
-  for (int r = 0; r < x.world; ++r) {
-    double* dst = x.inbox[r] + (base + x.rank) * kXEntry;
-    if (lane < n) dst[lane] = mine;
-  }
-  __threadfence_system();                                       // payloads before flags, at system scope
-  __syncwarp();
-  if (lane < x.world) {
-    double* dst = x.inbox[lane] + (base + x.rank) * kXEntry;
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(reinterpret_cast<unsigned long long*>(dst + kXMaxPayload)),
-                 "l"(seq)
-                 : "memory");
-    // ---- receive: wait for peer `lane`'s entry in MY inbox ----
-    const double* src = x.inbox[x.rank] + (base + lane) * kXEntry;
-    unsigned long long got = 0, t0 = 0;
+  double acc = 0.0;
+  if (lane < n) {
+    // ---- send: words 2 lane, 2 lane + 1 of entry [channel][slot][my rank] of every peer (my own inbox included) ----
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
+    const unsigned long long w0 = tag | (bits & 0xffffffffull), w1 = tag | (bits >> 32);
+    for (int r = 0; r < x.world; ++r) {
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(x.inbox[r]) + (base + x.rank) * kXEntry + 2 * lane;
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst), "l"(w0) : "memory");
+      asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(dst + 1), "l"(w1) : "memory");
+    }
+    // ---- receive, in rank order: identical result on every rank ----
+    unsigned long long t0 = 0;
     unsigned int spins = 0;
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got)
-                   : "l"(reinterpret_cast<const unsigned long long*>(src + kXMaxPayload))
-                   : "memory");
-      if (got != seq) {
-        __nanosleep(64);
+    for (int r = 0; r < x.world && !late; ++r) {
+      const unsigned long long* src = reinterpret_cast<const unsigned long long*>(x.inbox[x.rank]) + (base + r) * kXEntry + 2 * lane;
+      unsigned long long a, b;
+      while (true) {
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(a) : "l"(src) : "memory");
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(b) : "l"(src + 1) : "memory");
+        if ((a & 0xffffffff00000000ull) == tag && (b & 0xffffffff00000000ull) == tag) break;
+        __nanosleep(32);
         if ((++spins & 1023u) == 0 && x.timeout_ns) {
           const unsigned long long now = global_timer_ns();
           if (t0 == 0) t0 = now;
           else if (now - t0 > x.timeout_ns) { late = true; break; }
         }
       }
-    } while (got != seq);
+      acc += __longlong_as_double((long long)((a & 0xffffffffull) | (b << 32)));
+    }
   }
   late = __any_sync(0xffffffffu, late);
-  double acc = 0.0;
-  if (lane < n) {                                               // fixed rank order: identical result on every rank
-    for (int r = 0; r < x.world; ++r) {
-      const volatile double* src = x.inbox[x.rank] + (base + r) * kXEntry;
-      acc += src[lane];
-    }
-    if (late) acc = __longlong_as_double(0x7ff8000000000000ll);
-  }
+  if (late) acc = __longlong_as_double(0x7ff8000000000000ll);
   __syncwarp();
   if (lane == 0) {
     *seqp = seq;
-    if (late) reinterpret_cast<unsigned long long*>(x.inbox[x.rank] + (size_t)kXChannels * kXSlots * kXMaxRanks * kXEntry)[x.channel] = seq;
+    if (late) reinterpret_cast<unsigned long long*>(x.inbox[x.rank])[(size_t)kXChannels * kXSlots * kXMaxRanks * kXEntry + x.channel] = seq;
   }
   return acc;
 }

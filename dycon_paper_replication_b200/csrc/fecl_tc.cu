@@ -22,6 +22,7 @@
 // The four forward kernels are chained with programmatic dependent launch.
 #include <cstdlib>
 #include <mutex>
+#include <type_traits>
 
 #include "exchange.cuh"
 #include "fecl_internal.h"
@@ -85,6 +86,118 @@ __device__ __forceinline__ float pos_bwd(float t, float e, float n, float gamma)
   return w1 * omd * fmaf(gamma * kLn2 * d, tL, -omd);
 }
 
+// ---- rows sorted by label ----------------------------------------------------------------------------
+// FeCL is equivariant under a permutation of the rows of a sample, and every pair term depends on the labels only
+// through same / different.  The forward therefore packs the rows of each sample SORTED by label (stable): a
+// (row block, column sub-tile) is then all-positive, all-negative or -- only where a class boundary crosses it --
+// mixed, which the sweeps and the backward turn into three specialised epilogue bodies and into sub-tiles that
+// are skipped outright.  fecl_rank_kernel computes, per sample, the sorted position of every row (a counting
+// rank: N^2 / 4 compares per 64-row CTA out of shared memory) and, by sorted position, the original row
+// (`perm`, used to scatter the gradient back), the label, the row weight and the class bounds
+// [cls_lo, cls_hi) = sorted positions that carry the same label.  NaN labels compare unequal to everything,
+// themselves included (dycon_losses.py:172): each NaN row is a class of its own.
+enum { kClsMixed = 0, kClsSame = 1, kClsDiff = 2 };
+
+struct RankParams {
+  const float* labels;       // (B, N), the caller's order
+  const float* row_weight;   // (B, N) or nullptr
+  int N;
+  int* rank;                 // rank[b*N + n] = sorted position of row n
+  int* perm;                 // perm[b*N + pos] = n
+  int* cls_lo;               // by sorted position
+  int* cls_hi;
+  float* ys;                 // labels by sorted position
+  float* rws;                // row weights by sorted position (written only with a row_weight)
+  int pdl;
+};
+
+__device__ __forceinline__ uint32_t label_key(float y) {
+  const uint32_t u = __float_as_uint(y + 0.f);            // -0 -> +0: they are the same label
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);      // unsigned order == float order
+}
+
+// Grid (ceil(N / 64), B), 256 threads: thread (r = tid % 64, q = tid / 64) counts, for row i = 64 blockIdx.x + r,
+// the keys of quarter q of the sample that sort before it.  Dynamic shared memory: ceil4(N) keys.
+__global__ void __launch_bounds__(256) fecl_rank_kernel(const RankParams p) {
+  extern __shared__ __align__(16) uint32_t rk_keys[];
+  __shared__ int part[3][4][64];
+  const int tid = threadIdx.x, b = blockIdx.y, N = p.N, N4 = (N + 3) & ~3;
+  if (p.pdl) pdl_trigger();
+  const float* lab = p.labels + (size_t)b * N;
+  for (int j = tid; j < N4; j += 256) rk_keys[j] = j < N ? label_key(__ldg(lab + j)) : 0xffffffffu;
+  __syncthreads();
+  const int r = tid & 63, q = tid >> 6, i = blockIdx.x * 64 + r;
+  const int ic = i < N ? i : N - 1;
+  const uint32_t k = rk_keys[ic];
+  const int groups = N4 >> 2, gq = (groups + 3) >> 2;           // uint4 groups per quarter
+  const int g0 = q * gq, g1 = min(groups, g0 + gq);
+  int lt = 0, le = 0, eqb = 0;                                  // keys < k, keys <= k, equal keys in front of row i
+  const uint4* k4 = reinterpret_cast<const uint4*>(rk_keys);
+  for (int g = g0; g < g1; ++g) {
+    const uint4 kk = k4[g];                                     // the same address for the lanes of a quarter: broadcast
+    const uint32_t ks[4] = {kk.x, kk.y, kk.z, kk.w};
+    const int j = g << 2;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      lt += ks[u] < k;
+      le += ks[u] <= k;
+    }
+    if (j + 3 < ic) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) eqb += ks[u] == k;
+    } else if (j < ic) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) eqb += (ks[u] == k) && (j + u < ic);
+    }
+  }
+  part[0][q][r] = lt; part[1][q][r] = le; part[2][q][r] = eqb;
+  __syncthreads();
+  if (q == 0 && i < N) {
+    lt = part[0][0][r] + part[0][1][r] + part[0][2][r] + part[0][3][r];
+    le = part[1][0][r] + part[1][1][r] + part[1][2][r] + part[1][3][r];
+    eqb = part[2][0][r] + part[2][1][r] + part[2][2][r] + part[2][3][r];
+    // the padding keys 0xffffffff count as <= k only for k == 0xffffffff, a NaN, whose bounds are set below
+    const float y = __ldg(lab + i);
+    const int pos = lt + eqb;
+    const size_t o = (size_t)b * N;
+    p.rank[o + i] = pos;
+    p.perm[o + pos] = i;
+    p.ys[o + pos] = y;
+    if (p.row_weight) p.rws[o + pos] = __ldg(p.row_weight + o + i);
+    const bool nan = y != y;
+    p.cls_lo[o + pos] = nan ? pos : lt;
+    p.cls_hi[o + pos] = nan ? pos + 1 : le;
+  }
+}
+
+// The label range of the rows of a CTA in sorted positions: their labels occupy [lo, hi); `uniform`: one label.
+struct RowClass { int lo, hi, uniform; };
+__device__ __forceinline__ RowClass load_row_class(const int* cls_lo, const int* cls_hi, size_t off, int i0, int rows, int N) {
+  RowClass rc{0, 0x7fffffff, 0};                                // rows not sorted: every sub-tile is MIXED
+  if (cls_lo) {
+    const int last = min(i0 + rows, N) - 1;
+    const int a = __ldg(cls_lo + off + i0), b = __ldg(cls_lo + off + last);
+    rc.lo = a;
+    rc.hi = __ldg(cls_hi + off + last);
+    rc.uniform = a == b;
+  }
+  return rc;
+}
+// Sub-tiles (tc columns each) whose pairs are ALL positive: [ta, tb).  hi <= N, so none of them holds padding.
+__device__ __forceinline__ void same_range(const RowClass& rc, int tc, int& ta, int& tb) {
+  ta = tb = 0;
+  if (rc.uniform) {
+    ta = (rc.lo + tc - 1) / tc;
+    tb = rc.hi / tc;
+    if (tb < ta) tb = ta;
+  }
+}
+__device__ __forceinline__ int tile_class(const RowClass& rc, int t, int tc, int N, int ta, int tb) {
+  if (t >= ta && t < tb) return kClsSame;
+  const int j0 = t * tc, j1 = min(j0 + tc, N);
+  return (j1 <= rc.lo || j0 >= rc.hi) ? kClsDiff : kClsMixed;   // padded columns of a DIFF sub-tile have e = 0, cs = 0
+}
+
 // ---- pack: fp32 (B,N,D) with element strides -> bf16 [B][Npad][Dpad], zero padded ---------------
 template <bool kBf16> struct Cvt;
 template <> struct Cvt<true> {
@@ -118,6 +231,8 @@ struct PackParams {
   int pdl;
   int merge;           // global-negatives mode: the B samples become ONE sample of B*N rows (row b*N + n, no
                        // per-sample padding; the caller zero-fills the tail rows of the state once)
+  const int* rank;     // rows sorted by label: row n of sample b goes to row rank[b*N + n] (nullptr: stays at n).
+                       // Written by fecl_rank_kernel, the predecessor in the stream: griddepcontrol.wait first.
 };
 
 template <bool kBf16>
@@ -164,21 +279,26 @@ pack16_kernel(const PackParams p) {
       }
     }
     __syncthreads();
+    if (p.rank && p.pdl) pdl_wait();       // the loads above overlap the rank kernel; its output is needed from here on
     const int kx = tid & 31, ry = tid >> 5;
 #pragma unroll 4
     for (int r = ry; r < 64; r += 8) {
       const int n = n0 + r;
-      if (p.merge ? n < p.N : n < p.Npad)
-        *reinterpret_cast<uint32_t*>(dst + ((size_t)b * (p.merge ? p.N : p.Npad) + n) * p.Dpad + d0 + 2 * kx) =
+      if (p.merge ? n < p.N : n < p.Npad) {
+        const int nd = (p.rank && n < p.N) ? __ldg(p.rank + (size_t)b * p.N + n) : n;
+        *reinterpret_cast<uint32_t*>(dst + ((size_t)b * (p.merge ? p.N : p.Npad) + nd) * p.Dpad + d0 + 2 * kx) =
             Cvt<kBf16>::two(tile[2 * kx][r], tile[2 * kx + 1][r]);
+      }
     }
   } else {         // any other layout (d contiguous or generic): lanes along d for both
+    if (p.rank && p.pdl) pdl_wait();
     const int tx = tid & 63, ty = tid >> 6;
     for (int r = ty; r < 64; r += 4) {
       const int n = n0 + r, d = d0 + tx;
       if (p.merge ? n < p.N : n < p.Npad) {
         const float v = (n < p.N && d < p.D) ? __ldg(s + (int64_t)n * sn + (int64_t)d * sd) : 0.f;
-        dst[((size_t)b * (p.merge ? p.N : p.Npad) + n) * p.Dpad + d] = Cvt<kBf16>::one(v);
+        const int nd = (p.rank && n < p.N) ? __ldg(p.rank + (size_t)b * p.N + n) : n;
+        dst[((size_t)b * (p.merge ? p.N : p.Npad) + nd) * p.Dpad + d] = Cvt<kBf16>::one(v);
       }
     }
   }
@@ -220,8 +340,11 @@ struct SweepParams {
   double inv_rows_d;
   float hscale;
   float* hdr;
-  const float* labels;
+  const float* labels;       // by row of the packed operands (sorted by label when cls_lo != nullptr)
   const float* row_weight;
+  const int* cls_lo;         // rows sorted by label: class bounds by row (nullptr: the caller's row order, P1 counts
+  const int* cls_hi;         // the positives itself)
+  int use_classes;           // specialise / skip sub-tiles by their label class (needs cls_lo)
   float* stat_m;       // zero-filled before the sweeps; split CTAs combine with atomicMax / atomicAdd (<= 2
   float* stat_p;       // contributors per address, so the float sums are order-independent: a+b == b+a)
   float* stat_n;
@@ -242,8 +365,26 @@ struct SweepMisc {
   alignas(16) float col[2][2][2][64];   // [team][slot][stat: y, m2][column]; padded columns: y = NaN, m2 = +inf
 };
 
+// The sub-tiles a CTA walks: compact index u in [0, count) -> sub-tile t.  One contiguous run with at most one
+// gap, because the sub-tiles of one label class are contiguous once the rows are sorted.
+struct TileMap { int base, gap_at, gap_len, count; };
+__device__ __forceinline__ int tile_of(const TileMap& tm, int u) {
+  const int t = u + tm.base;
+  return t >= tm.gap_at ? t + tm.gap_len : t;
+}
+
+// Cross (teacher) term of one pair: -log(1 - cs + 1e-18) over the hard negatives (dycon_losses.py:217-229), ONE
+// log per chunk of 16 pairs from the product of the 64 (1 - cs) -- the power of two keeps sixteen factors inside
+// fp32's range unless cs > 0.9999 on average; the caller then falls back to one log per pair (cross_chunk_end).
+__device__ __forceinline__ void cross_pair(float cs, bool hard, float& cprod, float& cmin, float& nh) {
+  const float fac = hard ? fmaf(-64.f, cs, 64.f) : 1.f;
+  cmin = fminf(cmin, fac);           // <= 0: cs >= 1 (NaN like the reference's log of a negative number, or 1e-18)
+  cprod *= fac;
+  nh += hard ? 1.f : 0.f;
+}
+
 // kMode 0: row max m_i                                            (P0)
-// kMode 1: negative sums n_i and the positive counts P_i           (P1; needs every m)
+// kMode 1: negative sums n_i (and, for unsorted rows, the positive counts P_i)   (P1; needs every m)
 // kMode 2: kappa_i, row loss, A_i and the teacher cross term       (P2; needs every n and P)
 // Grid (row blocks, column splits, samples).  Three launches instead of one fused sweep: n_i needs all m_k
 // and d_ij needs the complete n_i, i.e. two grid-wide dependencies, and splitting the columns of a row
@@ -253,6 +394,10 @@ struct SweepMisc {
 // all columns of the sub-tile).  That halves the operand bytes per flop for P0 / P1, and -- what matters for
 // the epilogue-bound P2 -- it lets the grid be (row blocks / 2) x (up to 8 column splits): 140 of the 148 SMs
 // at the BraTS19 shape instead of the 112 that 128-row blocks x 2 splits reach.
+// Label classes (rows sorted by label): P1 only needs the sub-tiles that hold a negative pair and P2 without a
+// teacher only those that hold a positive pair -- the others are not even loaded -- and P2's epilogue runs a
+// positives-only body on all-positive sub-tiles, a cross-only body on all-negative ones and the general body
+// only where a class boundary crosses the sub-tile.  The class is uniform over the team, so nothing diverges.
 template <int kMode, bool kBf16, int kFocal, int kRT>
 __global__ void __launch_bounds__(kSwThreads, 1)
 fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapF,
@@ -270,8 +415,6 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   const bool teacher_on = kMode == 2 && p.has_teacher;
   const int tcols = teacher_on ? 32 : 64;                  // columns per sub-tile
   const int nt_all = (p.N + tcols - 1) / tcols;            // sub-tiles that hold at least one real column
-  const int jt0 = (int)((long long)split * nt_all / p.splits), jt1 = (int)((long long)(split + 1) * nt_all / p.splits);
-  const int nt = jt1 - jt0;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
@@ -297,22 +440,41 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 
   // Programmatic dependent launch: this grid may have started while the previous sweep (or the pack kernel)
   // still runs.  P0 reads the pack kernel's output, so everybody waits here; P1 / P2 only depend on their
-  // predecessor through the row statistics, so the TMA producer and the MMA issuers run ahead (operands come
-  // from the pack kernel, which is complete once the predecessor has passed its own wait) and only the
-  // epilogue warps wait, right before they first touch the statistics.
+  // predecessor through the row statistics, so the TMA producer and the MMA issuers run ahead (operands and
+  // class bounds come from the pack / rank kernels, which are complete once the predecessor has passed its own
+  // wait) and only the epilogue warps wait, right before they first touch the statistics.
   if (kMode == 0 && p.pdl) pdl_wait();
+
+  // ---- which sub-tiles this CTA walks (every agent computes the same map) ----
+  RowClass rc{0, 0x7fffffff, 0};
+  if (kMode != 0 && p.use_classes) rc = load_row_class(p.cls_lo, p.cls_hi, (size_t)b * p.N, i0, kTM * kRT, p.N);
+  int ta, tb;
+  same_range(rc, tcols, ta, tb);
+  TileMap tmap{0, 0x7fffffff, 0, nt_all};
+  if (kMode == 1) {                                  // all-positive sub-tiles hold no negative pair
+    tmap.gap_at = ta;
+    tmap.gap_len = tb - ta;
+    tmap.count = nt_all - (tb - ta);
+  } else if (kMode == 2 && !teacher_on) {            // all-negative sub-tiles hold no positive pair
+    const int td0 = min(rc.lo / tcols, nt_all - 1);
+    const int td1 = rc.hi >= p.N ? nt_all : (rc.hi + tcols - 1) / tcols;
+    tmap.base = td0;
+    tmap.count = max(td1 - td0, 1);
+  }
+  const int u0 = (int)((long long)split * tmap.count / p.splits), u1 = (int)((long long)(split + 1) * tmap.count / p.splits);
+  const int nt = u1 - u0;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0 && nt > 0) {
+    if (lane == 0) {
       // first the K chunk the first MMA needs, then the first B sub-tile, then the rest of A
       auto load_a = [&](int h, int c) {
         mbar_expect_tx(&ms.a_full[h * 4 + c], kChunk128);
         tma_load_2d(sA + h * a_tile + c * kChunk128, &mapA, c * 64, b * p.Npad + i0 + h * kTM, &ms.a_full[h * 4 + c]);
       };
-      load_a(0, 0);
+      if (nt > 0) load_a(0, 0);
       for (int t = 0; t < nt; ++t) {
-        const int s = t % kStages, row = b * p.Npad + (jt0 + t) * tcols;
+        const int s = t % kStages, row = b * p.Npad + tile_of(tmap, u0 + t) * tcols;
         uint8_t* dst = sStage + s * stage_bytes;
         mbar_wait_relaxed(&ms.b_empty[s], ((t / kStages) & 1) ^ 1);
         mbar_expect_tx(&ms.b_full[s], stage_bytes);
@@ -382,10 +544,10 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     // this thread's columns of a sub-tile: 32 of 64 (F only), or 16 of 32 of both S and CS (teacher)
     const int cbase = kRT == 2 ? 0 : teacher_on ? chalf * 16 : chalf * 32;
 
-    // column statistics of sub-tile t (tcols columns): threads 0..63 fetch the label, 64..127 the scaled max
-    auto fetch = [&](int t) -> float {
+    // column statistics of sub-tile T (tcols columns): threads 0..63 fetch the label, 64..127 the scaled max
+    auto fetch = [&](int T) -> float {
       if (tt >= 128) return 0.f;
-      const int c = tt & 63, j = t * tcols + c;
+      const int c = tt & 63, j = T * tcols + c;
       const bool ok = c < tcols && j < p.N;
       if (tt < 64) return ok ? __ldg(yb + j) : qnan;
       if (kMode == 0) return 0.f;
@@ -409,19 +571,23 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       }
       const bool row_writer = split == 0 && team == 0 && (kRT == 2 || chalf == 0) && row_ok;   // one thread per row
       if (row_writer) p.stat_n[g] = n_row;
-      // kappa_i = r_i c_i / (B N),  c_i = 1/(P_i - 1 + 1e-18)   (dycon_losses.py:192; P from the P1 launch)
+      // kappa_i = r_i c_i / (B N),  c_i = 1/(P_i - 1 + 1e-18)   (dycon_losses.py:192).  P_i = the size of the row's
+      // label class (sorted rows), else the count of the P1 launch
       const float rw = p.row_weight ? __ldg(p.row_weight + g) : 1.f;
-      kappa = rw / ((__ldg(p.stat_p + g) - 1.f) + kTiny) * p.inv_rows;
+      const float P_i = p.cls_lo ? (float)(__ldg(p.cls_hi + g) - __ldg(p.cls_lo + g)) : __ldg(p.stat_p + g);
+      kappa = rw / ((P_i - 1.f) + kTiny) * p.inv_rows;
       if (row_writer) p.stat_kappa[g] = kappa;
     }
 
-    if (team < nt) publish(0, fetch(jt0 + team));
+    if (team < nt) publish(0, fetch(tile_of(tmap, u0 + team)));
     sw_team_barrier(team);
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
     int it = 0;                                   // team-local iteration: sub-tile t = team + 2 * it
     for (int t = team; t < nt; t += 2, ++it) {
-      const int slot = it & 1, a = t & (kSwSlots - 1), j0 = (jt0 + t) * tcols;
-      const float nxt = fetch(jt0 + (t + 2 < nt ? t + 2 : t));
+      const int T = tile_of(tmap, u0 + t);        // sub-tile index inside the sample
+      const int slot = it & 1, a = t & (kSwSlots - 1), j0 = T * tcols;
+      const int cls = kMode == 0 ? kClsMixed : tile_class(rc, T, tcols, p.N, ta, tb);      // uniform over the team
+      const float nxt = fetch(tile_of(tmap, u0 + (t + 2 < nt ? t + 2 : t)));
       mbar_wait(&ms.acc_full[a], (t / kSwSlots) & 1);
       tcgen05_after_sync();
       if (!teacher_on) {
@@ -451,17 +617,26 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
               for (int c = 0; c < 32; ++c) acc0 = fmaxf(acc0, v[c]);     // padded columns hold S = 0 <= acc0
             }
           } else if (kMode == 1) {   // acc0 = n_i partial, acc1 = positive count                  (dycon_losses.py:183-184,192)
+            if (cls == kClsDiff) {   // every pair is a negative (padded columns: m2 = +inf -> e = 0)
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
-              const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
-              const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
+              for (int q = 0; q < 8; ++q) {
+                const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
+                acc0 += ex2_approx(fmaf(v[q * 4], p.c1, -mm.x)) + ex2_approx(fmaf(v[q * 4 + 1], p.c1, -mm.y));
+                acc0 += ex2_approx(fmaf(v[q * 4 + 2], p.c1, -mm.z)) + ex2_approx(fmaf(v[q * 4 + 3], p.c1, -mm.w));
+              }
+            } else {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const float e = ex2_approx(fmaf(v[q * 4 + k], p.c1, -m2[k]));   // padded: m2 = +inf -> e = 0
-                const bool same = ys[k] == yi;
-                acc0 += same ? 0.f : e;
-                acc1 += same ? 1.f : 0.f;
+              for (int q = 0; q < 8; ++q) {
+                const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
+                const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
+                const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float e = ex2_approx(fmaf(v[q * 4 + k], p.c1, -m2[k]));   // padded: m2 = +inf -> e = 0
+                  const bool same = ys[k] == yi;
+                  acc0 += same ? 0.f : e;
+                  acc1 += same ? 1.f : 0.f;
+                }
               }
             }
           } else {                   // acc0 / acc1 = loss / A partials                              (dycon_losses.py:186-206)
@@ -476,7 +651,8 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 const float tl = fmaf(v[c], p.c1, -m2[k]);
                 float phi2, at;
                 pos_fwd<kFocal>(tl, ex2_approx(tl), n_row, p.sc.gamma, phi2, at);
-                const bool pos = diag_here ? (ys[k] == yi) && (c != rdiag) : (ys[k] == yi);   // select, never multiply
+                const bool same = cls == kClsSame || ys[k] == yi;                 // (cls is uniform: no divergence)
+                const bool pos = diag_here ? same && (c != rdiag) : same;         // select, never multiply
                 acc0 += pos ? phi2 : 0.f;
                 acc1 += pos ? at : 0.f;
               }
@@ -493,8 +669,8 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           const float* cm = &ms.col[team][slot][1][cb];
           const int rdiag = i - j0 - cb;          // chunk-local column of the diagonal pair, if in range
           float v[16], w[16];
-          tmem_ld16(tmem + lane_base + a * kSlotCols + rh * 64 + cb, v);
-          tmem_ld16(tmem + lane_base + a * kSlotCols + rh * 64 + 32 + cb, w);
+          if (cls != kClsDiff) tmem_ld16(tmem + lane_base + a * kSlotCols + rh * 64 + cb, v);        // S: positives
+          if (cls != kClsSame) tmem_ld16(tmem + lane_base + a * kSlotCols + rh * 64 + 32 + cb, w);   // CS: negatives
           tmem_ld_wait();
           if (ch == kRT - 1) {
             tcgen05_before_sync();
@@ -503,42 +679,72 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           }
           const int w0 = i0 + rh * kTM + quarter * 32 - j0 - cb;
           const bool diag_here = w0 + 31 >= 0 && w0 < 16;
-          // one log per FOUR hard negatives (product of their 1 - cs): a factor is 1e-18 (cs == 1 exactly), or
-          // >= 2^-24 (the fp32 spacing below 1), or negative (cs > 1: NaN, like the reference's log of a negative
-          // number), so four regular factors cannot underflow; a group that does falls back to one log per pair
-          float cmin = 1.f;        // smallest factor of the chunk: an even number of negative factors must not cancel
+          if (cls == kClsSame) {
+            // all-positive sub-tile: student terms only, no label test, no hard negatives
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
-            const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
-            const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
-            float fac[4];
+            for (int q = 0; q < 4; ++q) {
+              const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
+              const float m2[4] = {mm.x, mm.y, mm.z, mm.w};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int c = q * 4 + k;
-              const float tl = fmaf(v[c], p.c1, -m2[k]);
-              float phi2, at;
-              pos_fwd<kFocal>(tl, ex2_approx(tl), n_row, p.sc.gamma, phi2, at);
-              const bool same = ys[k] == yi;
-              const bool pos = diag_here ? same && (c != rdiag) : same;
-              acc0 += pos ? phi2 : 0.f;
-              acc1 += pos ? at : 0.f;
-              // cross term: -log(1 - cs + 1e-18) over labels differ && cs > thresh (dycon_losses.py:217-229).
-              // Padded columns (y = NaN, so !same) have cs == 0 exactly (zero teacher rows) and the host
-              // guarantees thresh >= 0, so they are never hard negatives; padded rows are dropped at the end.
-              const float cs = w[c];
-              const bool hard = !same && cs > p.sc.cross_thresh;
-              fac[k] = hard ? (1.f - cs) + kTiny : 1.f;
-              cmin = fminf(cmin, fac[k]);
-              acc3 += hard ? 1.f : 0.f;
+              for (int k = 0; k < 4; ++k) {
+                const int c = q * 4 + k;
+                const float tl = fmaf(v[c], p.c1, -m2[k]);
+                float phi2, at;
+                pos_fwd<kFocal>(tl, ex2_approx(tl), n_row, p.sc.gamma, phi2, at);
+                const bool pos = !diag_here || c != rdiag;
+                acc0 += pos ? phi2 : 0.f;
+                acc1 += pos ? at : 0.f;
+              }
             }
-            const float gp = (fac[0] * fac[1]) * (fac[2] * fac[3]);
-            if (gp < 1e-30f)         // rare: several cs == 1 pairs (or a negative factor) in one group
-              acc2 += (lg2_approx(fac[0]) + lg2_approx(fac[1])) + (lg2_approx(fac[2]) + lg2_approx(fac[3]));
-            else
-              acc2 += lg2_approx(gp);
+          } else {
+            // cross term: -log(1 - cs + 1e-18) over labels differ && cs > thresh (dycon_losses.py:217-229).
+            // Padded columns (y = NaN, so never "same") have cs == 0 exactly (zero teacher rows) and the host
+            // guarantees thresh >= 0, so they are never hard negatives; padded rows are dropped at the end.
+            float cprod = 1.f, cmin = 1.f, nh = 0.f;
+            if (cls == kClsDiff) {
+              // all-negative sub-tile: no student term at all (the loss sums over positives only)
+#pragma unroll
+              for (int c = 0; c < 16; ++c) cross_pair(w[c], w[c] > p.sc.cross_thresh, cprod, cmin, nh);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
+                const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
+                const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const int c = q * 4 + k;
+                  const float tl = fmaf(v[c], p.c1, -m2[k]);
+                  float phi2, at;
+                  pos_fwd<kFocal>(tl, ex2_approx(tl), n_row, p.sc.gamma, phi2, at);
+                  const bool same = ys[k] == yi;
+                  const bool pos = diag_here ? same && (c != rdiag) : same;
+                  acc0 += pos ? phi2 : 0.f;
+                  acc1 += pos ? at : 0.f;
+                  cross_pair(w[c], !same && w[c] > p.sc.cross_thresh, cprod, cmin, nh);
+                }
+              }
+            }
+            acc3 += nh;
+            if (cmin > 0.f && cprod >= 1e-30f) {
+              acc2 += fmaf(-6.f, nh, lg2_approx(cprod));      // sum of log2(1 - cs): undo the 64 per hard negative
+            } else {
+              // rare: a pair with cs >= 1 (NaN / log(1e-18), as in the reference) or sixteen collapsed pairs whose
+              // product underflows -- one log per pair
+              const float4* cy4 = reinterpret_cast<const float4*>(cy);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {      // (unrolled: w[] must stay in registers)
+                const float4 yy = cy4[q];
+                const float ys[4] = {yy.x, yy.y, yy.z, yy.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float cs = w[q * 4 + k];
+                  const bool hard = (cls == kClsDiff || !(ys[k] == yi)) && cs > p.sc.cross_thresh;
+                  if (hard) acc2 += lg2_approx((1.f - cs) + kTiny);
+                }
+              }
+            }
           }
-          if (cmin < 0.f) acc2 = qnan;
         }
       }
       publish(slot ^ 1, nxt);
@@ -560,13 +766,15 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         if (kMode == 0) acc0 = fmaxf(acc0, o.x); else acc0 += o.x;
         acc1 += o.y; acc2 += o.z; acc3 += o.w;
       }
-      if (row_ok && nt > 0) {
+      // (a CTA without sub-tiles -- more splits than sub-tiles left after skipping -- still writes its zero
+      //  partials: the consumers add up every split's plane)
+      if (row_ok) {
         if (kMode == 0) {
           const float m = acc0 * p.sc.inv_tau;                           // >= 0, so the int ordering is the float ordering
           atomicMax(reinterpret_cast<int*>(p.stat_m + g), __float_as_int(m));
         } else if (kMode == 1) {
           p.npart[(size_t)split * gridDim.z * p.N + g] = acc0;           // summed in split order by P2 (deterministic)
-          atomicAdd(p.stat_p + g, acc1);                                  // integer-valued: exact in any order
+          if (!p.cls_lo) atomicAdd(p.stat_p + g, acc1);                  // integer-valued: exact in any order
         } else {
           p.apart[(size_t)split * gridDim.z * p.N + g] = acc1;           // summed in split order by the backward
           red[0] = (double)(kappa * (-kLn2 * acc0));                      // kappa_i = r_i c_i inv_rows
@@ -650,6 +858,10 @@ struct BwdParams {
   int64_t g_sb, g_sn, g_sd;
   int rb_lo, row_lo, row_hi;   // row blocks / rows of this launch (see SweepParams)
   int grad_rows;               // rows per sample of grad_feat in global-negatives mode (0: row i of sample b)
+  const int* cls_lo;           // rows sorted by label (nullptr: the caller's order): class bounds by row, and the
+  const int* cls_hi;           // original row of every sorted position -- the gradient is scattered back through it
+  const int* perm;
+  int use_classes;             // specialise the pair arithmetic by the label class of a sub-tile
 };
 
 struct BwdMisc {
@@ -660,35 +872,55 @@ struct BwdMisc {
   uint64_t df_full;
   uint32_t tmem_slot;
   uint32_t pad_;
-  alignas(16) float col[2][2][5][32];    // [team][slot][y, m2, n, -kappa A h, kappa h][column]
+  alignas(16) float col[2][2][5][32];    // [team][slot][y, m2, n 2^-m2, -kappa A h 2^m2, kappa h][column]
 };
 
-template <int kFocal, bool kTeacher>
-__device__ __forceinline__ void bwd_pair(float x, float cs, float yi, float m2i, float ni, float Pi, float ki,
-                                         float yj, float m2j, float nj, float Pj, float kj, float c1, float gamma,
+// One pair (i, j) of a sub-tile, both directions at once (H = G + G^T is built from S_ij = S_ji):
+//   e_ij = 2^(x c1 - m2_j) costs the ONE ex2 of the pair; the other direction, e_ji = 2^(x c1 - m2_i) =
+//   e_ij 2^m2_j 2^-m2_i, only ever appears as d_ji = e_ji / (e_ji + n_j) and as P_j e_ji, so it is carried
+//   divided by 2^m2_j:  ejs = e_ij ui (ui = 2^-m2_i, per row) against the column statistics njs = n_j 2^-m2_j and
+//   Pjs = P_j 2^m2_j, which the publishing threads scale once per column (m2 clamped at 120 in these factors, far
+//   above anything 16-bit operands can resolve).
+// kCls: the label class of the sub-tile (uniform over the team) -- all pairs positive (SAME: the focal terms of
+// both directions, no teacher term), all negative (DIFF: two FMAs, plus the teacher's 1/(1 - cs)), or MIXED
+// (both, then a select).
+template <int kFocal, bool kTeacher, int kCls>
+__device__ __forceinline__ void bwd_pair(float x, float cs, float yi, float m2i, float ui, float ni, float Pi, float ki,
+                                         float yj, float m2j, float njs, float Pjs, float kj, float c1, float gamma,
                                          float gl, float thresh, float gcs, float& h, float& g) {
-  const float tij = fmaf(x, c1, -m2j), tji = fmaf(x, c1, -m2i);
-  const float eij = ex2_approx(tij), eji = ex2_approx(tji);     // padded column: m2j = +inf -> eij = 0
-  const float Tij = eij + ni, Tji = eji + nj;
-  const float p2 = Tij * Tji;
+  const float tij = fmaf(x, c1, -m2j);
+  const float eij = ex2_approx(tij);                             // padded column: m2j = +inf -> eij = 0
+  const float ejs = eij * ui;
+  if (kCls == kClsDiff) {
+    h = fmaf(Pi, eij, Pjs * ejs);
+    g = 0.f;
+    if (kTeacher) {
+      // padded columns have cs == 0 exactly (zero teacher rows) and thresh >= 0 (host check): never hard
+      const float om = (1.f - cs) + kTiny;                       // dycon_losses.py:228
+      g = cs > thresh ? gcs * rcp_approx(om) : 0.f;
+    }
+    return;
+  }
+  const float Tij = eij + ni, Tjs = ejs + njs;
+  const float p2 = Tij * Tjs;
   float r2, rom = 0.f;
-  if (kTeacher) {
-    const float om = (1.f - cs) + kTiny;                         // dycon_losses.py:228
-    const float r = rcp_approx(p2 * om);
+  if (kTeacher && kCls == kClsMixed) {
+    const float om = (1.f - cs) + kTiny;
+    const float r = rcp_approx(p2 * om);                         // 1/T_ij, 1/T_ji, 1/(1-cs) from ONE reciprocal
     rom = r * p2;
     r2 = r * om;
   } else {
     r2 = rcp_approx(p2);
   }
-  const float rij = r2 * Tji, rji = r2 * Tij;
+  const float rij = r2 * Tjs, rjs = r2 * Tij;
   float pij, pji;                                                // phi'(d) d (1 - d)
   if (kFocal == kNoFocal) {
     pij = fmaf(eij, rij, -1.f);
-    pji = fmaf(eji, rji, -1.f);
+    pji = fmaf(ejs, rjs, -1.f);
   } else {
-    const float dij = eij * rij, dji = eji * rji;
-    float oij = fmaf(-eij, rij, 1.f), oji = fmaf(-eji, rji, 1.f);
-    const float Lij = tij - lg2_approx(Tij), Lji = tji - lg2_approx(Tji);   // log2 d
+    const float dij = eij * rij, dji = ejs * rjs;
+    float oij = fmaf(-eij, rij, 1.f), oji = fmaf(-ejs, rjs, 1.f);
+    const float Lij = tij - lg2_approx(Tij), Lji = (tij - m2i) - lg2_approx(Tjs);   // log2 d
     if (kFocal == kFocalG2) {
       const float aij = fmaf(gl, dij * Lij, -oij), aji = fmaf(gl, dji * Lji, -oji);
       pij = oij * oij * aij;
@@ -701,16 +933,15 @@ __device__ __forceinline__ void bwd_pair(float x, float cs, float yi, float m2i,
     }
   }
   const float gpos = fmaf(ki, pij, kj * pji);
-  const float gneg = fmaf(Pi, eij, Pj * eji);
+  if (kCls == kClsSame) {
+    h = gpos;
+    g = 0.f;
+    return;
+  }
+  const float gneg = fmaf(Pi, eij, Pjs * ejs);
   const bool same = yj == yi;                                    // NaN labels (padding) compare unequal
   h = same ? gpos : gneg;                                        // select: the unused branch may be NaN
-  if (kTeacher) {
-    // padded columns have cs == 0 exactly (zero teacher rows) and thresh >= 0 (host check): never hard
-    const bool hard = !same && cs > thresh;
-    g = hard ? gcs * rom : 0.f;
-  } else {
-    g = 0.f;
-  }
+  g = (kTeacher && !same && cs > thresh) ? gcs * rom : 0.f;
 }
 
 // Zero fill of the gradient for the split backward.  It releases its dependent at once: the backward is
@@ -747,6 +978,12 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   const int t0 = (int)((long long)split * nt_all / p.splits), t1 = (int)((long long)(split + 1) * nt_all / p.splits);
   const int nt = t1 - t0;                       // this CTA's 32-column sub-tiles: t0 .. t1-1
   const bool teacher = p.has_teacher != 0;
+  // label class of every sub-tile (rows sorted by label): all-positive sub-tiles need no teacher term at all --
+  // no Gc tile, no Gc T_J MMAs -- and every class has its own pair arithmetic (bwd_pair)
+  RowClass rc{0, 0x7fffffff, 0};
+  if (p.use_classes) rc = load_row_class(p.cls_lo, p.cls_hi, (size_t)b * p.N, i0, kTM, p.N);
+  int ta, tb;
+  same_range(rc, 32, ta, tb);
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
@@ -841,7 +1078,7 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
 #pragma unroll
         for (int k = 0; k < 2; ++k)
           umma_bf16(tm_df, desc_advance(h_desc0, (g * 2 + k) * 32), desc_advance(f_desc0, k * 2048), idesc_d, (t | k) != 0);
-        if (teacher) {
+        if (teacher && tile_class(rc, t0 + t, 32, p.N, ta, tb) != kClsSame) {
 #pragma unroll
           for (int k = 0; k < 2; ++k)
             umma_bf16(tm_df, desc_advance(g_desc0, (g * 2 + k) * 32), desc_advance(f_desc0, kChunk32 + k * 2048), idesc_d, true);
@@ -867,6 +1104,7 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const float h_mul = p.sc.inv_tau * hscale;
     const float yi = row_ok ? __ldg(p.labels + off + ic) : qnan;
     const float m2i = __ldg(p.stat_m + off + ic) * kLog2e;
+    const float ui = ex2_approx(-fminf(m2i, 120.f));          // e_ji / 2^m2_j = e_ij ui, see bwd_pair
     const float ni = __ldg(p.stat_n + off + ic);
     const float ki = row_ok ? __ldg(p.stat_kappa + off + ic) * h_mul : 0.f;
     const size_t bn = (size_t)gridDim.z * p.N;      // plane stride of the statistics
@@ -896,10 +1134,11 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       if (j >= p.N) return st == 0 ? qnan : st == 1 ? INFINITY : 0.f;
       const size_t g = off + j;
       if (st == 0) return __ldg(p.labels + g);
-      if (st == 1) return __ldg(p.stat_m + g) * kLog2e;
-      if (st == 2) return __ldg(p.stat_n + g);
+      const float m2 = __ldg(p.stat_m + g) * kLog2e;
+      if (st == 1) return m2;
+      if (st == 2) return __ldg(p.stat_n + g) * ex2_approx(-fminf(m2, 120.f));          // n_j 2^-m2_j
       const float kh = __ldg(p.stat_kappa + g) * h_mul;
-      return st == 3 ? -kh * a_of(g) : kh;
+      return st == 3 ? -kh * a_of(g) * ex2_approx(fminf(m2, 120.f)) : kh;              // P_j 2^m2_j | kappa_j h
     };
     auto publish = [&](int slot, float v) {
       if (tt < 160) ms.col[team][slot][tt >> 5][tt & 31] = v;
@@ -911,11 +1150,13 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     for (int t = team; t < nt; t += 2, ++it) {
       const int slot = it & 1, j0 = (t0 + t) * 32;
       const float nx = fetch_one(t0 + (t + 2 < nt ? t + 2 : t));
+      const int cls = tile_class(rc, t0 + t, 32, p.N, ta, tb);       // uniform over the team: no divergence
+      const bool with_g = teacher && cls != kClsSame;                 // all-positive sub-tiles have no hard negatives
       mbar_wait(&ms.sc_full[team], it & 1);
       tcgen05_after_sync();
       float sv[16], cv[16];
       tmem_ld16(tm_sc + lane_base + team * 64 + cbase, sv);
-      if (teacher) tmem_ld16(tm_sc + lane_base + team * 64 + 32 + cbase, cv);
+      if (with_g) tmem_ld16(tm_sc + lane_base + team * 64 + 32 + cbase, cv);
       tmem_ld_wait();
       tcgen05_before_sync();
       __syncwarp();
@@ -927,36 +1168,49 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       const float* cp = &ms.col[team][slot][3][cbase];
       const float* ck = &ms.col[team][slot][4][cbase];
       uint32_t hp[8], gp[8];
+      auto pairs = [&](auto cls_tag) {
+        constexpr int kCls = decltype(cls_tag)::value;
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 y4 = *reinterpret_cast<const float4*>(cy + q * 4), m4 = *reinterpret_cast<const float4*>(cm + q * 4);
-        const float4 n4 = *reinterpret_cast<const float4*>(cn + q * 4), p4 = *reinterpret_cast<const float4*>(cp + q * 4);
-        const float4 k4 = *reinterpret_cast<const float4*>(ck + q * 4);
-        const float ys[4] = {y4.x, y4.y, y4.z, y4.w}, m2[4] = {m4.x, m4.y, m4.z, m4.w}, ns[4] = {n4.x, n4.y, n4.z, n4.w};
-        const float ps[4] = {p4.x, p4.y, p4.z, p4.w}, ks[4] = {k4.x, k4.y, k4.z, k4.w};
-        float hv[4], gv[4];
+        for (int q = 0; q < 4; ++q) {
+          const float4 m4 = *reinterpret_cast<const float4*>(cm + q * 4), p4 = *reinterpret_cast<const float4*>(cp + q * 4);
+          const float m2[4] = {m4.x, m4.y, m4.z, m4.w}, ps[4] = {p4.x, p4.y, p4.z, p4.w};
+          float ys[4] = {0.f, 0.f, 0.f, 0.f}, ns[4] = {0.f, 0.f, 0.f, 0.f}, ks[4] = {0.f, 0.f, 0.f, 0.f};
+          if (kCls == kClsMixed) {
+            const float4 y4 = *reinterpret_cast<const float4*>(cy + q * 4);
+            ys[0] = y4.x; ys[1] = y4.y; ys[2] = y4.z; ys[3] = y4.w;
+          }
+          if (kCls != kClsDiff) {
+            const float4 n4 = *reinterpret_cast<const float4*>(cn + q * 4), k4 = *reinterpret_cast<const float4*>(ck + q * 4);
+            ns[0] = n4.x; ns[1] = n4.y; ns[2] = n4.z; ns[3] = n4.w;
+            ks[0] = k4.x; ks[1] = k4.y; ks[2] = k4.z; ks[3] = k4.w;
+          }
+          float hv[4], gv[4];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int c = q * 4 + k;
-          if (teacher)
-            bwd_pair<kFocal, true>(sv[c], cv[c], yi, m2i, ni, Pi, ki, ys[k], m2[k], ns[k], ps[k], ks[k], p.c1,
-                                   p.sc.gamma, gl, p.sc.cross_thresh, gcs, hv[k], gv[k]);
-          else
-            bwd_pair<kFocal, false>(sv[c], 0.f, yi, m2i, ni, Pi, ki, ys[k], m2[k], ns[k], ps[k], ks[k], p.c1,
-                                    p.sc.gamma, gl, p.sc.cross_thresh, gcs, hv[k], gv[k]);
+          for (int k = 0; k < 4; ++k) {
+            const int c = q * 4 + k;
+            if (teacher)
+              bwd_pair<kFocal, true, kCls>(sv[c], cv[c], yi, m2i, ui, ni, Pi, ki, ys[k], m2[k], ns[k], ps[k], ks[k],
+                                           p.c1, p.sc.gamma, gl, p.sc.cross_thresh, gcs, hv[k], gv[k]);
+            else
+              bwd_pair<kFocal, false, kCls>(sv[c], 0.f, yi, m2i, ui, ni, Pi, ki, ys[k], m2[k], ns[k], ps[k], ks[k],
+                                            p.c1, p.sc.gamma, gl, p.sc.cross_thresh, gcs, hv[k], gv[k]);
+          }
+          hp[q * 2] = Cvt<kBf16>::two(hv[0], hv[1]);
+          hp[q * 2 + 1] = Cvt<kBf16>::two(hv[2], hv[3]);
+          gp[q * 2] = Cvt<kBf16>::two(gv[0], gv[1]);
+          gp[q * 2 + 1] = Cvt<kBf16>::two(gv[2], gv[3]);
         }
-        hp[q * 2] = Cvt<kBf16>::two(hv[0], hv[1]);
-        hp[q * 2 + 1] = Cvt<kBf16>::two(hv[2], hv[3]);
-        gp[q * 2] = Cvt<kBf16>::two(gv[0], gv[1]);
-        gp[q * 2 + 1] = Cvt<kBf16>::two(gv[2], gv[3]);
-      }
+      };
+      if (cls == kClsSame) pairs(std::integral_constant<int, kClsSame>{});
+      else if (cls == kClsDiff) pairs(std::integral_constant<int, kClsDiff>{});
+      else pairs(std::integral_constant<int, kClsMixed>{});
       // the team's previous MMA2 must have finished reading this column half of sH / sG
       if (it > 0) mbar_wait(&ms.h_free[team], (it - 1) & 1);
 #pragma unroll
       for (int u = 0; u < 2; ++u) {     // two 16-byte units = 16 16-bit columns
         const uint32_t o = sw128_offset(r, hcol + u * 8);
         *reinterpret_cast<uint4*>(sH + o) = make_uint4(hp[u * 4], hp[u * 4 + 1], hp[u * 4 + 2], hp[u * 4 + 3]);
-        if (teacher) *reinterpret_cast<uint4*>(sG + o) = make_uint4(gp[u * 4], gp[u * 4 + 1], gp[u * 4 + 2], gp[u * 4 + 3]);
+        if (with_g) *reinterpret_cast<uint4*>(sG + o) = make_uint4(gp[u * 4], gp[u * 4 + 1], gp[u * 4 + 2], gp[u * 4 + 3]);
       }
       // the diagonal pair carries no gradient (l_ii is multiplied by 0, dycon_losses.py:176-178): clear it in
       // place instead of testing every pair.  (Its Gc is already 0: same label, never a hard negative.)
@@ -984,7 +1238,9 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         // global-negatives mode: row i of the merged batch is row (i - row_lo) % grad_rows of local sample
         // (i - row_lo) / grad_rows of this rank's gradient tensor
         const int il = i - p.row_lo;
-        const int gb = p.grad_rows ? il / p.grad_rows : b, gn = p.grad_rows ? il - gb * p.grad_rows : i;
+        // sorted rows: position i of sample b is the caller's row perm[i]
+        const int gb = p.grad_rows ? il / p.grad_rows : b;
+        const int gn = p.grad_rows ? il - gb * p.grad_rows : p.perm ? __ldg(p.perm + off + i) : i;
         float* dst = p.grad_feat + (int64_t)gb * p.g_sb + (int64_t)gn * p.g_sn + (int64_t)c0 * p.g_sd;
         if (p.g_sd == 1 && ((p.g_sn | p.g_sb) & 3) == 0 &&
             (reinterpret_cast<uintptr_t>(p.grad_feat) & 15) == 0) {  // rows contiguous and 16-byte aligned: vector stores
@@ -1031,13 +1287,24 @@ struct TcState {
   void* F;
   void* T;
   float* stats;
+  // rows sorted by label (fecl_rank_kernel): planes of B*N entries behind the statistics
+  int* rank;
+  int* perm;
+  int* cls_lo;
+  int* cls_hi;
+  float* ys;
+  float* rws;
 };
 constexpr size_t kHdrBytes = 1024;   // keeps the operand arrays 1024-B aligned relative to the state base
 inline int npad_of(int N) { return (N + 127) / 128 * 128; }
 inline int dpad_of(int D) { return (D + 63) / 64 * 64; }
 size_t operand_bytes(int B, int N, int D) { return align_up((size_t)B * npad_of(N) * dpad_of(D) * 2, 1024); }
-// kNumStats planes of row statistics + kMaxSplits planes each of P1's partial n_i and P2's partial A_i
-size_t stats_bytes(int B, int N) { return align_up((size_t)(kNumStats + 2 * kMaxSplits) * B * N * sizeof(float), 128); }
+// kNumStats planes of row statistics + kMaxSplits planes each of P1's partial n_i and P2's partial A_i + the six
+// planes of the label sort
+constexpr int kSortPlanes = 6;
+size_t stats_bytes(int B, int N) {
+  return align_up((size_t)(kNumStats + 2 * kMaxSplits + kSortPlanes) * B * N * sizeof(float), 128);
+}
 TcState carve(void* state, int B, int N, int D, int has_teacher) {
   char* p = reinterpret_cast<char*>(state);
   TcState s;
@@ -1048,7 +1315,35 @@ TcState carve(void* state, int B, int N, int D, int has_teacher) {
   s.T = has_teacher ? p : nullptr;
   if (has_teacher) p += operand_bytes(B, N, D);
   s.stats = reinterpret_cast<float*>(p);
+  const size_t plane = (size_t)B * N;
+  int* sp = reinterpret_cast<int*>(s.stats + (size_t)(kNumStats + 2 * kMaxSplits) * plane);
+  s.rank = sp;
+  s.perm = sp + plane;
+  s.cls_lo = sp + 2 * plane;
+  s.cls_hi = sp + 3 * plane;
+  s.ys = reinterpret_cast<float*>(sp + 4 * plane);
+  s.rws = reinterpret_cast<float*>(sp + 5 * plane);
   return s;
+}
+
+// Rows are packed sorted by label unless the batch is merged (global negatives: the row statistics are exchanged
+// between ranks by merged row index) or the sample is too long for the rank kernel's shared memory.
+// DYCON_FECL_SORT=0 keeps the caller's row order, DYCON_FECL_CLASSES=0 sorts but runs the general pair arithmetic
+// on every sub-tile (both: A/B switches for measurements).
+constexpr int kMaxSortRows = 49152;
+bool sort_rows(int N, bool merged) {
+  static const bool off = [] {
+    const char* e = getenv("DYCON_FECL_SORT");
+    return e && e[0] == '0';
+  }();
+  return !off && !merged && N <= kMaxSortRows;
+}
+bool use_classes() {
+  static const bool off = [] {
+    const char* e = getenv("DYCON_FECL_CLASSES");
+    return e && e[0] == '0';
+  }();
+  return !off;
 }
 
 // The kernels treat zero-padded columns as "cs == 0 <= thresh": a negative threshold would turn them into hard
@@ -1157,8 +1452,37 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
     return e && e[0] == '1';
   }();
   pk.pdl = no_pdl ? 0 : 1;
+  const bool sorted = sort_rows(N, a.merge_B > 0);
+  pk.rank = sorted ? s.rank : nullptr;
+  cudaLaunchAttribute pdl_attr[1];
+  pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
   dim3 pgrid(pk.Npad / 64, Dpad / 64, pk.B * (p.has_teacher ? 2 : 1));
-  if (a.phase_mask & 1) pack16_kernel<kBf16><<<pgrid, 256, 0, st>>>(pk);
+  if (a.phase_mask & 1) {
+    if (sorted) {
+      RankParams rp;
+      rp.labels = a.labels; rp.row_weight = a.row_weight; rp.N = N;
+      rp.rank = s.rank; rp.perm = s.perm; rp.cls_lo = s.cls_lo; rp.cls_hi = s.cls_hi; rp.ys = s.ys; rp.rws = s.rws;
+      rp.pdl = pk.pdl;
+      const size_t rsmem = (size_t)((N + 3) & ~3) * sizeof(uint32_t);
+      if (int rc = once_per_device([] {
+            DYCON_CUDA(cudaFuncSetAttribute(fecl_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            kMaxSortRows * (int)sizeof(uint32_t)));
+            return (int)DYCON_OK;
+          }))
+        return rc;
+      fecl_rank_kernel<<<dim3((N + 63) / 64, B), 256, rsmem, st>>>(rp);
+      DYCON_CUDA(cudaGetLastError());
+      count_launches(1);
+    }
+    cudaLaunchConfig_t pcfg = {};
+    pcfg.gridDim = pgrid;
+    pcfg.blockDim = dim3(256);
+    pcfg.stream = st;
+    pcfg.attrs = pdl_attr;
+    pcfg.numAttrs = (sorted && pk.pdl) ? 1 : 0;      // the pack kernel overlaps its loads with the rank kernel
+    DYCON_CUDA(cudaLaunchKernelEx(&pcfg, pack16_kernel<kBf16>, pk));
+  }
   // boxes: 128 rows (A tile), 64 rows (a sub-tile of F alone), 32 rows (F | T interleaved in teacher mode)
   CUtensorMap mapA, mapF64, mapF32, mapT32;
   if (int rc = make_tmap_16_2d(&mapA, s.F, (uint64_t)B * Npad, Dpad, 128, kBf16)) return rc;
@@ -1188,7 +1512,11 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   sp.inv_rows_d = p.inv_rows;
   sp.hscale = pick_hscale(p.inv_rows, p.sc.inv_tau);
   sp.hdr = s.hdr;
-  sp.labels = a.labels; sp.row_weight = a.row_weight;
+  sp.labels = sorted ? s.ys : a.labels;
+  sp.row_weight = a.row_weight ? (sorted ? s.rws : a.row_weight) : nullptr;
+  sp.cls_lo = sorted ? s.cls_lo : nullptr;
+  sp.cls_hi = sorted ? s.cls_hi : nullptr;
+  sp.use_classes = sorted && use_classes();
   sp.stat_m = s.stats + kStatM * plane; sp.stat_n = s.stats + kStatN * plane;
   sp.stat_kappa = s.stats + kStatKappa * plane;
   sp.stat_p = s.stats + kStatP * plane;
@@ -1209,9 +1537,6 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   DYCON_REQUIRE(smem <= 227 * 1024, DYCON_ERR_UNSUPPORTED, "FeCL tensor-core fwd: %zu bytes of shared memory needed", smem);
   dim3 grid(rb01, splits01, B);
   const CUtensorMap& mapF2 = p.has_teacher ? mapF32 : mapF64;      // mode 2 walks 32-column sub-tiles with a teacher
-  cudaLaunchAttribute pdl_attr[1];
-  pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kSwThreads);
@@ -1263,7 +1588,12 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
   bp.rb_lo = rb_lo; bp.row_lo = row_lo; bp.row_hi = row_hi; bp.grad_rows = a.grad_rows;
   bp.sc = p.sc;
   bp.c1 = p.sc.inv_tau * kLog2e;
-  bp.labels = a.labels;
+  const bool sorted = sort_rows(N, a.grad_rows > 0);
+  bp.labels = sorted ? s.ys : a.labels;
+  bp.cls_lo = sorted ? s.cls_lo : nullptr;
+  bp.cls_hi = sorted ? s.cls_hi : nullptr;
+  bp.perm = sorted ? s.perm : nullptr;
+  bp.use_classes = sorted && use_classes();
   bp.stat_m = s.stats + kStatM * plane; bp.stat_n = s.stats + kStatN * plane;
   bp.apart = s.stats + (size_t)(kNumStats + kMaxSplits) * plane;
   bp.stat_kappa = s.stats + kStatKappa * plane;

@@ -32,7 +32,7 @@ import torch.nn as nn
 from . import _lib, sharded
 
 __all__ = ["UnCLoss", "FeCLoss", "adaptive_beta", "sigmoid_rampup", "gambling_softmax",
-           "update_ema_variables"]
+           "update_ema_variables", "StepLosses", "sgd_clip_ema_step", "loss_is_finite_flag"]
 
 
 # =========================================================================== host scalars
@@ -224,6 +224,98 @@ class UnCLoss(nn.Module):
         if torch.is_tensor(beta):
             beta = float(beta)
         return _UnCLFunction.apply(s_logits, t_logits, beta, self.process_group, self.global_batch)
+
+
+# =========================================================================== fused step losses
+class _StepLossesFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, s_logits, t_logits, labels, labeled_bs, beta):
+        dev = s_logits.device
+        s = s_logits.contiguous()
+        t = t_logits.detach().contiguous()
+        B, Cn = s.shape[0], s.shape[1]
+        V = s[0, 0].numel()
+        with torch.cuda.device(dev):
+            _lib.require_b200(dev.index)
+            L = _lib.lib()
+            ws = _workspace(dev, "segcons", L.dycon_segcons_workspace_bytes())
+            sums = torch.empty(6, dtype=torch.float64, device=dev)
+            out = torch.empty(4, dtype=torch.float32, device=dev)
+            t0 = _tick()
+            _lib.check(L.dycon_segcons_fwd(_ptr(s), _ptr(t), _ptr(labels), B, labeled_bs, Cn, V, float(beta), _ptr(sums),
+                                           _ptr(out), _ptr(ws), ws.numel(), _stream_ptr(dev)), "dycon_segcons_fwd")
+            _tock("segcons_fwd", t0)
+        ctx.save_for_backward(s, t, sums) if labels is None else ctx.save_for_backward(s, t, sums, labels)
+        ctx.cfg = (B, Cn, V, labeled_bs, float(beta), labels is not None)
+        ctx.shape = s_logits.shape
+        return out[0], out[1], out[2], out[3]
+
+    @staticmethod
+    def backward(ctx, g_u, g_ce, g_dice, g_cons):
+        B, Cn, V, labeled_bs, beta, has_labels = ctx.cfg
+        saved = ctx.saved_tensors
+        s, t, sums = saved[0], saved[1], saved[2]
+        labels = saved[3] if has_labels else None
+        dev = s.device
+        go = torch.stack([g.reshape(()).to(torch.float32) for g in (g_u, g_ce, g_dice, g_cons)]).contiguous()
+        grad = torch.empty(ctx.shape, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            t0 = _tick()
+            _lib.check(_lib.lib().dycon_segcons_bwd(_ptr(s), _ptr(t), _ptr(labels), B, labeled_bs, Cn, V, beta, _ptr(sums),
+                                                    _ptr(go), _ptr(grad), _stream_ptr(dev)), "dycon_segcons_bwd")
+            _tock("segcons_bwd", t0)
+        return grad, None, None, None, None
+
+
+class StepLosses(nn.Module):
+    """The four voxel-wise losses of the reference step loop from ONE pass over the logits (an optional entry point
+    beside the unchanged ``UnCLoss``; reference: train_DyCON_BraTS19.py:308-314,351-352 with utils/losses.py:8-16,65-82):
+
+        u_loss, loss_seg, loss_seg_dice, consistency_loss = StepLosses()(stud_logits, ema_logits, label_batch, labeled_bs, beta)
+
+    equal to ``uncl_criterion(stud_logits, ema_logits, beta)``, ``F.cross_entropy(stud_logits[:lb], label_batch[:lb])``,
+    ``losses.dice_loss(stud_probs[:lb, 1], label_batch[:lb] == 1)`` and
+    ``losses.softmax_mse_loss(stud_probs[lb:], ema_probs[lb:]).mean()`` (the reference passes probabilities to a
+    function that takes the softmax again; reproduced).  Gradients flow to ``stud_logits`` only.  Two classes run in
+    the fused kernel pair; any other class count composes the UnCL kernels with the stock PyTorch ops."""
+
+    def forward(self, stud_logits, ema_logits, label_batch, labeled_bs, beta):
+        _require_cuda_fp32("stud_logits", stud_logits)
+        _require_cuda_fp32("ema_logits", ema_logits)
+        if stud_logits.shape != ema_logits.shape or stud_logits.dim() < 3:
+            raise ValueError("StepLosses expects equal (B, C, spatial...) logits")
+        if torch.is_tensor(ema_logits) and ema_logits.requires_grad and torch.is_grad_enabled():
+            raise RuntimeError("StepLosses: ema_logits requires grad; the teacher branch is a constant in DyCON")
+        B = stud_logits.shape[0]
+        labeled_bs = int(labeled_bs)
+        if not 0 <= labeled_bs <= B:
+            raise ValueError(f"labeled_bs={labeled_bs} outside [0, {B}]")
+        if torch.is_tensor(beta):
+            beta = float(beta)
+        labels = None
+        if labeled_bs > 0:
+            if not torch.is_tensor(label_batch) or not label_batch.is_cuda:
+                raise RuntimeError("label_batch must be a CUDA tensor (no CPU fallback)")
+            if label_batch.dtype != torch.int64:
+                raise TypeError(f"label_batch must be int64 class indices like F.cross_entropy's target (got {label_batch.dtype})")
+            if tuple(label_batch.shape[1:]) != tuple(stud_logits.shape[2:]) or label_batch.shape[0] < labeled_bs:
+                raise ValueError("label_batch must be (>= labeled_bs, spatial...) matching the logits")
+            labels = label_batch[:labeled_bs].contiguous()
+        if stud_logits.shape[1] == 2:
+            return _StepLossesFunction.apply(stud_logits, ema_logits, labels, labeled_bs, beta)
+        # C != 2: the UnCL kernels + the stock terms as PyTorch ops (they stay on PyTorch in the reference design)
+        import torch.nn.functional as F
+        u = _UnCLFunction.apply(stud_logits, ema_logits, beta, None, None)
+        ps, pt = F.softmax(stud_logits, dim=1), F.softmax(ema_logits.detach(), dim=1)
+        zero = stud_logits.new_zeros(())
+        ce = F.cross_entropy(stud_logits[:labeled_bs], labels) if labeled_bs > 0 else zero
+        if labeled_bs > 0:
+            score, target = ps[:labeled_bs, 1], (labels == 1).float()
+            dice = 1 - (2 * (score * target).sum() + 1e-5) / ((score * score).sum() + (target * target).sum() + 1e-5)
+        else:
+            dice = zero + 1 - 1e-5 / 1e-5
+        cons = ((F.softmax(ps[labeled_bs:], dim=1) - F.softmax(pt[labeled_bs:], dim=1)) ** 2).mean() if labeled_bs < B else zero
+        return u, ce, dice, cons
 
 
 # =========================================================================== FeCL
@@ -511,3 +603,122 @@ def update_ema_variables(model, ema_model, alpha, global_step):
         _lib.check(_lib.lib().dycon_ema_multi(e_arr, p_arr, c_arr, n, float(alpha), float(1 - alpha),
                                               _stream_ptr(dev)), "dycon_ema_multi")
         _tock("ema", t0)
+
+
+# =========================================================================== clip + SGD + EMA, finite flag (8 f3/f4)
+def loss_is_finite_flag(*losses, counter=None):
+    """Device-side replacement of ``if torch.isnan(loss) or torch.isinf(loss): continue``
+    (train_DyCON_BraTS19.py:360-362): returns an int32 device tensor that is 1 when any of the given 0-dim fp32
+    CUDA tensors is NaN / +-inf -- no ``.item()``, no host synchronisation.  Hand it to ``sgd_clip_ema_step`` as
+    ``skip_flag``: a raised flag turns the whole update into a no-op, which is what the reference's ``continue``
+    does.  ``counter`` (int64 device tensor of one element, optional) counts the skipped steps for later logging."""
+    import ctypes
+    if not 1 <= len(losses) <= 16:
+        raise ValueError("1..16 loss scalars")
+    vals = []
+    for x in losses:
+        _require_cuda_fp32("loss", x)
+        if x.numel() != 1:
+            raise ValueError("loss_is_finite_flag takes 0-dim / one-element tensors")
+        vals.append(x.detach().reshape(1).contiguous())
+    dev = vals[0].device
+    flag = torch.empty(1, dtype=torch.int32, device=dev)
+    table = (ctypes.c_void_p * len(vals))(*[v.data_ptr() for v in vals])
+    with torch.cuda.device(dev):
+        _lib.require_b200(dev.index)
+        _lib.check(_lib.lib().dycon_finite_check(table, len(vals), _ptr(flag), _ptr(counter), _stream_ptr(dev)),
+                   "dycon_finite_check")
+    flag._dycon_keepalive = vals          # the kernel reads them asynchronously
+    return flag
+
+
+def sgd_clip_ema_step(optimizer, model, ema_model, max_norm, ema_decay, global_step, *, skip_flag=None,
+                      scale_grads=False):
+    """``clip_grad_norm_(params, max_norm); optimizer.step(); update_ema_variables(model, ema_model, ema_decay,
+    global_step)`` (train_DyCON_BraTS19.py:366-372) as TWO multi-tensor launches: the gradient norm, then one pass
+    that reads every parameter, gradient, momentum buffer and teacher tensor once.
+
+    ``optimizer`` must be a ``torch.optim.SGD`` (dampening 0, not maximize); its hyper-parameters are read from
+    ``param_groups`` every call (the scripts change ``lr`` per iteration) and its momentum buffers live in
+    ``optimizer.state[p]['momentum_buffer']`` exactly as after ``optimizer.step()``, so ``state_dict()`` stays
+    interchangeable.  ``ema_model`` may be None (no teacher).  Returns the total gradient norm (0-dim device
+    tensor, like ``clip_grad_norm_``).  ``skip_flag``: see ``loss_is_finite_flag``.  ``scale_grads=True`` also leaves
+    the clipped values in ``.grad`` as ``clip_grad_norm_`` does (the scripts zero them right after)."""
+    import ctypes
+    if not isinstance(optimizer, torch.optim.SGD):
+        raise TypeError("sgd_clip_ema_step drives torch.optim.SGD (the reference's optimizer)")
+    alpha = min(1 - 1 / (global_step + 1), ema_decay)
+    src = model.module if hasattr(model, "module") else model
+    ema_of = {}
+    if ema_model is not None:
+        dst = ema_model.module if hasattr(ema_model, "module") else ema_model
+        for e, p in zip(dst.parameters(), src.parameters()):       # zip() semantics of the reference loop
+            ema_of[id(p)] = e
+    seen = set()
+    groups = []
+    dev = None
+    for group in optimizer.param_groups:
+        if group.get("dampening", 0) != 0 or group.get("maximize", False):
+            raise ValueError("sgd_clip_ema_step: dampening / maximize are not supported (the reference uses neither)")
+        ps, gs, bs, es, first = [], [], [], [], None
+        for p in group["params"]:
+            seen.add(id(p))
+            _require_cuda_fp32("parameter", p.data)
+            dev = dev or p.device
+            if p.device != dev:
+                raise RuntimeError("sgd_clip_ema_step: parameters span several devices")
+            g = p.grad
+            if g is not None:
+                _require_cuda_fp32("gradient", g)
+                if g.is_sparse or not _dense_like(g, p.data):
+                    raise RuntimeError("sgd_clip_ema_step: gradients must be dense with the parameter's strides")
+            buf = None
+            if g is not None and group["momentum"] != 0:
+                st = optimizer.state[p]
+                buf = st.get("momentum_buffer")
+                is_first = buf is None
+                if is_first:
+                    buf = st["momentum_buffer"] = torch.empty_like(p.data)
+                if first is None:
+                    first = is_first
+                elif first != is_first:
+                    raise RuntimeError("sgd_clip_ema_step: a group mixes fresh and initialised momentum buffers")
+            e = ema_of.get(id(p))
+            if e is not None:
+                _require_cuda_fp32("ema parameter", e.data)
+                if not _dense_like(e.data, p.data):
+                    raise RuntimeError("sgd_clip_ema_step: student/teacher parameters must be dense with equal strides")
+            ps.append(p.data); gs.append(g); bs.append(buf); es.append(None if e is None else e.data)
+        groups.append((group, ps, gs, bs, es, bool(first)))
+    # teacher tensors whose student parameter is not in the optimizer still follow it (plain EMA)
+    rest = [(p, ema_of[id(p)]) for p in src.parameters() if id(p) in ema_of and id(p) not in seen]
+    if dev is None:
+        return torch.zeros(())
+    tab = lambda xs: (ctypes.c_void_p * len(xs))(*[None if x is None else x.data_ptr() for x in xs])
+    with torch.cuda.device(dev):
+        _lib.require_b200(dev.index)
+        L = _lib.lib()
+        all_g = [g for _, _, gs, _, _, _ in groups for g in gs if g is not None]
+        clip = torch.empty(2, dtype=torch.float32, device=dev)
+        ws = _workspace(dev, "gradnorm", L.dycon_grad_norm_workspace_bytes())
+        t0 = _tick()
+        counts = (ctypes.c_int64 * max(len(all_g), 1))(*[g.numel() for g in all_g])
+        _lib.check(L.dycon_grad_norm(tab(all_g), counts, len(all_g), float(max_norm if max_norm is not None else 0.0),
+                                     _ptr(clip), _ptr(ws), ws.numel(), _stream_ptr(dev)), "dycon_grad_norm")
+        for group, ps, gs, bs, es, first in groups:
+            if not ps:
+                continue
+            n = (ctypes.c_int64 * len(ps))(*[p.numel() for p in ps])
+            _lib.check(L.dycon_sgd_ema_step(tab(ps), tab(gs), tab(bs), tab(es), n, len(ps), float(group["lr"]),
+                                            float(group["momentum"]), float(group["weight_decay"]),
+                                            int(bool(group.get("nesterov", False))), int(first), float(alpha),
+                                            float(1 - alpha), _ptr(clip), _ptr(skip_flag), int(bool(scale_grads)),
+                                            _stream_ptr(dev)), "dycon_sgd_ema_step")
+        if rest:
+            ps, es = [p.data for p, _ in rest], [e.data for _, e in rest]
+            n = (ctypes.c_int64 * len(ps))(*[p.numel() for p in ps])
+            _lib.check(L.dycon_sgd_ema_step(tab(ps), None, None, tab(es), n, len(ps), 0.0, 0.0, 0.0, 0, 0, float(alpha),
+                                            float(1 - alpha), None, _ptr(skip_flag), 0, _stream_ptr(dev)),
+                       "dycon_sgd_ema_step")
+        _tock("sgd_ema_step", t0)
+    return clip[0]

@@ -163,6 +163,54 @@ int dycon_fecl_gn_bwd(const void* state, size_t state_bytes, const float* labels
 int dycon_ema_multi(float* const* ema_ptrs, const float* const* param_ptrs, const int64_t* numels,
                     int n_tensors, float alpha, float one_minus_alpha, dycon_stream_t stream);
 
+/* ------------------------------------------------------------------ fused step losses (two classes)
+ * The four voxel-wise losses the step loop computes from the same logits (code/train_DyCON_BraTS19.py:308-314,
+ * 351-352), from ONE pass over s, t (B, 2, V) and the int64 labels of the first labeled_bs samples (labeled_bs, V):
+ *   losses_out[0] = UnCLoss(s, t, beta)                                       code/utils/dycon_losses.py:94-118
+ *   losses_out[1] = F.cross_entropy(s[:lb], label[:lb])                       (label == 1 -> class 1, else class 0)
+ *   losses_out[2] = dice_loss(softmax(s)[:lb, 1], label[:lb] == 1)            code/utils/losses.py:8-16
+ *   losses_out[3] = softmax_mse_loss(softmax(s)[lb:], softmax(t)[lb:]).mean() code/utils/losses.py:65-82 (the
+ *                   reference hands it probabilities, so it is a softmax of a softmax: kept)
+ * sums_out: 6 doubles {uncl, ce, dice intersect, dice z, dice y, consistency} kept for the backward.
+ * dycon_segcons_bwd: grad_s (B, 2, V) = d(sum_k grad_out4[k] * losses_out[k]) / ds, grad_out4 = 4 floats on the
+ * device.  C must be 2 (DYCON_ERR_UNSUPPORTED otherwise: compose the unfused entry points).
+ */
+size_t dycon_segcons_workspace_bytes(void);
+int dycon_segcons_fwd(const float* s, const float* t, const long long* label, int B, int labeled_bs, int C, int64_t V,
+                      float beta, double* sums_out, float* losses_out, void* workspace, size_t workspace_bytes,
+                      dycon_stream_t stream);
+int dycon_segcons_bwd(const float* s, const float* t, const long long* label, int B, int labeled_bs, int C, int64_t V,
+                      float beta, const double* sums, const float* grad_out4, float* grad_s, dycon_stream_t stream);
+
+/* ------------------------------------------------------------------ clip + SGD + EMA, finite check
+ * Replaces, with two launches over ALL parameter tensors, the per-tensor launches of
+ *   torch.nn.utils.clip_grad_norm_(params, max_norm); optimizer.step()  [torch.optim.SGD: lr, momentum,
+ *   weight_decay, nesterov; dampening 0]; update_ema_variables(model, ema_model, ema_decay, iter_num)
+ * (code/train_DyCON_BraTS19.py:268,366-372) and, through skip_flag, the host-side
+ *   if torch.isnan(loss) or torch.isinf(loss): continue                                   (:360-362).
+ * All pointer tables are HOST arrays of n_tensors entries (copied into the kernel parameters: graph capturable).
+ * dycon_grad_norm: out2 = {||g||_2 over all tensors, min(1, max_norm / (norm + 1e-6))} on the device (max_norm <= 0:
+ *   coefficient 1); NULL gradient entries are skipped; at most 160 tensors.
+ * dycon_sgd_ema_step, per element, with the rounding order of the PyTorch ops:
+ *   g' = rn(g * clip2[1]); g' = fma(wd, p, g'); buf = first_step ? g' : rn(rn(buf * momentum) + g');
+ *   p = fma(-lr, nesterov ? fma(momentum, buf, g') : buf, p); ema = fma(one_minus_alpha, p, rn(ema * alpha)).
+ *   grad_ptrs[k] == NULL: the parameter is not stepped (its teacher copy still follows it); ema_ptrs == NULL or
+ *   ema_ptrs[k] == NULL: no teacher copy; clip2 == NULL: coefficient 1; scale_grads: also write g' = g * coefficient
+ *   back (what clip_grad_norm_ leaves in .grad); skip_flag (1 int on the device, may be NULL) != 0: nothing is
+ *   written at all.
+ * dycon_finite_check: flag_out = 1 if any of the n <= 16 device scalars is NaN / +-inf, else 0; skipped_count
+ *   (device uint64, may be NULL) is incremented when the flag is raised.
+ */
+size_t dycon_grad_norm_workspace_bytes(void);
+int dycon_grad_norm(const float* const* grad_ptrs, const int64_t* numels, int n_tensors, float max_norm, float* out2,
+                    void* workspace, size_t workspace_bytes, dycon_stream_t stream);
+int dycon_sgd_ema_step(float* const* param_ptrs, const float* const* grad_ptrs, float* const* buf_ptrs,
+                       float* const* ema_ptrs, const int64_t* numels, int n_tensors, float lr, float momentum,
+                       float weight_decay, int nesterov, int first_step, float alpha, float one_minus_alpha,
+                       const float* clip2, const int* skip_flag, int scale_grads, dycon_stream_t stream);
+int dycon_finite_check(const float* const* value_ptrs, int n, int* flag_out, unsigned long long* skipped_count,
+                       dycon_stream_t stream);
+
 /* ------------------------------------------------------------------ sharded batches
  * The path shards over ranks along the batch; the only exchange is the all-reduce of the partial sums above
  * (dycon_uncl_fwd: sum_out; dycon_fecl_fwd: sums_out; the reference has no multi-process mode, its

@@ -173,13 +173,15 @@ def fecl_grad_error(grad, ref, teacher, max_per_row=14):
 
 def fecl_blocked(feat, mask, teacher=None, row_weight=None, *, inv_tau, gamma=2.0, use_focal=False,
                  cross_thresh=0.5, lambda_cross=1.0, go=1.0, rows_global=None, cnt_global=None, block=1024,
-                 grad_rows=None):
+                 grad_rows=None, ambiguity=0.0):
     """The same value and gradient as ``fecl`` for ONE sample (feat (N,D) or (1,N,D)) without ever holding an
     (N,N) array: four sweeps over row blocks (row max; negative sums; loss and A; gradient), the transposed
     gradient term G_ji evaluated from the per-row statistics of row j -- the structure the kernels use.  For
     shapes where ``fecl`` does not fit (ISLES22 N=9216, merged batches of config 5).  ``grad_rows`` = (lo, hi)
     restricts the gradient sweep to those rows (the loss always covers all rows).  float64 throughout, on torch
-    CPU tensors so that the element-wise passes use all host cores.  dycon_losses.py:150-235."""
+    CPU tensors so that the element-wise passes use all host cores.  ``ambiguity`` > 0 also returns what
+    ``fecl_grad_error_strict`` needs (boundary pairs, un-normalised cross sums, the student part), shaped for a
+    batch of one.  dycon_losses.py:150-235."""
     import torch
     f = torch.as_tensor(np.asarray(feat, np.float64)).reshape(-1, np.asarray(feat).shape[-1])
     n = f.shape[0]
@@ -241,6 +243,9 @@ def fecl_blocked(feat, mask, teacher=None, row_weight=None, *, inv_tau, gamma=2.
 
     lo, hi = grad_rows if grad_rows is not None else (0, n)
     grad = torch.zeros((hi - lo, f.shape[1]), dtype=torch.float64)
+    grad_student = torch.zeros_like(grad) if ambiguity > 0 else None
+    cross_unnorm = torch.zeros_like(grad) if (ambiguity > 0 and tf is not None) else None
+    ambiguous = []
     zero = torch.zeros((), dtype=torch.float64)
     for a, b in [(max(a, lo), min(b, hi)) for a, b in blocks if min(b, hi) > max(a, lo)]:
         pos, pm, e, tt, d, dphi = pair_terms(a, b)
@@ -254,14 +259,26 @@ def fecl_blocked(feat, mask, teacher=None, row_weight=None, *, inv_tau, gamma=2.
         h = (gij + gji) * inv_tau
         h[idx[a:b] - a, idx[a:b]] = 0.0
         g = h @ f
+        if grad_student is not None:
+            grad_student[a - lo:b - lo] = g
         if tf is not None:
             cs = f[a:b] @ tf.T
             hard = ~pos & (cs > cross_thresh)
             gc = torch.where(hard, 1.0 / ((1.0 - cs + EPS_FECL) * (cg + EPS_FECL)), zero)
             g = g + lambda_cross * (gc @ tf)
+            if cross_unnorm is not None:
+                cross_unnorm[a - lo:b - lo] = torch.where(hard, 1.0 / (1.0 - cs + EPS_FECL), zero) @ tf
+                near = ~pos & ((cs - cross_thresh).abs() <= ambiguity)
+                for ii, jj in zip(*torch.nonzero(near, as_tuple=True)):
+                    ambiguous.append((0, int(ii) + a - lo, int(jj), float(cs[ii, jj]), bool(hard[ii, jj])))
         grad[a - lo:b - lo] = g
-    return {"loss": loss, "grad": (go * grad).numpy(), "m": m.numpy(), "n": nsum.numpy(), "A": amat.numpy(),
-            "kappa": kappa.numpy(), "student_sum": student_sum, "cross_sum": cross_sum, "cnt": cnt}
+    out = {"loss": loss, "grad": (go * grad).numpy(), "m": m.numpy(), "n": nsum.numpy(), "A": amat.numpy(),
+           "kappa": kappa.numpy(), "student_sum": student_sum, "cross_sum": cross_sum, "cnt": cnt}
+    if ambiguity > 0:
+        out.update(grad=out["grad"][None], grad_student=(go * grad_student).numpy()[None],
+                   cross_unnorm=None if cross_unnorm is None else cross_unnorm.numpy()[None], ambiguous=ambiguous,
+                   go=go, lambda_cross=lambda_cross, labels=y.numpy()[None, lo:hi])
+    return out
 
 
 def round_operand(x, mode):

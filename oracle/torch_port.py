@@ -128,3 +128,30 @@ def fecl_fwd_bwd(feat, mask, teacher=None, unc=None, epoch=0, go=1.0, dtype=None
                      None if unc is None else unc.to(dt), epoch, **kw)
     (loss * go).backward()
     return loss.detach(), f.grad.detach()
+
+
+# --------------------------------------------------------------------------- stock step-loop losses
+def dice_loss(score, target):
+    """Soft Dice on one class (code/utils/losses.py:8-16)."""
+    target = target.to(score.dtype)
+    smooth = 1e-5
+    inter = torch.sum(score * target)
+    return 1 - (2 * inter + smooth) / (torch.sum(score * score) + torch.sum(target * target) + smooth)
+
+
+def softmax_mse(input_logits, target_logits):
+    """Element-wise squared difference of the two softmaxes over dim 1 (code/utils/losses.py:65-82)."""
+    return (torch.softmax(input_logits, dim=1) - torch.softmax(target_logits, dim=1)) ** 2
+
+
+def step_losses(stud_logits, ema_logits, label_batch, labeled_bs, beta):
+    """The four voxel-wise losses of one step, as the loop computes them (code/train_DyCON_BraTS19.py:308-314,
+    351-352): (u_loss, loss_seg, loss_seg_dice, consistency_loss).  The consistency term is handed the
+    PROBABILITIES (:352), so softmax_mse takes the softmax of a softmax -- restated as is."""
+    stud_probs = torch.softmax(stud_logits, dim=1)                             # :308
+    ema_probs = torch.softmax(ema_logits, dim=1)                               # :309
+    loss_seg = torch.nn.functional.cross_entropy(stud_logits[:labeled_bs], label_batch[:labeled_bs])          # :313
+    loss_seg_dice = dice_loss(stud_probs[:labeled_bs, 1], label_batch[:labeled_bs] == 1)                      # :314
+    u_loss = uncl_loss(stud_logits, ema_logits, beta)                          # :351
+    consistency = softmax_mse(stud_probs[labeled_bs:], ema_probs[labeled_bs:]).mean()                         # :352
+    return u_loss, loss_seg, loss_seg_dice, consistency

@@ -111,19 +111,23 @@ def main():
     fecl = FeCLoss(dev, process_group=g, global_batch=B, **ctor)
     uncl = UnCLoss(process_group=g, global_batch=B)
     mk, tk, tl = inp.mask[lo:hi].to(dev), inp.teacher[lo:hi].to(dev), inp.t_logits[lo:hi].to(dev)
+    # fresh leaves whose first backward runs on the side stream (an AccumulateGrad node bound to the legacy
+    # stream cannot be captured)
+    fg = inp.feat[lo:hi].to(dev).requires_grad_(True)
+    sg = inp.s_logits[lo:hi].to(dev).requires_grad_(True)
 
     def sharded_step():
-        f.grad = s.grad = None
-        fl = fecl(f, mk, tk, None, 100)
-        ul = uncl(s, tl, 1.58)
+        fg.grad = sg.grad = None
+        fl = fecl(fg, mk, tk, None, 100)
+        ul = uncl(sg, tl, 1.58)
         (0.5 * (fl + ul)).backward()
         return fl, ul
 
-    fl, ul = sharded_step()
-    want = (fl.item(), ul.item(), f.grad.clone(), s.grad.clone())
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
+        fl, ul = sharded_step()
+        want = (fl.item(), ul.item(), fg.grad.clone(), sg.grad.clone())
         sharded_step()
     torch.cuda.current_stream().wait_stream(side)
     dist.barrier()
@@ -134,7 +138,7 @@ def main():
         graph.replay()
     torch.cuda.synchronize()
     assert gfl.item() == want[0] and gul.item() == want[1], (gfl.item(), want[0], gul.item(), want[1])
-    assert torch.equal(f.grad, want[2]) and torch.equal(s.grad, want[3])
+    assert torch.equal(fg.grad, want[2]) and torch.equal(sg.grad, want[3])
     ex = sharded._exchanges.get((id(g), dev.index))
     assert ex is None or not ex.timed_out()
 
