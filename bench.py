@@ -49,11 +49,18 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--train-step", action="store_true",
+                    help="BASELINE config 3: the full mean-teacher train step with the reference UNet3D as context "
+                         "(tools/train_step.py: reference vs drop-in vs fused arms, loss trajectories + step-time breakdown)")
     ap.add_argument("--profile-ranges", action="store_true",
                     help="only run the per-family launch loops, each inside a cudaProfilerStart/Stop range (for "
                          "`ncu --replay-mode range`: DRAM bytes per family including the write-backs); prints no bench line")
     ap.add_argument("--no-parity", action="store_true",
-                    help="N > 1: skip the multi-rank parity block (CPU oracle on the concatenated batch, rank 0)")
+                    help="N > 1: skip the multi-rank parity block (rank 0: the unsharded kernels and the CPU oracle on "
+                         "the concatenated batch)")
+    ap.add_argument("--no-parity-oracle", action="store_true",
+                    help="N > 1: keep the sharded-vs-unsharded check on the GPU but skip the fp64 CPU oracle (minutes of "
+                         "host time at the ISLES22 / merged-batch sizes, during which every GPU of the job idles)")
     ap.add_argument("--global-negatives", action="store_true",
                     help="BASELINE config 5: FeCL contrasts every row against the rows of all samples of all ranks")
     return ap.parse_args()
@@ -350,11 +357,13 @@ def multi_rank_parity(args, world, precision, seeds, loss_f, loss_u, grads_f, gr
         out["fecl_grad_rows_checked"] = list(rows)
         out["fecl_comparator"] = "plain max|dg|/max|g| (no flip tolerance)"
     else:
+        # (N x N arrays of the dense closed form do not fit comfortably at the ISLES22 size: row-blocked variant there)
+        fe = closed_form.fecl if N <= 4096 else (lambda f, m, t, u, **k: closed_form.fecl_blocked(f, m, t, u, block=1024, **k))
         per = []          # first pass: per-sample sums (the hard-negative count is batch-global, dycon_losses.py:229)
         for inp in inps:
             for b in range(Bl):
-                per.append(closed_form.fecl(inp.feat[b:b + 1].numpy(), inp.mask[b:b + 1].numpy(), inp.teacher[b:b + 1].numpy(),
-                                            None, rows_global=B_all * N, **kw))
+                per.append(fe(inp.feat[b:b + 1].numpy(), inp.mask[b:b + 1].numpy(), inp.teacher[b:b + 1].numpy(),
+                              None, rows_global=B_all * N, **(kw if N <= 4096 else dict(kw, grad_rows=(0, 0)))))
         student = sum(p["student_sum"] for p in per)
         cross, cnt = sum(p["cross_sum"] for p in per), sum(p["cnt"] for p in per)
         f_ref = student / (B_all * N) + cross / (cnt + 1e-18)
@@ -365,9 +374,9 @@ def multi_rank_parity(args, world, precision, seeds, loss_f, loss_u, grads_f, gr
         for r in check_ranks:             # second pass with the global count: this rank's gradient slice
             for b in range(Bl):
                 inp = inps[r]
-                refs[(r, b)] = closed_form.fecl(inp.feat[b:b + 1].numpy(), inp.mask[b:b + 1].numpy(),
-                                                inp.teacher[b:b + 1].numpy(), None, rows_global=B_all * N,
-                                                cnt_global=cnt, ambiguity=amb, **kw)
+                refs[(r, b)] = fe(inp.feat[b:b + 1].numpy(), inp.mask[b:b + 1].numpy(),
+                                  inp.teacher[b:b + 1].numpy(), None, rows_global=B_all * N,
+                                  cnt_global=cnt, ambiguity=amb, **kw)
                 gmax = max(gmax, float(np.abs(refs[(r, b)]["grad"]).max()))
         for (r, b), ref in refs.items():
             g = grads_f[check_ranks.index(r)][b:b + 1]
@@ -383,6 +392,36 @@ def multi_rank_parity(args, world, precision, seeds, loss_f, loss_u, grads_f, gr
     out["ok"] = bool(out["uncl_loss_rel_err"] <= 1e-5 and out["uncl_grad_err"] <= 1e-5 and
                      out["fecl_loss_rel_err"] <= tol_f and out["fecl_grad_err"] <= tol_f)
     out["oracle_seconds"] = time.time() - t_start
+    return out
+
+
+def unsharded_parity(args, world, precision, seeds, loss_f, loss_u, grads_f, grads_s, check_ranks, dev):
+    """Rank 0: the SAME kernels on the concatenated batch of all ranks in one process (no process group) against
+    what the sharded run returned.  The unsharded path is itself pinned to the oracle at every shape by tests/, so
+    this closes the chain cheaply where the CPU oracle would take minutes (ISLES22, merged batches)."""
+    import torch
+    from dycon_paper_replication_b200 import FeCLoss, UnCLoss
+    from dycon_paper_replication_b200.synthetic import make_inputs
+    inps = [make_inputs(args.shape, batch=args.batch, dim=args.dim, seed=sd).to(dev) for sd in seeds]
+    cat = lambda k: torch.cat([getattr(i, k) for i in inps])
+    Bl = args.batch
+    f = cat("feat").requires_grad_(True)
+    s = cat("s_logits").requires_grad_(True)
+    fecl = FeCLoss(dev, precision=precision, cross_gpu_negatives=args.global_negatives, **CTOR)
+    lf = fecl(feat=f, mask=cat("mask"), teacher_feat=cat("teacher"), gambling_uncertainty=None, epoch=EPOCH)
+    lu = UnCLoss()(s, cat("t_logits"), BETA)
+    (U_WEIGHT * (lf + lu)).backward()
+    torch.cuda.synchronize()
+    out = {"fecl_loss_rel_diff": abs(loss_f - float(lf)) / abs(float(lf)), "uncl_loss_rel_diff": abs(loss_u - float(lu)) / abs(float(lu))}
+    gf, gs = 0.0, 0.0
+    for k, r in enumerate(check_ranks):
+        a, b = f.grad[r * Bl:(r + 1) * Bl], torch.from_numpy(grads_f[k]).to(dev)
+        gf = max(gf, float((a - b).abs().max() / f.grad.abs().max()))
+        a, b = s.grad[r * Bl:(r + 1) * Bl], torch.from_numpy(grads_s[k]).to(dev)
+        gs = max(gs, float((a - b).abs().max() / s.grad.abs().max()))
+    out["fecl_grad_diff"], out["uncl_grad_diff"] = gf, gs
+    out["ok"] = bool(max(out.values()) <= 5e-6)
+    out["what"] = "sharded run vs the same kernels on the concatenated batch in one process (rank 0's GPU)"
     return out
 
 
@@ -816,9 +855,12 @@ def run_ours(args):
         line["e2e"] = e2e
     if parity is not None:
         seeds = [1337 + 101 * r for r in range(world)]
+        pargs = (args, world, precision, seeds, parity["loss_f"], parity["loss_u"], parity["gf"], parity["gs"], parity["check"])
         try:
-            line["parity"] = multi_rank_parity(args, world, precision, seeds, parity["loss_f"], parity["loss_u"],
-                                               parity["gf"], parity["gs"], parity["check"])
+            line["parity"] = {"unsharded": unsharded_parity(*pargs, dev)}
+            if not args.no_parity_oracle:
+                line["parity"].update(multi_rank_parity(*pargs))
+            line["parity"]["ok"] = bool(line["parity"]["unsharded"]["ok"] and line["parity"].get("ok", True))
         except Exception as err:           # never lose the bench line to the checker
             line["parity"] = {"ok": False, "error": f"{type(err).__name__}: {err}"}
     if n_gpus == 1 and not args.no_cpu_baseline:
@@ -853,6 +895,12 @@ def shutdown(world):
 
 if __name__ == "__main__":
     a = parse()
+    if a.train_step:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import train_step
+        shape = a.shape if a.shape != "brats19" else "pancreas"          # config 3 is quoted on the Pancreas shape
+        sys.exit(train_step.main(["--shape", shape, "--batch", str(a.batch if a.batch != 4 else 8),
+                                  "--steps", str(a.steps), "--timed", str(max(a.warmup, 10))]))
     if a.impl == "reference":
         run_reference(a)
     elif a.impl == "reference-eager-gpu":

@@ -10,7 +10,9 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "_dycon_b200.so")
+# DYCON_SO_VARIANT=timeline loads the measurement build (DYCON_TIMELINE=1 python -m ...csrc.build; tools/timeline.py)
+_VARIANT = os.environ.get("DYCON_SO_VARIANT", "")
+SO_PATH = os.path.join(_HERE, f"_dycon_b200_{_VARIANT}.so" if _VARIANT else "_dycon_b200.so")
 
 FECL_FP32 = 0
 FECL_BF16 = 1
@@ -18,6 +20,7 @@ FECL_FP16 = 2
 ABI_VERSION = 2
 EXCHANGE_NONE, EXCHANGE_UNCL, EXCHANGE_FECL, EXCHANGE_FECL_TEACHER = 0, 1, 2, 3
 EXCHANGE_CHANNELS = 3
+LABEL_INT64, LABEL_FLOAT32, LABEL_UINT8 = 0, 1, 2
 
 _lock = threading.Lock()
 _lib = None
@@ -43,6 +46,7 @@ PROTOTYPES = {
     "dycon_fecl_fwd": (_i, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, _p, _i, _i, _i,
                             _f, _f, _i, _f, _f, _d, _i, _p, _sz, _p, _p, _p, _sz, _p]),
     "dycon_fecl_bwd": (_i, [_p, _sz, _p, _i, _i, _i, _i, _f, _f, _i, _i, _f, _f, _i, _p, _p, _p, _i64, _i64, _i64, _p]),
+    "dycon_debug_timeline": (_sz, [_p, _sz]),
     "dycon_fecl_gn_state_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "dycon_fecl_gn_layout": (_i, [_i, _i, _i, _i, _i, _p]),
     "dycon_fecl_gn_fwd": (_i, [_i, _p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, _p, _i, _i, _i, _f, _f, _i, _f, _f,
@@ -52,6 +56,11 @@ PROTOTYPES = {
     "dycon_segcons_workspace_bytes": (_sz, []),
     "dycon_segcons_fwd": (_i, [_p, _p, _p, _i, _i, _i, _i64, _f, _p, _p, _p, _sz, _p]),
     "dycon_segcons_bwd": (_i, [_p, _p, _p, _i, _i, _i, _i64, _f, _p, _p, _p, _p]),
+    "dycon_pool_mask": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
+    "dycon_row_inv_norm": (_i, [_p, _i64, _i64, _i64, _i, _i, _i, _p, _p]),
+    "dycon_normalize_bwd": (_i, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, _i, _i, _i, _p, _i64, _i64, _i64, _p]),
+    "dycon_fecl_fwd_scaled": (_i, [_p, _i64, _i64, _i64, _p, _i64, _i64, _i64, _p, _p, _p, _p, _i, _i, _i,
+                                   _f, _f, _i, _f, _f, _d, _i, _p, _sz, _p, _p, _p, _sz, _p, _i, _i, _p, _d, _p]),
     "dycon_grad_norm_workspace_bytes": (_sz, []),
     "dycon_grad_norm": (_i, [_p, _p, _i, _f, _p, _p, _sz, _p]),
     "dycon_sgd_ema_step": (_i, [_p, _p, _p, _p, _p, _i, _f, _f, _f, _i, _i, _f, _f, _p, _p, _i, _p]),

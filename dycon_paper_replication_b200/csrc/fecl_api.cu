@@ -20,7 +20,8 @@ int fecl_fwd_checked(const float* feat, int64_t f_sb, int64_t f_sn, int64_t f_sd
                    int64_t t_sn, int64_t t_sd, const float* labels, const float* row_weight, int B, int N, int D,
                    float inv_tau, float gamma, int use_focal, float cross_thresh, float lambda_cross, double inv_rows,
                    int precision, void* state, size_t state_bytes, double* sums_out, float* loss_out, void* workspace,
-                   size_t workspace_bytes, const ExchangeCtx* xc, dycon_stream_t stream) {
+                   size_t workspace_bytes, const ExchangeCtx* xc, dycon_stream_t stream, const float* feat_scale = nullptr,
+                   const float* teacher_scale = nullptr) {
   if (int rc = check_shape(B, N, D, precision)) return rc;
   DYCON_REQUIRE(feat && labels && state && sums_out && workspace, DYCON_ERR_ARG,
                 "FeCL fwd: NULL feat/labels/state/sums_out/workspace");
@@ -39,6 +40,9 @@ int fecl_fwd_checked(const float* feat, int64_t f_sb, int64_t f_sn, int64_t f_sd
                 inv_rows, precision};
   FeclFwdArgs a{feat, f_sb, f_sn, f_sd, teacher, t_sb, t_sn, t_sd, labels, row_weight, state, sums_out, loss_out, workspace};
   a.xc = xc;
+  DYCON_REQUIRE(aligned(feat_scale, 4) && aligned(teacher_scale, 4), DYCON_ERR_ARG, "FeCL fwd: misaligned row scale");
+  a.feat_scale = feat_scale;
+  a.teacher_scale = teacher ? teacher_scale : nullptr;
   return precision != DYCON_FECL_FP32 ? fecl_tc_fwd(p, a, as_stream(stream)) : fecl_simt_fwd(p, a, as_stream(stream));
 }
 
@@ -107,6 +111,30 @@ int dycon_fecl_bwd(const void* state, size_t state_bytes, const float* labels, i
   FeclBwdArgs a{state, labels, cross_cnt, grad_out, grad_feat, g_sb, g_sn, g_sd};
   return precision != DYCON_FECL_FP32 ? fecl_tc_bwd(p, a, as_stream(stream)) : fecl_simt_bwd(p, a, as_stream(stream));
 }
+
+int dycon_fecl_fwd_scaled(const float* feat, int64_t f_sb, int64_t f_sn, int64_t f_sd, const float* teacher, int64_t t_sb,
+                          int64_t t_sn, int64_t t_sd, const float* feat_row_scale, const float* teacher_row_scale,
+                          const float* labels, const float* row_weight, int B, int N, int D, float inv_tau, float gamma,
+                          int use_focal, float cross_thresh, float lambda_cross, double inv_rows, int precision, void* state,
+                          size_t state_bytes, double* sums_out, float* loss_out, void* workspace, size_t workspace_bytes,
+                          void* const* peer_inboxes, int rank, int world, unsigned long long* seq_counters,
+                          double timeout_s, dycon_stream_t stream) {
+  ExchangeCtx xc;
+  if (int rc = make_exchange_ctx(&xc, peer_inboxes, rank, world, seq_counters, DYCON_CHANNEL_FECL, timeout_s)) return rc;
+  const bool fused = xc.world > 1 && precision != DYCON_FECL_FP32;
+  if (int rc = fecl_fwd_checked(feat, f_sb, f_sn, f_sd, teacher, t_sb, t_sn, t_sd, labels, row_weight, B, N, D, inv_tau,
+                                gamma, use_focal, cross_thresh, lambda_cross, inv_rows, precision, state, state_bytes,
+                                sums_out, (xc.world > 1 && !fused) ? nullptr : loss_out, workspace, workspace_bytes,
+                                fused ? &xc : nullptr, stream, feat_row_scale, teacher_row_scale))
+    return rc;
+  if (xc.world > 1 && !fused)
+    return dycon_exchange_sums(sums_out, 3, sums_out, peer_inboxes, rank, world, seq_counters,
+                               teacher ? DYCON_EXCHANGE_FECL_TEACHER : DYCON_EXCHANGE_FECL, inv_rows, lambda_cross, loss_out,
+                               timeout_s, stream);
+  return DYCON_OK;
+}
+
+size_t dycon_debug_timeline(void* host_out, size_t bytes) { return fecl_tc_debug_timeline(host_out, bytes); }
 
 // ---- global negatives: the merged batch as ONE sample, rows split over ranks (include/dycon_b200.h) -------
 size_t dycon_fecl_gn_state_bytes(int B_all, int N, int D, int has_teacher, int precision) {

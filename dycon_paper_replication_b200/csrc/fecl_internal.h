@@ -34,6 +34,9 @@ struct FeclFwdArgs {
   int phase_mask = 15;
   int row_lo = 0, row_hi = -1;
   const ExchangeCtx* xc = nullptr;   // sharded batch: exchange the three sums in the tail of the loss sweep
+  // F.normalize folded into the operand staging: per-row factors (B*N floats each, or nullptr) applied to feat / teacher
+  const float* feat_scale = nullptr;
+  const float* teacher_scale = nullptr;
 };
 
 struct FeclBwdArgs {
@@ -66,5 +69,6 @@ int fecl_tc_fwd(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st);
 int fecl_tc_bwd(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st);
 // byte offsets inside the tensor-core state: {hdr, m, n, kappa, A partial plane 0, plane stride}
 void fecl_tc_layout(int B, int N, int D, int has_teacher, size_t out[6]);
+size_t fecl_tc_debug_timeline(void* host_out, size_t bytes);
 
 }  // namespace dycon

@@ -88,7 +88,7 @@ __device__ __forceinline__ float row_max16(float v) {
 // ---- pack: (B,N,D) with element strides -> contiguous [B][N][D] -------------------------------
 __global__ void __launch_bounds__(256)
 pack_rows_kernel(const float* __restrict__ src, int64_t sb, int64_t sn, int64_t sd, int N, int D,
-                 float* __restrict__ dst) {
+                 float* __restrict__ dst, const float* __restrict__ row_scale /* B*N factors or nullptr */) {
   __shared__ float tile[32][33];
   const int b = blockIdx.z, n0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
@@ -101,12 +101,13 @@ pack_rows_kernel(const float* __restrict__ src, int64_t sb, int64_t sn, int64_t 
     __syncthreads();
     for (int k = ty; k < 32; k += 8) {
       const int n = n0 + k, d = d0 + tx;
-      if (n < N && d < D) dst[((size_t)b * N + n) * D + d] = tile[tx][k];
+      if (n < N && d < D) dst[((size_t)b * N + n) * D + d] = tile[tx][k] * (row_scale ? __ldg(row_scale + (size_t)b * N + n) : 1.f);
     }
   } else {  // d is the faster dimension: straight copy
     for (int k = ty; k < 32; k += 8) {
       const int n = n0 + k, d = d0 + tx;
-      if (n < N && d < D) dst[((size_t)b * N + n) * D + d] = s[(int64_t)n * sn + (int64_t)d * sd];
+      if (n < N && d < D)
+        dst[((size_t)b * N + n) * D + d] = s[(int64_t)n * sn + (int64_t)d * sd] * (row_scale ? __ldg(row_scale + (size_t)b * N + n) : 1.f);
     }
   }
 }
@@ -431,8 +432,8 @@ int fecl_simt_fwd(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   SimtState s = carve(a.state, B, N, D, p.has_teacher);
   const size_t plane = (size_t)B * N;
   dim3 pgrid((N + 31) / 32, (D + 31) / 32, B);
-  pack_rows_kernel<<<pgrid, 256, 0, st>>>(a.feat, a.f_sb, a.f_sn, a.f_sd, N, D, s.F);
-  if (p.has_teacher) pack_rows_kernel<<<pgrid, 256, 0, st>>>(a.teacher, a.t_sb, a.t_sn, a.t_sd, N, D, s.T);
+  pack_rows_kernel<<<pgrid, 256, 0, st>>>(a.feat, a.f_sb, a.f_sn, a.f_sd, N, D, s.F, a.feat_scale);
+  if (p.has_teacher) pack_rows_kernel<<<pgrid, 256, 0, st>>>(a.teacher, a.t_sb, a.t_sn, a.t_sd, N, D, s.T, a.teacher_scale);
   dim3 grid(row_blocks, B);
   fecl_simt_rowmax_kernel<<<grid, kThreads, 0, st>>>(s.F, a.labels, a.row_weight, N, D, p.sc.inv_tau,
                                                      (float)p.inv_rows, s.stats + kStatM * plane,

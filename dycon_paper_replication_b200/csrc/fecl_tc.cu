@@ -33,6 +33,21 @@ namespace {
 
 using namespace tc;
 
+// ---- device-clock timeline of ONE CTA (measurement aid, compiled in only with -DDYCON_TIMELINE) --------------
+// Lane 0 of the producer warp, of the MMA issuer warps and of one warp per epilogue team stores clock64() at the
+// events of every sub-tile into a buffer that tools/timeline.py reads back through dycon_debug_timeline().
+#ifdef DYCON_TIMELINE
+__device__ unsigned long long g_timeline[2][4][64][8];      // [kernel: 0 sweep (P2), 1 backward][role][sub-tile][event]
+#define DYCON_TL(kern, on, role, t, ev)                                                  \
+  do {                                                                                   \
+    if ((on) && (t) < 64) g_timeline[kern][role][t][ev] = (unsigned long long)clock64(); \
+  } while (0)
+__device__ __forceinline__ void g_tl_cls(int t, int cls) { if (t < 64) g_timeline[1][0][t][7] = (unsigned long long)cls; }
+#else
+#define DYCON_TL(kern, on, role, t, ev) do {} while (0)
+__device__ __forceinline__ void g_tl_cls(int, int) {}
+#endif
+
 constexpr int kTM = 128;               // rows per CTA (UMMA M)
 constexpr uint32_t kChunk128 = 128 * 128;   // bytes of a [128 rows][64 bf16] swizzle chunk
 constexpr uint32_t kChunk64 = 64 * 128;     // bytes of a [ 64 rows][64 bf16] swizzle chunk
@@ -92,7 +107,7 @@ __device__ __forceinline__ float pos_bwd(float t, float e, float n, float gamma)
 // (row block, column sub-tile) is then all-positive, all-negative or -- only where a class boundary crosses it --
 // mixed, which the sweeps and the backward turn into three specialised epilogue bodies and into sub-tiles that
 // are skipped outright.  fecl_rank_kernel computes, per sample, the sorted position of every row (a counting
-// rank: N^2 / 4 compares per 64-row CTA out of shared memory) and, by sorted position, the original row
+// rank: every row is compared with every key of the sample out of shared memory) and, by sorted position, the original row
 // (`perm`, used to scatter the gradient back), the label, the row weight and the class bounds
 // [cls_lo, cls_hi) = sorted positions that carry the same label.  NaN labels compare unequal to everything,
 // themselves included (dycon_losses.py:172): each NaN row is a class of its own.
@@ -116,57 +131,69 @@ __device__ __forceinline__ uint32_t label_key(float y) {
   return (u & 0x80000000u) ? ~u : (u | 0x80000000u);      // unsigned order == float order
 }
 
-// Grid (ceil(N / 64), B), 256 threads: thread (r = tid % 64, q = tid / 64) counts, for row i = 64 blockIdx.x + r,
-// the keys of quarter q of the sample that sort before it.  Dynamic shared memory: ceil4(N) keys.
+// Grid (ceil(N / 32), B), 256 threads: warp w ranks the four rows 32 blockIdx.x + 4 w + {0..3}; its lanes stride
+// over the keys of the sample (shared memory, conflict-free) and every loaded key is compared against the four row
+// keys.  An iteration lies entirely in front of, entirely behind or (at most two) across the four rows, which
+// decides warp-uniformly whether an equal key counts as "in front" (stable order).  Dynamic shared memory:
+// ceil4(N) keys.  (A first version with one THREAD per row ran 15 us at N = 1728: 216 long, lonely warps.)
 __global__ void __launch_bounds__(256) fecl_rank_kernel(const RankParams p) {
   extern __shared__ __align__(16) uint32_t rk_keys[];
-  __shared__ int part[3][4][64];
   const int tid = threadIdx.x, b = blockIdx.y, N = p.N, N4 = (N + 3) & ~3;
+  const int warp = tid >> 5, lane = tid & 31;
   if (p.pdl) pdl_trigger();
   const float* lab = p.labels + (size_t)b * N;
   for (int j = tid; j < N4; j += 256) rk_keys[j] = j < N ? label_key(__ldg(lab + j)) : 0xffffffffu;
   __syncthreads();
-  const int r = tid & 63, q = tid >> 6, i = blockIdx.x * 64 + r;
-  const int ic = i < N ? i : N - 1;
-  const uint32_t k = rk_keys[ic];
-  const int groups = N4 >> 2, gq = (groups + 3) >> 2;           // uint4 groups per quarter
-  const int g0 = q * gq, g1 = min(groups, g0 + gq);
-  int lt = 0, le = 0, eqb = 0;                                  // keys < k, keys <= k, equal keys in front of row i
-  const uint4* k4 = reinterpret_cast<const uint4*>(rk_keys);
-  for (int g = g0; g < g1; ++g) {
-    const uint4 kk = k4[g];                                     // the same address for the lanes of a quarter: broadcast
-    const uint32_t ks[4] = {kk.x, kk.y, kk.z, kk.w};
-    const int j = g << 2;
+  const int i0 = blockIdx.x * 32 + warp * 4;
+  if (i0 >= N) return;
+  uint32_t k[4];
+  int lt[4] = {0, 0, 0, 0}, eqb[4] = {0, 0, 0, 0}, eqa[4] = {0, 0, 0, 0};   // keys < k; equal keys in front of / behind row i
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      lt += ks[u] < k;
-      le += ks[u] <= k;
-    }
-    if (j + 3 < ic) {
+  for (int r = 0; r < 4; ++r) k[r] = rk_keys[min(i0 + r, N - 1)];
+  for (int base = 0; base < N4; base += 32) {
+    const int j = base + lane;
+    const uint32_t kj = j < N4 ? rk_keys[j] : 0xffffffffu;        // padding never sorts in front of a row
+    if (base + 31 < i0) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) eqb += ks[u] == k;
-    } else if (j < ic) {
+      for (int r = 0; r < 4; ++r) { lt[r] += kj < k[r]; eqb[r] += kj == k[r]; }
+    } else if (base > i0 + 3) {
 #pragma unroll
-      for (int u = 0; u < 4; ++u) eqb += (ks[u] == k) && (j + u < ic);
+      for (int r = 0; r < 4; ++r) { lt[r] += kj < k[r]; eqa[r] += kj == k[r]; }
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const bool e = kj == k[r];
+        lt[r] += kj < k[r];
+        eqb[r] += e && j < i0 + r;
+        eqa[r] += e && j >= i0 + r;
+      }
     }
   }
-  part[0][q][r] = lt; part[1][q][r] = le; part[2][q][r] = eqb;
-  __syncthreads();
-  if (q == 0 && i < N) {
-    lt = part[0][0][r] + part[0][1][r] + part[0][2][r] + part[0][3][r];
-    le = part[1][0][r] + part[1][1][r] + part[1][2][r] + part[1][3][r];
-    eqb = part[2][0][r] + part[2][1][r] + part[2][2][r] + part[2][3][r];
-    // the padding keys 0xffffffff count as <= k only for k == 0xffffffff, a NaN, whose bounds are set below
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      lt[r] += __shfl_xor_sync(0xffffffffu, lt[r], o);
+      eqb[r] += __shfl_xor_sync(0xffffffffu, eqb[r], o);
+      eqa[r] += __shfl_xor_sync(0xffffffffu, eqa[r], o);
+    }
+  }
+  if (lane < 4 && i0 + lane < N) {
+    const int i = i0 + lane;
+    const int l = lane == 0 ? lt[0] : lane == 1 ? lt[1] : lane == 2 ? lt[2] : lt[3];
+    const int eb = lane == 0 ? eqb[0] : lane == 1 ? eqb[1] : lane == 2 ? eqb[2] : eqb[3];
+    const int ea = lane == 0 ? eqa[0] : lane == 1 ? eqa[1] : lane == 2 ? eqa[2] : eqa[3];
+    // (the padding keys 0xffffffff only ever equal a NaN key, whose bounds are set below)
     const float y = __ldg(lab + i);
-    const int pos = lt + eqb;
+    const int pos = l + eb;
     const size_t o = (size_t)b * N;
     p.rank[o + i] = pos;
     p.perm[o + pos] = i;
     p.ys[o + pos] = y;
     if (p.row_weight) p.rws[o + pos] = __ldg(p.row_weight + o + i);
     const bool nan = y != y;
-    p.cls_lo[o + pos] = nan ? pos : lt;
-    p.cls_hi[o + pos] = nan ? pos + 1 : le;
+    p.cls_lo[o + pos] = nan ? pos : l;
+    p.cls_hi[o + pos] = nan ? pos + 1 : l + eb + ea;
   }
 }
 
@@ -233,6 +260,8 @@ struct PackParams {
                        // per-sample padding; the caller zero-fills the tail rows of the state once)
   const int* rank;     // rows sorted by label: row n of sample b goes to row rank[b*N + n] (nullptr: stays at n).
                        // Written by fecl_rank_kernel, the predecessor in the stream: griddepcontrol.wait first.
+  const float* scale[2];   // per-row factor (B*N floats, or nullptr): 1/max(|x|, eps) of F.normalize folded into the
+                           // conversion, so that the caller need not materialise normalised embeddings (prep.cu)
 };
 
 template <bool kBf16>
@@ -248,6 +277,7 @@ pack16_kernel(const PackParams p) {
   const float* s = (which ? p.src[1] : p.src[0]) + (int64_t)b * (which ? p.sb[1] : p.sb[0]);
   const int64_t sn = which ? p.sn[1] : p.sn[0], sd = which ? p.sd[1] : p.sd[0];
   T16* dst = reinterpret_cast<T16*>(which ? p.dst[1] : p.dst[0]);
+  const float* rscale = which ? p.scale[1] : p.scale[0];
   if (which == 0 && blockIdx.y == 0) {
     for (int q = tid; q < kNumStats * 64; q += 256) {
       const int n = n0 + (q & 63);
@@ -286,8 +316,9 @@ pack16_kernel(const PackParams p) {
       const int n = n0 + r;
       if (p.merge ? n < p.N : n < p.Npad) {
         const int nd = (p.rank && n < p.N) ? __ldg(p.rank + (size_t)b * p.N + n) : n;
+        const float sc = (rscale && n < p.N) ? __ldg(rscale + (size_t)b * p.N + n) : 1.f;
         *reinterpret_cast<uint32_t*>(dst + ((size_t)b * (p.merge ? p.N : p.Npad) + nd) * p.Dpad + d0 + 2 * kx) =
-            Cvt<kBf16>::two(tile[2 * kx][r], tile[2 * kx + 1][r]);
+            Cvt<kBf16>::two(tile[2 * kx][r] * sc, tile[2 * kx + 1][r] * sc);
       }
     }
   } else {         // any other layout (d contiguous or generic): lanes along d for both
@@ -296,7 +327,8 @@ pack16_kernel(const PackParams p) {
     for (int r = ty; r < 64; r += 4) {
       const int n = n0 + r, d = d0 + tx;
       if (p.merge ? n < p.N : n < p.Npad) {
-        const float v = (n < p.N && d < p.D) ? __ldg(s + (int64_t)n * sn + (int64_t)d * sd) : 0.f;
+        const float sc = (rscale && n < p.N) ? __ldg(rscale + (size_t)b * p.N + n) : 1.f;
+        const float v = (n < p.N && d < p.D) ? __ldg(s + (int64_t)n * sn + (int64_t)d * sd) * sc : 0.f;
         const int nd = (p.rank && n < p.N) ? __ldg(p.rank + (size_t)b * p.N + n) : n;
         dst[((size_t)b * (p.merge ? p.N : p.Npad) + nd) * p.Dpad + d] = Cvt<kBf16>::one(v);
       }
@@ -403,7 +435,9 @@ __global__ void __launch_bounds__(kSwThreads, 1)
 fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapF,
                      const __grid_constant__ CUtensorMap mapT, const SweepParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (broadcast: tells the compiler that the warp index is warp-uniform, so that everything the single-thread
+  //  roles derive from it -- sub-tile numbers, smem / TMEM addresses, descriptors -- lives in uniform registers)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int KC = p.KC;
   constexpr int kStages = kRT == 2 ? 3 : kSwStages;
   constexpr int kSlotCols = 64 * kRT;
@@ -434,7 +468,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   tcgen05_before_sync();
   __syncthreads();
   tcgen05_after_sync();
-  const uint32_t tmem = ms.tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, ms.tmem_slot, 0);
 
   double red[3] = {0.0, 0.0, 0.0};
 
@@ -463,10 +497,15 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   }
   const int u0 = (int)((long long)split * tmap.count / p.splits), u1 = (int)((long long)(split + 1) * tmap.count / p.splits);
   const int nt = u1 - u0;
+  const bool tl_on = kMode == 2 && blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 1 && lane == 0;   // (timeline build only)
+  (void)tl_on;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0) {
+    // (elect.sync, not lane == 0: with a lane test nvcc wraps EVERY tcgen05.mma / TMA instruction of a single-thread
+    //  role into an ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall, ~130 issue cycles per MMA -- which is what bound
+    //  the sweeps: a sub-tile's 32 MMAs took 4300 cycles to issue against ~1600 to execute)
+    if (elect_one()) {
       // first the K chunk the first MMA needs, then the first B sub-tile, then the rest of A
       auto load_a = [&](int h, int c) {
         mbar_expect_tx(&ms.a_full[h * 4 + c], kChunk128);
@@ -477,11 +516,13 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         const int s = t % kStages, row = b * p.Npad + tile_of(tmap, u0 + t) * tcols;
         uint8_t* dst = sStage + s * stage_bytes;
         mbar_wait_relaxed(&ms.b_empty[s], ((t / kStages) & 1) ^ 1);
+        DYCON_TL(0, tl_on, 0, t, 0);
         mbar_expect_tx(&ms.b_full[s], stage_bytes);
         for (int c = 0; c < KC; ++c) {
           tma_load_2d(dst + c * kChunk64, &mapF, c * 64, row, &ms.b_full[s]);       // box: 64 rows, or 32 with a teacher
           if (teacher_on) tma_load_2d(dst + c * kChunk64 + kChunk32, &mapT, c * 64, row, &ms.b_full[s]);
         }
+        DYCON_TL(0, tl_on, 0, t, 1);
         if (t == 0) {
           for (int h = 0; h < kRT; ++h)
             for (int c = (h == 0 ? 1 : 0); c < KC; ++c) load_a(h, c);
@@ -490,9 +531,9 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     }
   } else if (warp < 4) {
     // ================================ MMA issuers =================================
-    // One thread needs ~130 cycles of issue slots per tcgen05.mma (descriptor arithmetic + the election
-    // wrapper) but an N = 64 MMA only occupies the tensor pipe for 32: three warps issue alternate sub-tiles.
-    if (lane == 0 && nt > 0) {
+    // Three warps issue alternate sub-tiles (a remnant of the lane == 0 version, whose issue loop was three times
+    // slower than the tensor pipe; harmless now).
+    if (nt > 0 && elect_one()) {
       const uint32_t idesc = umma_idesc_16(128, 64, false, false, kBf16);
       const uint64_t a_desc0 = umma_desc_kmajor(smem_u32(sA));
       for (int t = warp - 1; t < nt; t += 3) {
@@ -500,7 +541,9 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         const int s = t % kStages, a = t & (kSwSlots - 1);
         const uint64_t b_desc0 = umma_desc_kmajor(smem_u32(sStage + s * stage_bytes));
         mbar_wait_relaxed(&ms.b_full[s], (t / kStages) & 1);
+        DYCON_TL(0, tl_on, 1, t, 0);
         mbar_wait_relaxed(&ms.acc_empty[a], ((t / kSwSlots) & 1) ^ 1);
+        DYCON_TL(0, tl_on, 1, t, 1);
         tcgen05_after_sync();
 #pragma unroll
         for (int h = 0; h < kRT; ++h) {
@@ -520,12 +563,15 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         }
         umma_commit(&ms.b_empty[s]);
         umma_commit(&ms.acc_full[a]);
+        DYCON_TL(0, tl_on, 1, t, 2);
       }
     }
   } else if (warp >= 4) {
     // ================================ epilogue teams ==============================
     const int team = (warp - 4) >> 3;             // 0: even sub-tiles, 1: odd sub-tiles
     const int tt = threadIdx.x - 128 - team * kSwTeamThreads;   // 0..255 inside the team
+    const bool tl_e = tl_on && (warp == 4 || warp == 12);
+    (void)tl_e;
     const int quarter = warp & 3, chalf = ((warp - 4) >> 2) & 1;
     // kRT = 1: the two warp groups of a team split the columns of a sub-tile; kRT = 2: they split the two
     // 128-row tiles and every thread walks all 64 columns in two chunks
@@ -587,8 +633,10 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       const int T = tile_of(tmap, u0 + t);        // sub-tile index inside the sample
       const int slot = it & 1, a = t & (kSwSlots - 1), j0 = T * tcols;
       const int cls = kMode == 0 ? kClsMixed : tile_class(rc, T, tcols, p.N, ta, tb);      // uniform over the team
+      DYCON_TL(0, tl_e, 2 + team, t, 0);
       const float nxt = fetch(tile_of(tmap, u0 + (t + 2 < nt ? t + 2 : t)));
       mbar_wait(&ms.acc_full[a], (t / kSwSlots) & 1);
+      DYCON_TL(0, tl_e, 2 + team, t, 1);
       tcgen05_after_sync();
       if (!teacher_on) {
 #pragma unroll 1
@@ -747,9 +795,12 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           }
         }
       }
+      DYCON_TL(0, tl_e, 2 + team, t, 2);
       publish(slot ^ 1, nxt);
       sw_team_barrier(team);
+      DYCON_TL(0, tl_e, 2 + team, t, 3);
     }
+    DYCON_TL(0, tl_e, 2 + team, 62, 0);
 
     // ---- combine the threads that share a row (kRT = 1: 2 teams x 2 column halves; kRT = 2: the 2 teams),
     //      then the column splits ----
@@ -814,6 +865,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       }
     }
   }
+  DYCON_TL(0, tl_on && warp == 4, 2, 63, 0);
   tcgen05_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, kSwSlots * kSlotCols);
@@ -964,7 +1016,7 @@ __global__ void __launch_bounds__(kBwdThreads, 1)
 fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapF,
                    const __grid_constant__ CUtensorMap mapT, const BwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int KC = p.KC, Dpad = KC * 64;
   const uint32_t a_bytes = (uint32_t)KC * kChunk128, j_bytes = (uint32_t)KC * kChunk32;
   const uint32_t stage_bytes = j_bytes * 2;       // F_J sub-tile + T_J sub-tile, interleaved per K chunk
@@ -984,6 +1036,8 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   if (p.use_classes) rc = load_row_class(p.cls_lo, p.cls_hi, (size_t)b * p.N, i0, kTM, p.N);
   int ta, tb;
   same_range(rc, 32, ta, tb);
+  const bool tl_on = blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 1 && lane == 0;     // (timeline build only)
+  (void)tl_on;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
@@ -1008,13 +1062,13 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   tcgen05_before_sync();
   __syncthreads();
   tcgen05_after_sync();
-  const uint32_t tmem = ms.tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, ms.tmem_slot, 0);
   // TMEM columns: team g's S | CS at g*64 (32 + 32 columns), dF at 256 (Dpad columns)
   const uint32_t tm_sc = tmem, tm_df = tmem + 256;
 
   if (warp == 0) {
     // ================================ TMA producer ================================
-    if (lane == 0 && nt > 0) {
+    if (nt > 0 && elect_one()) {
       auto load_a = [&](int c) {
         mbar_expect_tx(&ms.a_full[c], kChunk128);
         tma_load_2d(sA + c * kChunk128, &mapA, c * 64, b * p.Npad + i0, &ms.a_full[c]);
@@ -1024,6 +1078,7 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         const int s = t % kBwdStages, row = b * p.Npad + (t0 + t) * 32;
         uint8_t* dst = sStage + s * stage_bytes;
         mbar_wait_relaxed(&ms.b_empty[s], ((t / kBwdStages) & 1) ^ 1);
+        DYCON_TL(1, tl_on, 0, t, 0);
         mbar_expect_tx(&ms.b_full[s], teacher ? stage_bytes : j_bytes);
         for (int c = 0; c < KC; ++c) {     // chunk c = [32 F rows | 32 T rows] x 64 K: one N = 64 B operand for MMA1
           tma_load_2d(dst + c * kChunk64, &mapF, c * 64, row, &ms.b_full[s]);
@@ -1036,7 +1091,7 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     }
   } else if (warp == 1 || warp == 3) {
     // ================================ MMA1 issuers: S, CS (warp 1: team 0's sub-tiles, warp 3: team 1's) ====
-    if (lane == 0 && nt > 0) {
+    if (nt > 0 && elect_one()) {
       // one MMA per K step computes S | CS side by side (N = 64: the F and T rows of a chunk are contiguous)
       const uint32_t idesc_s = umma_idesc_16(128, teacher ? 64 : 32, false, false, kBf16);
       const uint64_t a_desc0 = umma_desc_kmajor(smem_u32(sA));
@@ -1045,7 +1100,9 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         const int s = t % kBwdStages, g = t & 1;
         const uint64_t b_desc0 = umma_desc_kmajor(smem_u32(sStage + s * stage_bytes));
         mbar_wait_relaxed(&ms.b_full[s], (t / kBwdStages) & 1);
+        DYCON_TL(1, tl_on, 1, t, 0);
         mbar_wait_relaxed(&ms.sc_empty[g], ((t >> 1) & 1) ^ 1);
+        DYCON_TL(1, tl_on, 1, t, 1);
         tcgen05_after_sync();
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
@@ -1061,11 +1118,12 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
           }
         }
         umma_commit(&ms.sc_full[g]);
+        DYCON_TL(1, tl_on, 1, t, 2);
       }
     }
   } else if (warp == 2) {
     // ================================ MMA2 issuer: dF += H F_J + Gc T_J ===========
-    if (lane == 0 && nt > 0) {
+    if (nt > 0 && elect_one()) {
       const uint32_t idesc_d = umma_idesc_16(128, Dpad, false, true, kBf16);   // B = F_J / T_J read MN-major
       const uint64_t h_desc0 = umma_desc_kmajor(smem_u32(sH)), g_desc0 = umma_desc_kmajor(smem_u32(sG));
       for (int t = 0; t < nt; ++t) {
@@ -1073,6 +1131,7 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         // MN-major B: 64-element MN blocks are the chunks (LBO = 8 KB), 8 K rows per 1 KB atom (SBO)
         const uint64_t f_desc0 = umma_desc(smem_u32(sStage + s * stage_bytes), kChunk64, 1024);
         mbar_wait_relaxed(&ms.h_full[g], (t >> 1) & 1);
+        DYCON_TL(1, tl_on, 1, t, 3);
         tcgen05_after_sync();
         // K = the 32 columns of the sub-tile = 2 steps of 16: columns g*32 + k*16 of sH, rows k*16 (2048 B) of F_J
 #pragma unroll
@@ -1085,6 +1144,7 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
         }
         umma_commit(&ms.b_empty[s]);
         umma_commit(&ms.h_free[g]);
+        DYCON_TL(1, tl_on, 1, t, 4);
       }
       umma_commit(&ms.df_full);
     }
@@ -1125,6 +1185,8 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     const int cbase = chalf * 16;                 // this thread's 16 columns of the 32-column sub-tile
     const int hcol = team * 32 + cbase;           // ... and of the 64-column sH / sG tiles
+    const bool tl_e = tl_on && (warp == 4 || warp == 12);
+    (void)tl_e;
 
     // column statistics of sub-tile t: 5 planes x 32 columns, fetched by threads 0..159 of the team and
     // published through shared memory.  Padded columns: y = NaN, m2 = +inf, rest 0 (-> e_ij = 0, h = g = 0).
@@ -1152,7 +1214,9 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       const float nx = fetch_one(t0 + (t + 2 < nt ? t + 2 : t));
       const int cls = tile_class(rc, t0 + t, 32, p.N, ta, tb);       // uniform over the team: no divergence
       const bool with_g = teacher && cls != kClsSame;                 // all-positive sub-tiles have no hard negatives
+      DYCON_TL(1, tl_e, 2 + team, t, 0);
       mbar_wait(&ms.sc_full[team], it & 1);
+      DYCON_TL(1, tl_e, 2 + team, t, 1);
       tcgen05_after_sync();
       float sv[16], cv[16];
       tmem_ld16(tm_sc + lane_base + team * 64 + cbase, sv);
@@ -1204,8 +1268,10 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       if (cls == kClsSame) pairs(std::integral_constant<int, kClsSame>{});
       else if (cls == kClsDiff) pairs(std::integral_constant<int, kClsDiff>{});
       else pairs(std::integral_constant<int, kClsMixed>{});
+      DYCON_TL(1, tl_e, 2 + team, t, 2);
       // the team's previous MMA2 must have finished reading this column half of sH / sG
       if (it > 0) mbar_wait(&ms.h_free[team], (it - 1) & 1);
+      DYCON_TL(1, tl_e, 2 + team, t, 3);
 #pragma unroll
       for (int u = 0; u < 2; ++u) {     // two 16-byte units = 16 16-bit columns
         const uint32_t o = sw128_offset(r, hcol + u * 8);
@@ -1221,10 +1287,14 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(&ms.h_full[team]);
       bwd_team_barrier(team);
+      DYCON_TL(1, tl_e, 2 + team, t, 4);
+      if (tl_e) g_tl_cls(t, cls);
     }
+    DYCON_TL(1, tl_e, 2 + team, 62, 0);
 
     // ---- dF (TMEM) * go -> grad_feat: the 16 epilogue warps split the Dpad columns four ways ----
     mbar_wait(&ms.df_full, 0);
+    DYCON_TL(1, tl_e, 2 + team, 62, 1);
     tcgen05_after_sync();
     if (p.pdl) pdl_wait();                          // the zero fill of grad_feat is complete and visible
     const float go = __ldg(p.grad_out) / hscale;
@@ -1276,6 +1346,7 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
       }
     }
   }
+  DYCON_TL(1, tl_on && warp == 4, 2, 63, 0);
   tcgen05_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
@@ -1326,17 +1397,20 @@ TcState carve(void* state, int B, int N, int D, int has_teacher) {
   return s;
 }
 
-// Rows are packed sorted by label unless the batch is merged (global negatives: the row statistics are exchanged
-// between ranks by merged row index) or the sample is too long for the rank kernel's shared memory.
-// DYCON_FECL_SORT=0 keeps the caller's row order, DYCON_FECL_CLASSES=0 sorts but runs the general pair arithmetic
-// on every sub-tile (both: A/B switches for measurements).
+// Rows packed sorted by label (DYCON_FECL_SORT=1; never for a merged batch -- global negatives exchange the row
+// statistics between ranks by merged row index -- nor beyond the rank kernel's shared memory).  OFF by default: on
+// the B200 the class-specialised bodies cut the executed instructions of the loss sweep by 28 % and of the backward
+// by 20 % and shorten the arithmetic phase of a sub-tile by a third, but both kernels are bound by their MUFU + issue
+// floor per SM and by the life time of an operand stage, not by those instructions, so the step only pays for the
+// extra launch (138 vs 150 us; profiles/r2_fecl_timeline.md).  DYCON_FECL_CLASSES=0 sorts but runs the general
+// pair arithmetic on every sub-tile.
 constexpr int kMaxSortRows = 49152;
 bool sort_rows(int N, bool merged) {
-  static const bool off = [] {
+  static const bool on = [] {
     const char* e = getenv("DYCON_FECL_SORT");
-    return e && e[0] == '0';
+    return e && e[0] == '1';
   }();
-  return !off && !merged && N <= kMaxSortRows;
+  return on && !merged && N <= kMaxSortRows;
 }
 bool use_classes() {
   static const bool off = [] {
@@ -1441,6 +1515,7 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   pk.src[1] = a.teacher; pk.sb[1] = a.t_sb; pk.sn[1] = a.t_sn; pk.sd[1] = a.t_sd; pk.dst[1] = s.T;
   pk.stats = s.stats; pk.B = B; pk.N = N; pk.D = D; pk.Npad = Npad; pk.Dpad = Dpad;
   pk.merge = 0;
+  pk.scale[0] = a.feat_scale; pk.scale[1] = a.teacher_scale;
   if (a.merge_B > 0) {       // global negatives: merge_B samples of N / merge_B rows -> one sample of N rows
     pk.B = a.merge_B; pk.N = N / a.merge_B; pk.Npad = npad_of(pk.N); pk.merge = 1;
   }
@@ -1471,7 +1546,7 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
             return (int)DYCON_OK;
           }))
         return rc;
-      fecl_rank_kernel<<<dim3((N + 63) / 64, B), 256, rsmem, st>>>(rp);
+      fecl_rank_kernel<<<dim3((N + 31) / 32, B), 256, rsmem, st>>>(rp);
       DYCON_CUDA(cudaGetLastError());
       count_launches(1);
     }
@@ -1642,6 +1717,18 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
 }
 
 }  // namespace
+
+// copies the timeline of the last launches to the host (timeline build only; returns 0 bytes otherwise)
+size_t fecl_tc_debug_timeline(void* host_out, size_t bytes) {
+#ifdef DYCON_TIMELINE
+  const size_t n = sizeof(unsigned long long) * 2 * 4 * 64 * 8;
+  if (bytes < n || cudaMemcpyFromSymbol(host_out, g_timeline, n) != cudaSuccess) return 0;
+  return n;
+#else
+  (void)host_out; (void)bytes;
+  return 0;
+#endif
+}
 
 int fecl_tc_fwd(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   if (int rc = check_tc_shape(p.B, p.N, p.D)) return rc;

@@ -32,7 +32,7 @@ import torch.nn as nn
 from . import _lib, sharded
 
 __all__ = ["UnCLoss", "FeCLoss", "adaptive_beta", "sigmoid_rampup", "gambling_softmax",
-           "update_ema_variables", "StepLosses", "sgd_clip_ema_step", "loss_is_finite_flag"]
+           "update_ema_variables", "StepLosses", "sgd_clip_ema_step", "loss_is_finite_flag", "pooled_label_mask"]
 
 
 # =========================================================================== host scalars
@@ -471,6 +471,106 @@ class _FeCLGlobalFunction(torch.autograd.Function):
         return (grad,) + (None,) * 10
 
 
+class _FeCLFeaturesFunction(torch.autograd.Function):
+    """FeCL on the RAW feature volumes: ``F.normalize(features.view(B, C, -1).transpose(1, 2), dim=-1)``
+    of student and teacher (train_DyCON_BraTS19.py:316-323) is folded into FeCL's operand staging as a per-row
+    scale, and its Jacobian is applied to FeCL's gradient by one kernel -- the normalised fp32 embeddings and the
+    autograd chain through them never exist."""
+
+    @staticmethod
+    def forward(ctx, features, teacher_features, labels, row_weight, inv_tau, gamma, use_focal, cross_thresh,
+                lambda_cross, precision, process_group, global_batch):
+        dev = features.device
+        x = features.contiguous()
+        B, D = x.shape[0], x.shape[1]
+        N = x[0, 0].numel()
+        xv = x.view(B, D, N).transpose(1, 2)                    # (B, N, D) with strides (D*N, 1, N), no copy
+        has_teacher = teacher_features is not None
+        tv = teacher_features.contiguous().view(B, D, N).transpose(1, 2) if has_teacher else None
+        gb = sharded.global_batch_of(B, global_batch, process_group)
+        inv_rows = 1.0 / (gb * N)
+        with torch.cuda.device(dev):
+            _lib.require_b200(dev.index)
+            L = _lib.lib()
+            t0 = _tick()
+            inv_s = torch.empty(B * N, dtype=torch.float32, device=dev)
+            _lib.check(L.dycon_row_inv_norm(_ptr(xv), *xv.stride(), B, N, D, _ptr(inv_s), _stream_ptr(dev)), "dycon_row_inv_norm")
+            inv_t = None
+            if has_teacher:
+                inv_t = torch.empty(B * N, dtype=torch.float32, device=dev)
+                _lib.check(L.dycon_row_inv_norm(_ptr(tv), *tv.stride(), B, N, D, _ptr(inv_t), _stream_ptr(dev)),
+                           "dycon_row_inv_norm")
+            sbytes = L.dycon_fecl_state_bytes(B, N, D, int(has_teacher), precision)
+            wbytes = L.dycon_fecl_workspace_bytes(B, N, D, precision)
+            state = torch.empty(max(sbytes, 16), dtype=torch.uint8, device=dev)
+            ws = _workspace(dev, f"fecl{precision}", wbytes)
+            sums = torch.empty(3, dtype=torch.float64, device=dev)
+            loss = torch.empty((), dtype=torch.float32, device=dev)
+            ts = tv.stride() if has_teacher else (0, 0, 0)
+            ex = sharded.fused_exchange(dev, process_group)
+            xargs = ex.abi_args() if ex is not None else (None, 0, 1, None, -1.0)
+            _lib.check(L.dycon_fecl_fwd_scaled(_ptr(xv), *xv.stride(), _ptr(tv), *ts, _ptr(inv_s), _ptr(inv_t), _ptr(labels),
+                                               _ptr(row_weight), B, N, D, inv_tau, gamma, int(use_focal), cross_thresh,
+                                               lambda_cross, inv_rows, precision, _ptr(state), state.numel(), _ptr(sums),
+                                               _ptr(loss), _ptr(ws), ws.numel(), *xargs, _stream_ptr(dev)),
+                       "dycon_fecl_fwd_scaled")
+            _tock("fecl_fwd", t0)
+            if ex is None and process_group is not None:
+                loss = sharded.reduce_fecl(sums, inv_rows, lambda_cross, has_teacher, process_group)
+        ctx.save_for_backward(state, labels, sums, x, inv_s)
+        ctx.cfg = (B, N, D, has_teacher, inv_tau, gamma, int(use_focal), row_weight is not None, cross_thresh,
+                   lambda_cross, precision)
+        ctx.shape = features.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, go):
+        state, labels, sums, x, inv_s = ctx.saved_tensors
+        B, N, D, has_teacher, inv_tau, gamma, use_focal, has_rw, cross_thresh, lambda_cross, precision = ctx.cfg
+        dev = state.device
+        xv = x.view(B, D, N).transpose(1, 2)
+        g = torch.empty_strided((B, N, D), (N * D, 1, N), dtype=torch.float32, device=dev)     # gradient w.r.t. the unit rows
+        dx = torch.empty_like(x)
+        dxv = dx.view(B, D, N).transpose(1, 2)
+        go = _scalar_grad(go)
+        with torch.cuda.device(dev):
+            L = _lib.lib()
+            t0 = _tick()
+            _lib.check(L.dycon_fecl_bwd(_ptr(state), state.numel(), _ptr(labels), B, N, D, int(has_teacher), inv_tau, gamma,
+                                        use_focal, int(has_rw), cross_thresh, lambda_cross, precision,
+                                        ctypes.c_void_p(sums.data_ptr() + 16), _ptr(go), _ptr(g), *g.stride(),
+                                        _stream_ptr(dev)), "dycon_fecl_bwd")
+            _lib.check(L.dycon_normalize_bwd(_ptr(xv), *xv.stride(), _ptr(g), *g.stride(), _ptr(inv_s), B, N, D, _ptr(dxv),
+                                             *dxv.stride(), _stream_ptr(dev)), "dycon_normalize_bwd")
+            _tock("fecl_bwd", t0)
+        return (dx.view(ctx.shape),) + (None,) * 11
+
+
+def pooled_label_mask(label_batch, feature_spatial):
+    """``(F.avg_pool3d(label.float(), k, k) > 0.5).float().reshape(B, -1)`` with per-axis kernels
+    k = label extent // feature extent (train_DyCON_BraTS19.py:326-330; train_DyCON_ISLES22.py:268-281), one kernel,
+    straight from the int64 / uint8 / float32 label volume.  Returns (B, N) fp32 in {0, 1}."""
+    if not torch.is_tensor(label_batch) or not label_batch.is_cuda:
+        raise RuntimeError("label_batch must be a CUDA tensor (no CPU fallback)")
+    if label_batch.dim() != 4 or len(feature_spatial) != 3:
+        raise ValueError("label_batch must be (B, H, W, D) and feature_spatial three extents")
+    codes = {torch.int64: _lib.LABEL_INT64, torch.float32: _lib.LABEL_FLOAT32, torch.uint8: _lib.LABEL_UINT8}
+    if label_batch.dtype not in codes:
+        raise TypeError(f"label_batch must be int64, uint8 or float32 (got {label_batch.dtype})")
+    lab = label_batch.contiguous()
+    B, H, W, Dz = lab.shape
+    k = [ext // f for ext, f in zip((H, W, Dz), feature_spatial)]
+    if min(k) < 1 or any(ext // kk != f for ext, kk, f in zip((H, W, Dz), k, feature_spatial)):
+        raise ValueError(f"label volume {(H, W, Dz)} does not pool onto the feature grid {tuple(feature_spatial)}")
+    dev = lab.device
+    out = torch.empty(B, feature_spatial[0] * feature_spatial[1] * feature_spatial[2], dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.require_b200(dev.index)
+        _lib.check(_lib.lib().dycon_pool_mask(_ptr(lab), codes[lab.dtype], B, H, W, Dz, k[0], k[1], k[2], _ptr(out),
+                                              _stream_ptr(dev)), "dycon_pool_mask")
+    return out
+
+
 class FeCLoss(nn.Module):
     """Feature contrastive loss with focal positives and the teacher hard-negative branch
     (reference: dycon_losses.py:120-235; constructor :141-148, forward :150-235).
@@ -535,6 +635,49 @@ class FeCLoss(nn.Module):
         return _FeCLFunction.apply(feat, labels, teacher_feat, rw, 1.0 / float(self.temperature), float(self.gamma),
                                    bool(self.use_focal), float(cross_thresh), float(self.lambda_cross),
                                    _PRECISIONS[self.precision], self.process_group, self.global_batch)
+
+
+def _fecl_from_features(self, stud_features, label_batch, ema_features=None, gambling_uncertainty=None, epoch=0):
+    """``FeCLoss.from_features``: the loss straight from what the network returns and the loader delivers.
+
+    Equivalent to the reference's caller-side preparation followed by ``forward`` (train_DyCON_BraTS19.py:316-350)::
+
+        emb  = F.normalize(stud_features.view(B, C, -1).transpose(1, 2), dim=-1)       # same for ema_features
+        mask = (F.avg_pool3d(label_batch.float(), k, k) > 0.5).float().reshape(B, -1).unsqueeze(1)
+        loss = fecl(feat=emb, mask=mask, teacher_feat=ema_emb, gambling_uncertainty=..., epoch=epoch)
+
+    with k = label extent // feature extent per axis.  The gradient flows to ``stud_features``."""
+    _require_cuda_fp32("stud_features", stud_features)
+    if stud_features.dim() != 5:
+        raise ValueError(f"stud_features must be (B, C, h, w, d), got {tuple(stud_features.shape)}")
+    B, C = stud_features.shape[:2]
+    N = stud_features[0, 0].numel()
+    grad_on = torch.is_grad_enabled()
+    if ema_features is not None:
+        _require_cuda_fp32("ema_features", ema_features)
+        if ema_features.shape != stud_features.shape:
+            raise ValueError("ema_features must have the shape of stud_features")
+        if ema_features.requires_grad and grad_on:
+            raise RuntimeError("FeCLoss: ema_features requires grad; the teacher is a constant in DyCON")
+        ema_features = ema_features.detach()
+    labels = pooled_label_mask(label_batch, tuple(stud_features.shape[2:]))
+    rw = None
+    if gambling_uncertainty is not None:
+        if gambling_uncertainty.requires_grad and grad_on:
+            raise RuntimeError("FeCLoss: gambling_uncertainty requires grad; it is a constant weight")
+        if gambling_uncertainty.numel() != B * N:
+            raise ValueError("gambling_uncertainty must be (B, N)")
+        rw = gambling_uncertainty.detach().reshape(B, N).to(device=stud_features.device, dtype=torch.float32).contiguous()
+    if self.cross_gpu_negatives:
+        raise RuntimeError("FeCLoss.from_features does not combine with cross_gpu_negatives (use forward)")
+    cross_thresh = sigmoid_rampup(epoch, self.rampup_epochs, min_threshold=0.3, max_threshold=0.5)
+    return _FeCLFeaturesFunction.apply(stud_features, ema_features, labels, rw, 1.0 / float(self.temperature),
+                                       float(self.gamma), bool(self.use_focal), float(cross_thresh),
+                                       float(self.lambda_cross), _PRECISIONS[self.precision], self.process_group,
+                                       self.global_batch)
+
+
+FeCLoss.from_features = _fecl_from_features
 
 
 # =========================================================================== EMA

@@ -122,6 +122,11 @@ int dycon_fecl_bwd(const void* state, size_t state_bytes, const float* labels, i
                    const float* grad_out, float* grad_feat, int64_t g_sb, int64_t g_sn, int64_t g_sd,
                    dycon_stream_t stream);
 
+/* Measurement aid: a library built with -DDYCON_TIMELINE (DYCON_TIMELINE=1 python -m ...csrc.build) records
+ * device-clock stamps of one CTA of the FeCL loss sweep and backward; this copies them to host_out ([2][4][64][8]
+ * uint64) and returns the byte count -- 0 in a normal build.  tools/timeline.py prints them. */
+size_t dycon_debug_timeline(void* host_out, size_t bytes);
+
 /* ------------------------------------------------------------------ FeCL with global negatives
  * Extension for batches sharded over ranks (BASELINE config 5; not in the reference, whose contrast is per
  * sample): every row is contrasted against the rows of ALL B_all samples of the global batch.  The result is
@@ -181,6 +186,36 @@ int dycon_segcons_fwd(const float* s, const float* t, const long long* label, in
                       dycon_stream_t stream);
 int dycon_segcons_bwd(const float* s, const float* t, const long long* label, int B, int labeled_bs, int C, int64_t V,
                       float beta, const double* sums, const float* grad_out4, float* grad_s, dycon_stream_t stream);
+
+/* ------------------------------------------------------------------ caller-side preparation at the FeCL boundary
+ * What the step loop runs between the network and FeCLoss (code/train_DyCON_BraTS19.py:316-330):
+ *   emb  = F.normalize(features.view(B, C, -1).transpose(1, 2), dim=-1)   -> dycon_row_inv_norm + a row scale folded
+ *          into FeCL's operand staging (dycon_fecl_fwd_scaled): the normalised embeddings are never materialised
+ *   mask = (F.avg_pool3d(label.float(), k, k) > 0.5).float()               -> dycon_pool_mask (per-axis kernels)
+ * and, for the backward, the Jacobian of the normalisation applied to FeCL's gradient -> dycon_normalize_bwd:
+ *   dx = (g - f (f . g)) * inv,  f = x * inv,  inv = 1/max(|x|_2, 1e-12)   (rows below eps: dx = g * inv).
+ * label: (B, H, W, Dz) contiguous, dtype DYCON_LABEL_*; mask_out: (B, (H/kh)*(W/kw)*(Dz/kd)) floats in {0, 1}.
+ * x / g / dx: (B, N, D) fp32 with ELEMENT strides; inv: B*N floats.
+ * dycon_fecl_fwd_scaled: dycon_fecl_fwd with the two row-scale vectors (either may be NULL) and, optionally, the
+ * sharded exchange of dycon_fecl_fwd_sharded (peer_inboxes NULL: not sharded).
+ */
+#define DYCON_LABEL_INT64 0
+#define DYCON_LABEL_FLOAT32 1
+#define DYCON_LABEL_UINT8 2
+int dycon_pool_mask(const void* label, int label_dtype, int B, int H, int W, int Dz, int kh, int kw, int kd,
+                    float* mask_out, dycon_stream_t stream);
+int dycon_row_inv_norm(const float* x, int64_t sb, int64_t sn, int64_t sd, int B, int N, int D, float* inv_out,
+                       dycon_stream_t stream);
+int dycon_normalize_bwd(const float* x, int64_t x_sb, int64_t x_sn, int64_t x_sd, const float* g, int64_t g_sb, int64_t g_sn,
+                        int64_t g_sd, const float* inv_norm, int B, int N, int D, float* dx, int64_t d_sb, int64_t d_sn,
+                        int64_t d_sd, dycon_stream_t stream);
+int dycon_fecl_fwd_scaled(const float* feat, int64_t f_sb, int64_t f_sn, int64_t f_sd, const float* teacher, int64_t t_sb,
+                          int64_t t_sn, int64_t t_sd, const float* feat_row_scale, const float* teacher_row_scale,
+                          const float* labels, const float* row_weight, int B, int N, int D, float inv_tau, float gamma,
+                          int use_focal, float cross_thresh, float lambda_cross, double inv_rows, int precision, void* state,
+                          size_t state_bytes, double* sums_out, float* loss_out, void* workspace, size_t workspace_bytes,
+                          void* const* peer_inboxes, int rank, int world, unsigned long long* seq_counters,
+                          double timeout_s, dycon_stream_t stream);
 
 /* ------------------------------------------------------------------ clip + SGD + EMA, finite check
  * Replaces, with two launches over ALL parameter tensors, the per-tensor launches of

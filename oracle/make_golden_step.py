@@ -39,8 +39,54 @@ def step_case(ref, stock, shape, labeled_bs, beta, scale, seed, dtype):
                 losses=np.array([u.item(), ce.item(), dice.item(), cons.item()], np.float64), grad=s.grad.numpy())
 
 
+def prep_case(ref, feat_shape, label_shape, seed, dtype, epoch=100, teacher=True):
+    """The caller-side preparation of code/train_DyCON_BraTS19.py:316-330 (restated line for line: the script itself
+    cannot be imported) in front of the UNMODIFIED FeCLoss."""
+    g = torch.Generator().manual_seed(seed)
+    b, c = feat_shape[:2]
+    base = torch.randn(1, c, 1, 1, 1, generator=g)
+    x32 = base + 0.8 * torch.randn(feat_shape, generator=g)
+    label = torch.zeros(label_shape, dtype=torch.long)
+    k = tuple(le // fe for le, fe in zip(label_shape[1:], feat_shape[2:]))
+    coarse = torch.rand((b,) + tuple(feat_shape[2:]), generator=g) < 0.35          # blocky labels, some cells half full
+    label = coarse.repeat_interleave(k[0], 1).repeat_interleave(k[1], 2).repeat_interleave(k[2], 3).long()
+    label = label * (torch.rand(label_shape, generator=g) < 0.8).long()
+    x32 = x32 + 0.5 * coarse.float().unsqueeze(1)
+    t32 = x32 + 0.1 * torch.randn(feat_shape, generator=g)
+    stud_features = x32.to(dtype).clone().requires_grad_(True)
+    ema_features = t32.to(dtype)
+    stud_embedding = stud_features.view(b, c, -1)                                  # :317
+    stud_embedding = torch.transpose(stud_embedding, 1, 2)                         # :318
+    stud_embedding = F.normalize(stud_embedding, dim=-1)                           # :319
+    ema_embedding = F.normalize(torch.transpose(ema_features.view(b, c, -1), 1, 2), dim=-1)       # :321-323
+    mask_con = F.avg_pool3d(label.float(), kernel_size=k, stride=k)                # :326-327
+    mask_con = (mask_con > 0.5).float().reshape(b, -1).unsqueeze(1).to(dtype)      # :328-330
+    torch.set_default_dtype(dtype)
+    try:
+        crit = ref.FeCLoss(device="cpu", temperature=0.6, gamma=2.0, use_focal=True, rampup_epochs=1500)
+        loss = crit(feat=stud_embedding, mask=mask_con, teacher_feat=ema_embedding if teacher else None,
+                    gambling_uncertainty=None, epoch=epoch)                        # :346-350
+    finally:
+        torch.set_default_dtype(torch.float32)
+    (0.5 * loss).backward()
+    return dict(features=x32.numpy(), ema_features=t32.numpy(), label=label.numpy(), mask=mask_con.float().numpy(),
+                loss=np.float64(loss.item()), grad=stud_features.grad.numpy())
+
+
 def main():
     ref, stock = ref_loader.dycon_losses(), ref_loader.stock_losses()
+    prep = {}
+    for name, (fs, ls, seed, teacher) in {"cubic_k4": ((2, 16, 3, 3, 2), (2, 12, 12, 8), 21, True),
+                                          "anisotropic": ((2, 8, 4, 2, 3), (2, 8, 6, 12), 22, True),
+                                          "no_teacher_k2": ((3, 12, 2, 3, 4), (3, 4, 6, 8), 23, False)}.items():
+        r32 = prep_case(ref, fs, ls, seed, torch.float32, teacher=teacher)
+        r64 = prep_case(ref, fs, ls, seed, torch.float64, teacher=teacher)
+        rec = dict(features=r32["features"], ema_features=r32["ema_features"], label=r32["label"], mask=r32["mask"],
+                   teacher=np.int64(teacher), epoch=np.int64(100), go=np.float64(0.5), loss32=r32["loss"], grad32=r32["grad"],
+                   loss64=r64["loss"], grad64=r64["grad"])
+        prep.update({f"{name}/{k}": v for k, v in rec.items()})
+    np.savez_compressed(os.path.join(OUT, "prep.npz"), **prep)
+    print("wrote prep.npz")
     specs = {
         "half_labelled": ((4, 2, 6, 5, 4), 2, 1.58, 2.0, 11),
         "three_of_four": ((4, 2, 5, 4, 3), 3, 5.0, 2.0, 12),

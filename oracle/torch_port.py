@@ -155,3 +155,27 @@ def step_losses(stud_logits, ema_logits, label_batch, labeled_bs, beta):
     u_loss = uncl_loss(stud_logits, ema_logits, beta)                          # :351
     consistency = softmax_mse(stud_probs[labeled_bs:], ema_probs[labeled_bs:]).mean()                         # :352
     return u_loss, loss_seg, loss_seg_dice, consistency
+
+
+# --------------------------------------------------------------------------- caller-side preparation
+def prep_embeddings(features):
+    """(B, C, h, w, d) -> unit rows (B, N, C) (code/train_DyCON_BraTS19.py:316-319)."""
+    b, c = features.shape[:2]
+    return torch.nn.functional.normalize(torch.transpose(features.reshape(b, c, -1), 1, 2), dim=-1)
+
+
+def prep_mask(label_batch, feature_spatial):
+    """(B, H, W, D) labels -> (B, 1, N) float mask (train_DyCON_BraTS19.py:326-330; per-axis kernels as in
+    train_DyCON_ISLES22.py:268-281)."""
+    k = tuple(ext // f for ext, f in zip(label_batch.shape[1:], feature_spatial))
+    m = torch.nn.functional.avg_pool3d(label_batch.float(), kernel_size=k, stride=k)
+    m = (m > 0.5).float()
+    return m.reshape(label_batch.shape[0], -1).unsqueeze(1)
+
+
+def fecl_from_features(stud_features, label_batch, ema_features=None, epoch=0, **ctor):
+    """Preparation + FeCL, as the step loop chains them (train_DyCON_BraTS19.py:316-350)."""
+    emb = prep_embeddings(stud_features)
+    temb = None if ema_features is None else prep_embeddings(ema_features)
+    mask = prep_mask(label_batch, stud_features.shape[2:]).to(emb.dtype)
+    return fecl_loss(emb, mask, temb, None, epoch, **ctor)

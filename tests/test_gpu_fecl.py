@@ -323,3 +323,19 @@ def test_bad_arguments_raise():
         crit(f.cuda(), torch.zeros(2, 1, 15).cuda())
     with pytest.raises(TypeError):
         crit(f.cuda().half(), m.cuda())
+
+
+def test_label_sorted_variant_in_a_subprocess():
+    """DYCON_FECL_SORT=1 packs the rows of every sample sorted by label and runs class-specialised epilogue bodies
+    (all-positive / all-negative / mixed sub-tiles, skipped sub-tiles, gradient scattered back through the
+    permutation).  The switch is read once per process, so the parity cases run again in a child process."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, DYCON_FECL_SORT="1")
+    here = os.path.dirname(os.path.abspath(__file__))
+    sel = "test_golden or test_seeded_shapes_vs_oracle or test_ragged or test_single_class or test_near_identical or test_backward_work_split"
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_fecl.py"), "-x", "-q", "-k", sel,
+                          "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert " passed" in out.stdout and "failed" not in out.stdout.splitlines()[-1]
