@@ -21,7 +21,34 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 }
 }  // namespace
 
+// A tensor map is a pure function of (base, rows, cols, box rows, element type): a small per-thread cache of host-side
+// descriptors saves the driver call on every launch of a training loop that reuses its buffers (the caching allocator
+// hands the same state buffer back step after step) -- and keeps driver calls out of ncu's range replays.
+struct TmapKey {
+  const void* base;
+  uint64_t rows, cols;
+  uint32_t box_rows;
+  bool bf16;
+  bool operator==(const TmapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && box_rows == o.box_rows && bf16 == o.bf16;
+  }
+};
+constexpr int kTmapCache = 64;
+struct TmapCache {
+  TmapKey key[kTmapCache];
+  CUtensorMap map[kTmapCache];
+  int n = 0, next = 0;
+};
+
 int make_tmap_16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, bool bf16) {
+  static thread_local TmapCache cache;
+  const TmapKey k{base, rows, cols, box_rows, bf16};
+  for (int i = 0; i < cache.n; ++i) {
+    if (cache.key[i] == k) {
+      *out = cache.map[i];
+      return DYCON_OK;
+    }
+  }
   auto fn = encode_fn();
   DYCON_REQUIRE(fn != nullptr, DYCON_ERR_DEVICE, "cuTensorMapEncodeTiled is not available from this driver");
   DYCON_REQUIRE(aligned(base, 128) && cols % 64 == 0 && box_rows >= 1 && box_rows <= 256, DYCON_ERR_ARG,
@@ -34,6 +61,9 @@ int make_tmap_16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   DYCON_REQUIRE(r == CUDA_SUCCESS, DYCON_ERR_ARG, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  const int slot = cache.n < kTmapCache ? cache.n++ : (cache.next = (cache.next + 1) % kTmapCache);
+  cache.key[slot] = k;
+  cache.map[slot] = *out;
   return DYCON_OK;
 }
 

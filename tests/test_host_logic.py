@@ -85,3 +85,39 @@ def test_synthetic_inputs_have_the_callers_layout():
     assert torch.equal(inp.feat, again.feat) and torch.equal(inp.s_logits, again.s_logits)
     shapes = unet3d_param_shapes()
     assert len(shapes) == 48 and sum(math.prod(s) for s in shapes) == 6148532
+
+
+def test_fused_entry_points_keep_the_drop_in_surface_and_refuse_cpu_tensors():
+    """SURVEY 8(f) entry points: new names beside the unchanged ones, no CPU fallback, SGD only."""
+    from dycon_paper_replication_b200 import dycon_losses as dl
+    sig = lambda f: str(inspect.signature(f))
+    assert sig(dl.StepLosses.forward) == "(self, stud_logits, ema_logits, label_batch, labeled_bs, beta)"
+    assert sig(dl.FeCLoss.from_features) == ("(self, stud_features, label_batch, ema_features=None, "
+                                             "gambling_uncertainty=None, epoch=0)")
+    assert sig(dl.sgd_clip_ema_step).startswith("(optimizer, model, ema_model, max_norm, ema_decay, global_step, *")
+    x = torch.randn(2, 2, 4, 4, 4)
+    lab = torch.zeros(2, 4, 4, 4, dtype=torch.long)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dl.StepLosses()(x, x, lab, 1, 1.0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dl.FeCLoss("cpu").from_features(torch.randn(2, 8, 2, 2, 2), lab)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dl.loss_is_finite_flag(torch.tensor(1.0))
+    lin = torch.nn.Linear(3, 3)
+    with pytest.raises(TypeError, match="SGD"):
+        dl.sgd_clip_ema_step(torch.optim.Adam(lin.parameters()), lin, None, 1.0, 0.99, 0)
+    lin.weight.grad = torch.zeros_like(lin.weight)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dl.sgd_clip_ema_step(torch.optim.SGD(lin.parameters(), lr=0.1), lin, None, 1.0, 0.99, 0)
+
+
+def test_reference_loader_finds_the_unmodified_modules():
+    """bench.py's reference arm and the config-3 harness execute the reference itself (oracle/ref_loader.py): from
+    /root/reference in the build container, from the staged git-ignored copy elsewhere."""
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.skip("no reference here (neither /root/reference nor baseline/_ref)")
+    ref = ref_loader.dycon_losses()
+    assert ref.adaptive_beta(0, 10) == 5.0 and hasattr(ref, "FeCLoss") and hasattr(ref, "UnCLoss")
+    net = ref_loader.unet3d()(in_channels=1, n_classes=2, scale_factor=2, use_aspp=False)      # net_factory_3d.py:8
+    assert sum(p.numel() for p in net.parameters()) == 6148532 and len(list(net.parameters())) == 48
