@@ -277,7 +277,9 @@ class StepLosses(nn.Module):
     ``losses.dice_loss(stud_probs[:lb, 1], label_batch[:lb] == 1)`` and
     ``losses.softmax_mse_loss(stud_probs[lb:], ema_probs[lb:]).mean()`` (the reference passes probabilities to a
     function that takes the softmax again; reproduced).  Gradients flow to ``stud_logits`` only.  Two classes run in
-    the fused kernel pair; any other class count composes the UnCL kernels with the stock PyTorch ops."""
+    the fused kernel pair; any other class count composes the UnCL kernels with the stock PyTorch ops.  Edge cases
+    the scripts never reach: ``labeled_bs == 0`` gives ``loss_seg = 0`` and ``labeled_bs == B`` gives
+    ``consistency_loss = 0`` where the reference's means over empty tensors are NaN."""
 
     def forward(self, stud_logits, ema_logits, label_batch, labeled_bs, beta):
         _require_cuda_fp32("stud_logits", stud_logits)
@@ -803,7 +805,7 @@ def sgd_clip_ema_step(optimizer, model, ema_model, max_norm, ema_decay, global_s
     for group in optimizer.param_groups:
         if group.get("dampening", 0) != 0 or group.get("maximize", False):
             raise ValueError("sgd_clip_ema_step: dampening / maximize are not supported (the reference uses neither)")
-        ps, gs, bs, es, first = [], [], [], [], None
+        fresh, warm = ([], [], [], []), ([], [], [], [])     # (params, grads, buffers, teachers): first step of a buffer / later steps
         for p in group["params"]:
             seen.add(id(p))
             _require_cuda_fp32("parameter", p.data)
@@ -815,24 +817,24 @@ def sgd_clip_ema_step(optimizer, model, ema_model, max_norm, ema_decay, global_s
                 _require_cuda_fp32("gradient", g)
                 if g.is_sparse or not _dense_like(g, p.data):
                     raise RuntimeError("sgd_clip_ema_step: gradients must be dense with the parameter's strides")
-            buf = None
+            buf, is_first = None, False
             if g is not None and group["momentum"] != 0:
                 st = optimizer.state[p]
                 buf = st.get("momentum_buffer")
                 is_first = buf is None
-                if is_first:
-                    buf = st["momentum_buffer"] = torch.empty_like(p.data)
-                if first is None:
-                    first = is_first
-                elif first != is_first:
-                    raise RuntimeError("sgd_clip_ema_step: a group mixes fresh and initialised momentum buffers")
+                if is_first:                                  # torch.optim.SGD: buf = clone(grad) on the first step
+                    # zeros, not empty: if skip_flag drops this very step, the next one runs buf = 0 * mu + g = g
+                    buf = st["momentum_buffer"] = torch.zeros_like(p.data)
             e = ema_of.get(id(p))
             if e is not None:
                 _require_cuda_fp32("ema parameter", e.data)
                 if not _dense_like(e.data, p.data):
                     raise RuntimeError("sgd_clip_ema_step: student/teacher parameters must be dense with equal strides")
-            ps.append(p.data); gs.append(g); bs.append(buf); es.append(None if e is None else e.data)
-        groups.append((group, ps, gs, bs, es, bool(first)))
+            dstl = fresh if is_first else warm
+            dstl[0].append(p.data); dstl[1].append(g); dstl[2].append(buf); dstl[3].append(None if e is None else e.data)
+        for lists, first in ((fresh, True), (warm, False)):
+            if lists[0]:
+                groups.append((group, *lists, first))
     # teacher tensors whose student parameter is not in the optimizer still follow it (plain EMA)
     rest = [(p, ema_of[id(p)]) for p in src.parameters() if id(p) in ema_of and id(p) not in seen]
     if dev is None:

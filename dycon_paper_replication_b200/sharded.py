@@ -13,6 +13,13 @@ once its default averaging is undone (multiply by world size).  With a process g
 are ALWAYS global: ``global_batch`` defaults to ``B_local * world_size`` (equal shards); pass it
 explicitly for ragged shards.
 
+The exchange itself runs over NVLink peer memory in the TAIL of the forward kernels (``dycon_uncl_fwd_sharded`` /
+``dycon_fecl_fwd_sharded``, csrc/exchange.cuh): no extra launch, no NCCL call on the step's critical path.  Ranks may
+lag behind each other (rank-0-only validation, a data-loader stall): the others wait inside their kernel, like in a
+blocking collective, for at most ``DYCON_EXCHANGE_TIMEOUT_S`` seconds (default 600, 0 = for ever); a rank that gives
+up gets NaN losses and a raised error word (``PeerExchange.timed_out()``) instead of a destroyed CUDA context.  Set
+``DYCON_PEER_EXCHANGE=0`` to use the backend's all-reduce instead.
+
 This module holds only host logic (no kernels) so the N>1 protocol can be tested on CPU with gloo.
 """
 from __future__ import annotations

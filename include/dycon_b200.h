@@ -5,8 +5,10 @@
  * dycon_paper_replication_b200/csrc/build.py for sm_100a) exports exactly these
  * entry points.  Every pointer is a plain device pointer unless stated
  * otherwise; the library allocates no device memory, keeps no device state
- * between calls, never synchronises the host with the device and only enqueues
- * work on the stream it is given (all launches are CUDA-graph capturable).
+ * between calls (host side: per-device kernel attributes and a per-thread cache
+ * of TMA descriptors, each a pure function of its key), never synchronises the
+ * host with the device and only enqueues work on the stream it is given (all
+ * launches are CUDA-graph capturable).
  *
  * Reference interfaces replaced (rogeliorjr/DyCON_Paper_Replication):
  *   dycon_uncl_*   UnCLoss.forward + its autograd backward    code/utils/dycon_losses.py:94-118

@@ -4,6 +4,8 @@
     python tools/ncu_summary.py launches gpurun_out/launches.csv            > profiles/rNN_launches.md
     python tools/ncu_summary.py full     gpurun_out/prof.ncu-rep [regex]    > profiles/rNN_<kernel>.md
     python tools/ncu_summary.py traffic  a.ncu-rep b.ncu-rep ...            > profiles/rNN_traffic.json
+    python tools/ncu_summary.py ranges   gpurun_out/ranges.csv name1,name2.. N  > profiles/rNN_traffic.json
+      (ncu --replay-mode range of `bench.py --profile-ranges`: one range per kernel family, N launches each)
 
 `launches` reads the CSV written by `ncu --metrics gpu__time_duration.sum --csv --log-file ...`;
 `full` reads a `--set full` report through `ncu -i ... --page raw/source --csv` (no GPU needed).
@@ -121,8 +123,36 @@ def traffic(reps):
                       "kernels": out}, indent=1))
 
 
+def ranges(path, names, per_range):
+    """CSV of `ncu --replay-mode range --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum`
+    -> {"families": {name: {dram_read_bytes, dram_write_bytes, dram_bytes_per_launch, us_per_launch}}}."""
+    import json
+    rows = [r for r in csv.reader(open(path, newline="")) if len(r) > 5 and r[0].isdigit()]
+    out = {}
+    for r in rows:
+        rid, metric, unit, val = int(r[0]), r[-3], r[-2], float(r[-1].replace(",", ""))
+        if rid >= len(names):
+            continue
+        d = out.setdefault(names[rid], {})
+        if metric == "dram__bytes_read.sum":
+            d["dram_read_bytes"] = val / per_range
+        elif metric == "dram__bytes_write.sum":
+            d["dram_write_bytes"] = val / per_range
+        elif metric == "gpu__time_duration.sum":
+            d["us_per_launch_under_ncu"] = val / 1e3 / per_range
+    for d in out.values():
+        d["dram_bytes_per_launch"] = d.get("dram_read_bytes", 0.0) + d.get("dram_write_bytes", 0.0)
+    print(json.dumps({"how": "ncu --replay-mode range over bench.py --profile-ranges: every range = %d back-to-back launches of one "
+                             "kernel family on 4 rotating input sets (452 MB > 126 MB L2); bytes are per launch. Outputs that are "
+                             "rewritten in place every launch (the 28 MB UnCL gradient, the 7 MB FeCL gradient) stay in the 126 MB "
+                             "L2 and show up as fewer DRAM writes than the algorithmic bytes." % per_range,
+                      "families": out}, indent=1))
+
+
 if __name__ == "__main__":
-    if sys.argv[1] == "launches":
+    if sys.argv[1] == "ranges":
+        ranges(sys.argv[2], sys.argv[3].split(","), int(sys.argv[4]))
+    elif sys.argv[1] == "launches":
         launches(sys.argv[2])
     elif sys.argv[1] == "traffic":
         traffic(sys.argv[2:])
