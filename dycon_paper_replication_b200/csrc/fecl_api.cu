@@ -53,7 +53,7 @@ extern "C" {
 
 size_t dycon_fecl_state_bytes(int B, int N, int D, int has_teacher, int precision) {
   if (B <= 0 || N <= 0 || D <= 0) return 0;
-  return precision != DYCON_FECL_FP32 ? fecl_tc_state_bytes(B, N, D, has_teacher)
+  return precision != DYCON_FECL_FP32 ? fecl_tc_state_bytes(B, N, D, has_teacher, precision == DYCON_FECL_FP16)
                                       : fecl_simt_state_bytes(B, N, D, has_teacher);
 }
 
@@ -139,7 +139,7 @@ size_t dycon_debug_timeline(void* host_out, size_t bytes) { return fecl_tc_debug
 // ---- global negatives: the merged batch as ONE sample, rows split over ranks (include/dycon_b200.h) -------
 size_t dycon_fecl_gn_state_bytes(int B_all, int N, int D, int has_teacher, int precision) {
   if (B_all <= 0 || N <= 0 || D <= 0 || precision == DYCON_FECL_FP32) return 0;
-  return fecl_tc_state_bytes(1, B_all * N, D, has_teacher);
+  return fecl_tc_state_bytes(1, B_all * N, D, has_teacher, false);
 }
 
 int dycon_fecl_gn_layout(int B_all, int N, int D, int has_teacher, int precision, size_t* out6) {

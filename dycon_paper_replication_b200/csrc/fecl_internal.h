@@ -63,7 +63,8 @@ int fecl_simt_fwd(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st);
 int fecl_simt_bwd(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st);
 
 // bf16 tcgen05 path (fecl_tc.cu)
-size_t fecl_tc_state_bytes(int B, int N, int D, int has_teacher);
+// pairs: include the stored-pairs matrices of the per-sample loss (fecl_tc.cu: stored_pairs); never for a merged batch
+size_t fecl_tc_state_bytes(int B, int N, int D, int has_teacher, bool pairs);
 size_t fecl_tc_workspace_bytes(int B, int N, int D);
 int fecl_tc_fwd(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st);
 int fecl_tc_bwd(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st);

@@ -21,6 +21,7 @@
 //                                 MN-major operands from the very stage that produced S | CS.
 // The four forward kernels are chained with programmatic dependent launch.
 #include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <type_traits>
 
@@ -99,6 +100,34 @@ __device__ __forceinline__ float pos_bwd(float t, float e, float n, float gamma)
   const float tL = t - lg2_approx(T);
   const float w1 = kFocal == kFocalG2 ? omd : pow_gm1(omd, gamma);
   return w1 * omd * fmaf(gamma * kLn2 * d, tL, -omd);
+}
+
+// The loss sweep of the stored-pairs build (kStore): the forward terms of pos_fwd AND the backward term
+// px = phi'(d) d (1 - d) of the same pair (it shares every factor with a_term), and -- with a teacher -- the
+// reciprocal of the cross term's argument out of the SAME MUFU.RCP:  fac = 1 - cs on a hard negative, else 1, so
+// that R = 1/(T fac) yields 1/T = R fac and 1/(1 - cs) = R T.
+template <int kFocal>
+__device__ __forceinline__ void pos_fwd_x(float t, float e, float n, float gamma, float fac, float& phi2, float& a_term,
+                                          float& px, float& rom) {
+  const float T = e + n;
+  const float R = rcp_approx(T * fac);
+  const float rT = R * fac;
+  rom = R * T;
+  const float tL = t - lg2_approx(T);
+  if (kFocal == kNoFocal) {
+    phi2 = tL;
+    a_term = -rT;
+    px = -(n * rT);                       // -(1 - d)
+  } else {
+    const float d = e * rT;
+    float omd = 1.f - d;
+    const float w1 = kFocal == kFocalG2 ? omd : pow_gm1(omd, gamma);
+    const float w = w1 * omd;
+    const float y = fmaf(gamma * kLn2 * d, tL, -omd);
+    phi2 = tL * w;
+    a_term = w1 * y * rT;
+    px = w * y;
+  }
 }
 
 // ---- rows sorted by label ----------------------------------------------------------------------------
@@ -262,6 +291,7 @@ struct PackParams {
                        // Written by fecl_rank_kernel, the predecessor in the stream: griddepcontrol.wait first.
   const float* scale[2];   // per-row factor (B*N floats, or nullptr): 1/max(|x|, eps) of F.normalize folded into the
                            // conversion, so that the caller need not materialise normalised embeddings (prep.cu)
+  unsigned int* gc_flag;   // stored pairs: (Npad/128) x (Npad/64) tile flags per sample, cleared here (or nullptr)
 };
 
 template <bool kBf16>
@@ -278,6 +308,10 @@ pack16_kernel(const PackParams p) {
   const int64_t sn = which ? p.sn[1] : p.sn[0], sd = which ? p.sd[1] : p.sd[0];
   T16* dst = reinterpret_cast<T16*>(which ? p.dst[1] : p.dst[0]);
   const float* rscale = which ? p.scale[1] : p.scale[0];
+  if (which == 0 && blockIdx.y == 0 && blockIdx.x == 0 && p.gc_flag) {
+    const int nf = (p.Npad >> 7) * (p.Npad >> 6);
+    for (int q = tid; q < nf; q += 256) p.gc_flag[(size_t)b * nf + q] = 0u;
+  }
   if (which == 0 && blockIdx.y == 0) {
     for (int q = tid; q < kNumStats * 64; q += 256) {
       const int n = n0 + (q & 63);
@@ -386,6 +420,12 @@ struct SweepParams {
   double* sums_out;
   float* loss_out;
   ExchangeCtx x;       // sharded batch (x.world > 1): P2's last block exchanges the three sums with the peers
+  // stored pairs (kStore): the loss sweep leaves, per pair, what the backward needs -- the backward then is a
+  // streaming GEMM with an elementwise fix-up instead of a fourth recomputation of the similarity tiles
+  void* pair_x;        // [B][Npad][Npad] 16-bit: kappa_i phi'(d) d (1-d) h_mul on positive pairs (final), 256 e_ij on
+                       // negative pairs (the backward multiplies it by -kappa_i A_i h_mul / 256), 0 on the diagonal / padding
+  void* pair_gc;       // [B][Npad][Npad] 16-bit: 1/(1 - cs_ij) on hard negatives, else 0 (teacher only)
+  unsigned int* gc_flag;   // [B][Npad/128][Npad/64]: set where a (128-row, 64-column) tile of pair_gc is not all zero
 };
 
 struct SweepMisc {
@@ -430,25 +470,31 @@ __device__ __forceinline__ void cross_pair(float cs, bool hard, float& cprod, fl
 // teacher only those that hold a positive pair -- the others are not even loaded -- and P2's epilogue runs a
 // positives-only body on all-positive sub-tiles, a cross-only body on all-negative ones and the general body
 // only where a class boundary crosses the sub-tile.  The class is uniform over the team, so nothing diverges.
-template <int kMode, bool kBf16, int kFocal, int kRT>
+template <int kMode, bool kBf16, int kFocal, int kRT, bool kStore = false>
 __global__ void __launch_bounds__(kSwThreads, 1)
 fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapF,
-                     const __grid_constant__ CUtensorMap mapT, const SweepParams p) {
+                     const __grid_constant__ CUtensorMap mapT, const __grid_constant__ CUtensorMap mapXs,
+                     const __grid_constant__ CUtensorMap mapGs, const SweepParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   // (broadcast: tells the compiler that the warp index is warp-uniform, so that everything the single-thread
   //  roles derive from it -- sub-tile numbers, smem / TMEM addresses, descriptors -- lives in uniform registers)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int KC = p.KC;
-  constexpr int kStages = kRT == 2 ? 3 : kSwStages;
+  // stored pairs: 32 KB of staging tiles for the TMA stores of X / Gc take the place of one ring stage
+  constexpr int kStages = kRT == 2 ? (kStore ? 2 : 3) : (kStore ? kSwStages - 1 : kSwStages);
+  constexpr uint32_t kStgBytes = kStore ? 32768u : 0u;
   constexpr int kSlotCols = 64 * kRT;
   const uint32_t a_tile = (uint32_t)KC * kChunk128, a_bytes = a_tile * kRT, stage_bytes = (uint32_t)KC * kChunk64;
   uint8_t* const sA = smem;
   uint8_t* const sStage = smem + a_bytes;
-  SweepMisc& ms = *reinterpret_cast<SweepMisc*>(sStage + kStages * stage_bytes);
+  uint8_t* const sStg = sStage + kStages * stage_bytes;      // [team][X | Gc][2 regions][128 rows][16 cols] (kStore)
+  SweepMisc& ms = *reinterpret_cast<SweepMisc*>(sStg + kStgBytes);
   const int b = blockIdx.z, i0 = (blockIdx.x + p.rb_lo) * kTM * kRT, split = blockIdx.y;
   const bool teacher_on = kMode == 2 && p.has_teacher;
   const int tcols = teacher_on ? 32 : 64;                  // columns per sub-tile
-  const int nt_all = (p.N + tcols - 1) / tcols;            // sub-tiles that hold at least one real column
+  // sub-tiles that hold at least one real column (stored pairs: the backward reads 64-column tiles, so the
+  // columns up to the next multiple of 64 are swept too -- they come out as zeros)
+  const int nt_all = kStore ? (p.N + 63) / 64 * (64 / tcols) : (p.N + tcols - 1) / tcols;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
@@ -459,6 +505,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     prefetch_tmap(&mapA);
     prefetch_tmap(&mapF);
     if (teacher_on) prefetch_tmap(&mapT);
+    if (kStore) prefetch_tmap(&mapXs), prefetch_tmap(&mapGs);
     if (kMode == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
       p.hdr[0] = p.hscale;
       p.hdr[1] = (float)p.splits;       // how many partial A_i planes the backward has to add up
@@ -533,10 +580,14 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     // ================================ MMA issuers =================================
     // Three warps issue alternate sub-tiles (a remnant of the lane == 0 version, whose issue loop was three times
     // slower than the tensor pipe; harmless now).
-    if (nt > 0 && elect_one()) {
+    // (stored pairs: ONE issuer.  With three issuers and a 2- or 4-stage ring an issuer can reach use u + 1 of a
+    //  stage before use u has even been loaded; its wait for phase parity p then passes at once, because the barrier
+    //  has not completed phase p ^ 1 yet.  In the 3-stage ring every stage has its own issuer.)
+    constexpr int kIssuers = kStore ? 1 : 3;
+    if (nt > 0 && warp - 1 < kIssuers && elect_one()) {
       const uint32_t idesc = umma_idesc_16(128, 64, false, false, kBf16);
       const uint64_t a_desc0 = umma_desc_kmajor(smem_u32(sA));
-      for (int t = warp - 1; t < nt; t += 3) {
+      for (int t = warp - 1; t < nt; t += kIssuers) {
         const bool first = t == warp - 1;         // this issuer's first sub-tile: the A chunks may still be in flight
         const int s = t % kStages, a = t & (kSwSlots - 1);
         const uint64_t b_desc0 = umma_desc_kmajor(smem_u32(sStage + s * stage_bytes));
@@ -625,6 +676,53 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       if (row_writer) p.stat_kappa[g] = kappa;
     }
 
+    // stored pairs: positive pairs carry kappa_i h_mul px (the same scaling as the H tiles of the recomputing
+    // backward), negative pairs 256 e_ij; rows outside [row_lo, row_hi) and the padding store zeros (yi = NaN makes every
+    // one of their pairs a "negative")
+    const float kx = (kStore && row_ok) ? kappa * p.sc.inv_tau * p.hscale : 0.f;
+    const float xs = (kStore && row_ok) ? 256.f : 0.f;
+    // The pair terms leave through shared memory: a thread owns a ROW, so direct stores would touch 32 lines per
+    // instruction.  Each team has two staging buffers (X | Gc -- without a teacher both carry X) of two regions of
+    // [128 rows][16 cols]; region = the 128-row tile (kRT = 2) or the column half of the team's sub-tile (kRT = 1).
+    // After a team barrier one thread issues the TMA stores into the row-major matrices [B Npad][Npad].
+    uint8_t* const stg = sStg + team * 16384;
+    const int x_region = kRT == 2 ? rh : chalf;
+    uint8_t* const stg_row = stg + x_region * 4096 + (quarter * 32 + lane) * 32;
+    const int x_row0 = b * p.Npad + i0;
+    const bool x_two = kRT == 1 || i0 + kTM < p.Npad;      // kRT = 2: the second row tile may lie beyond the padded sample
+    // (col0 = first column of this chunk)
+    auto stage_pairs = [&](const uint32_t (&a)[8], const uint32_t (&g)[8], int col0, bool with_g) {
+      if (tt == 0) bulk_wait_read0();        // the previous chunk's stores have read the staging tiles
+      sw_team_barrier(team);
+      uint4* dx = reinterpret_cast<uint4*>(stg_row);
+      dx[0] = make_uint4(a[0], a[1], a[2], a[3]);
+      dx[1] = make_uint4(a[4], a[5], a[6], a[7]);
+      uint4* dg = reinterpret_cast<uint4*>(stg_row + 8192);
+      dg[0] = make_uint4(g[0], g[1], g[2], g[3]);
+      dg[1] = make_uint4(g[4], g[5], g[6], g[7]);
+      fence_async_smem();
+      sw_team_barrier(team);
+      if (tt == 0) {
+        // teacher: buffer 1 is Gc (same coordinates, its own matrix); else buffer 1 = the next 16 columns of X
+        const CUtensorMap* m1 = with_g ? &mapGs : &mapXs;
+        const int c1 = with_g ? col0 : col0 + 16;
+        if (kRT == 2) {
+          tma_store_2d(&mapXs, col0, x_row0, stg);
+          tma_store_2d(m1, c1, x_row0, stg + 8192);
+          if (x_two) {
+            tma_store_2d(&mapXs, col0, x_row0 + kTM, stg + 4096);
+            tma_store_2d(m1, c1, x_row0 + kTM, stg + 8192 + 4096);
+          }
+        } else {                             // regions = the two column halves of the sub-tile
+          const int step = with_g ? 16 : 32;
+          tma_store_2d(&mapXs, col0, x_row0, stg);
+          tma_store_2d(m1, c1, x_row0, stg + 8192);
+          tma_store_2d(&mapXs, col0 + step, x_row0, stg + 4096);
+          tma_store_2d(m1, c1 + step, x_row0, stg + 8192 + 4096);
+        }
+        bulk_commit();
+      }
+    };
     if (team < nt) publish(0, fetch(tile_of(tmap, u0 + team)));
     sw_team_barrier(team);
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
@@ -632,7 +730,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     for (int t = team; t < nt; t += 2, ++it) {
       const int T = tile_of(tmap, u0 + t);        // sub-tile index inside the sample
       const int slot = it & 1, a = t & (kSwSlots - 1), j0 = T * tcols;
-      const int cls = kMode == 0 ? kClsMixed : tile_class(rc, T, tcols, p.N, ta, tb);      // uniform over the team
+      const int cls = (kMode == 0 || kStore) ? kClsMixed : tile_class(rc, T, tcols, p.N, ta, tb);      // uniform over the team
       DYCON_TL(0, tl_e, 2 + team, t, 0);
       const float nxt = fetch(tile_of(tmap, u0 + (t + 2 < nt ? t + 2 : t)));
       mbar_wait(&ms.acc_full[a], (t / kSwSlots) & 1);
@@ -687,6 +785,35 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 }
               }
             }
+          } else if (kStore) {       // loss / A partials, and the pair terms of the backward go to pair_x
+            uint32_t xp[16];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
+              const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
+              const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
+              float xv[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int c = q * 4 + k;
+                const float tl = fmaf(v[c], p.c1, -m2[k]);
+                const float e = ex2_approx(tl);                   // padded column: m2 = +inf -> e = 0
+                float phi2, at, px, rom;
+                pos_fwd_x<kFocal>(tl, e, n_row, p.sc.gamma, 1.f, phi2, at, px, rom);
+                const bool same = ys[k] == yi;
+                const bool pos = diag_here ? same && (c != rdiag) : same;
+                acc0 += pos ? phi2 : 0.f;
+                acc1 += pos ? at : 0.f;
+                xv[k] = pos ? px * kx : same ? 0.f : e * xs;       // (same && !pos: the diagonal)
+              }
+              xp[q * 2] = Cvt<kBf16>::two(xv[0], xv[1]);
+              xp[q * 2 + 1] = Cvt<kBf16>::two(xv[2], xv[3]);
+            }
+            {
+              const uint32_t lo[8] = {xp[0], xp[1], xp[2], xp[3], xp[4], xp[5], xp[6], xp[7]};
+              const uint32_t hi[8] = {xp[8], xp[9], xp[10], xp[11], xp[12], xp[13], xp[14], xp[15]};
+              stage_pairs(lo, hi, j0 + (kRT == 2 ? cb : 0), false);
+            }
           } else {                   // acc0 / acc1 = loss / A partials                              (dycon_losses.py:186-206)
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
@@ -727,7 +854,67 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           }
           const int w0 = i0 + rh * kTM + quarter * 32 - j0 - cb;
           const bool diag_here = w0 + 31 >= 0 && w0 < 16;
-          if (cls == kClsSame) {
+          if (kStore) {
+            // general body + the pair terms of the backward: pair_x as above, pair_gc = 1 / (64 (1 - cs)) on hard
+            // negatives (the 64 of cross_pair; the backward folds it into its scalar factor)
+            float cprod = 1.f, cmin = 1.f, nh = 0.f;
+            uint32_t xp[8], gp[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
+              const float4 mm = *reinterpret_cast<const float4*>(cm + q * 4);
+              const float ys[4] = {yy.x, yy.y, yy.z, yy.w}, m2[4] = {mm.x, mm.y, mm.z, mm.w};
+              float xv[4], gv[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int c = q * 4 + k;
+                const float tl = fmaf(v[c], p.c1, -m2[k]);
+                const float e = ex2_approx(tl);
+                const bool same = ys[k] == yi;
+                const bool hard = !same && w[c] > p.sc.cross_thresh;
+                const float fac = hard ? fmaf(-64.f, w[c], 64.f) : 1.f;
+                cmin = fminf(cmin, fac);
+                cprod *= fac;
+                nh += hard ? 1.f : 0.f;
+                float phi2, at, px, rom;
+                pos_fwd_x<kFocal>(tl, e, n_row, p.sc.gamma, fac, phi2, at, px, rom);
+                const bool pos = diag_here ? same && (c != rdiag) : same;
+                acc0 += pos ? phi2 : 0.f;
+                acc1 += pos ? at : 0.f;
+                xv[k] = pos ? px * kx : same ? 0.f : e * xs;
+                gv[k] = hard ? rom : 0.f;
+              }
+              xp[q * 2] = Cvt<kBf16>::two(xv[0], xv[1]);
+              xp[q * 2 + 1] = Cvt<kBf16>::two(xv[2], xv[3]);
+              gp[q * 2] = Cvt<kBf16>::two(gv[0], gv[1]);
+              gp[q * 2 + 1] = Cvt<kBf16>::two(gv[2], gv[3]);
+            }
+            {
+              const bool rowhard = row_ok && nh > 0.f;
+              if (!rowhard) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) gp[u] = 0u;
+              }
+              if (__any_sync(0xffffffffu, rowhard) && lane == 0)
+                p.gc_flag[((size_t)b * (p.Npad >> 7) + (i >> 7)) * (p.Npad >> 6) + ((j0 + cb) >> 6)] = 1u;
+              stage_pairs(xp, gp, j0 + (kRT == 2 ? cb : 0), true);
+            }
+            acc3 += nh;
+            if (cmin > 0.f && cprod >= 1e-30f) {
+              acc2 += fmaf(-6.f, nh, lg2_approx(cprod));
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
+                const float ys[4] = {yy.x, yy.y, yy.z, yy.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float cs = w[q * 4 + k];
+                  if (!(ys[k] == yi) && cs > p.sc.cross_thresh) acc2 += lg2_approx((1.f - cs) + kTiny);
+                }
+              }
+            }
+          } else if (cls == kClsSame) {
             // all-positive sub-tile: student terms only, no label test, no hard negatives
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -801,6 +988,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       DYCON_TL(0, tl_e, 2 + team, t, 3);
     }
     DYCON_TL(0, tl_e, 2 + team, 62, 0);
+    if (kStore && tt == 0) bulk_wait0();      // this team's TMA stores are complete
 
     // ---- combine the threads that share a row (kRT = 1: 2 teams x 2 column halves; kRT = 2: the 2 teams),
     //      then the column splits ----
@@ -1352,6 +1540,306 @@ fecl_tc_bwd_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_consta
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+// =================================================================================================
+//  Backward from stored pairs: a streaming GEMM with an elementwise fix-up
+// =================================================================================================
+// The loss sweep (kStore) has left X and Gc in the state: everything MUFU-heavy the recomputing backward evaluates a
+// fourth time.  What it could not finish is the negative pairs' gradient -kappa_i A_i e_ij: A_i is complete only
+// when the sweep is.  So a CTA (128 rows I, a column split) streams, per 64-column tile J,
+//   X_IJ  [128 i][64 j]  K-major A           X_JI  [64 j][128 i]  the transposed direction, read as an MN-major A
+//   Gc_IJ [128 i][64 j]  K-major A           F_J, T_J [64 j][Dpad]  MN-major B                       (all by TMA)
+// the fix-up warps scale the negative pairs of both X tiles IN PLACE by their row's -kappa A h_mul / 256 (a pair is
+// negative where the labels differ -- the test the sweep used), and one thread issues
+//   dF1 += X_IJ F_J + X_JI^T F_J            dF2 += Gc_IJ T_J     (two 128 x Dpad fp32 accumulators = 512 TMEM columns)
+// grad = go / hscale (dF1 + 64 lambda hscale / cnt dF2).  No similarity tile, no TMEM round trip per pair, no MUFU.
+// Gc tiles without a hard negative (flagged by the sweep) are neither loaded nor multiplied.
+constexpr int kGbThreads = 640;
+constexpr int kGbFixThreads = 512;
+constexpr int kGbStages = 2;
+
+struct GbParams {
+  int N, Npad, KC, D, has_teacher;
+  int splits, pdl;
+  float inv_tau, lambda_cross;
+  const float* labels;
+  const float* apart;
+  const float* stat_kappa;
+  const float* hdr;
+  const double* cross_cnt;
+  const unsigned int* gc_flag;
+  const float* grad_out;
+  float* grad_feat;
+  int64_t g_sb, g_sn, g_sd;
+};
+
+struct GbMisc {
+  uint64_t full[kGbStages], fixed[kGbStages], empty[kGbStages];
+  uint64_t df_full;
+  uint32_t tmem_slot;
+  uint32_t pad_;
+  alignas(16) float y_own[128];
+  alignas(16) float s_own[128];
+  alignas(16) float y_col[kGbStages][64];
+  alignas(16) float s_col[kGbStages][64];
+};
+
+template <bool kBf16>
+__device__ __forceinline__ void gb_unpack(uint32_t v, float& a, float& b) {
+  if (kBf16) {
+    a = __uint_as_float(v << 16);
+    b = __uint_as_float(v & 0xffff0000u);
+  } else {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&v));
+    a = f.x;
+    b = f.y;
+  }
+}
+
+// One 16-byte unit (8 pairs of one tile row): pairs whose labels differ are scaled by the row's factor.
+template <bool kBf16>
+__device__ __forceinline__ void gb_fix_unit(uint8_t* unit, float y_row, float s_row, const float* y8) {
+  uint4 v = *reinterpret_cast<uint4*>(unit);
+  const float4 ya = *reinterpret_cast<const float4*>(y8), yb = *reinterpret_cast<const float4*>(y8 + 4);
+  const float ys[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+  uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    float a, b;
+    gb_unpack<kBf16>(w[q], a, b);
+    a = ys[2 * q] == y_row ? a : a * s_row;
+    b = ys[2 * q + 1] == y_row ? b : b * s_row;
+    w[q] = Cvt<kBf16>::two(a, b);
+  }
+  *reinterpret_cast<uint4*>(unit) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <bool kBf16>
+__global__ void __launch_bounds__(kGbThreads, 1)
+fecl_tc_bwd_gemm_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_constant__ CUtensorMap mapT,
+                        const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapG,
+                        const GbParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int KC = p.KC, Dpad = KC * 64;
+  const uint32_t ft_bytes = (uint32_t)KC * kChunk64;                 // F_J (or T_J): [KC chunks][64 j][64 d]
+  const uint32_t stage_bytes = 2 * ft_bytes + 3 * kChunk128;         // F_J | T_J | X_IJ | X_JI | Gc_IJ
+  GbMisc& ms = *reinterpret_cast<GbMisc*>(smem + kGbStages * stage_bytes);
+  const int b = blockIdx.z, i0 = blockIdx.x * kTM, split = blockIdx.y;
+  const int nt_all = (p.N + 63) / 64;
+  const int t0 = (int)((long long)split * nt_all / p.splits), t1 = (int)((long long)(split + 1) * nt_all / p.splits);
+  const int nt = t1 - t0;
+  const bool teacher = p.has_teacher != 0;
+  const unsigned int* flags = p.gc_flag + ((size_t)b * (p.Npad >> 7) + blockIdx.x) * (p.Npad >> 6) + t0;
+
+  if (threadIdx.x == 0) {
+    if (smem_u32(smem) & 1023u) __trap();
+    for (int s = 0; s < kGbStages; ++s) {
+      mbar_init(&ms.full[s], 1);
+      mbar_init(&ms.fixed[s], kGbFixThreads / 32);
+      mbar_init(&ms.empty[s], 1);
+    }
+    mbar_init(&ms.df_full, 1);
+    fence_mbar_init();
+    prefetch_tmap(&mapF);
+    prefetch_tmap(&mapX);
+    if (teacher) prefetch_tmap(&mapT), prefetch_tmap(&mapG);
+  }
+  if (warp == 1) tmem_alloc(&ms.tmem_slot, 512);
+  tcgen05_before_sync();
+  __syncthreads();
+  tcgen05_after_sync();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, ms.tmem_slot, 0);
+  const uint32_t tm_d1 = tmem, tm_d2 = tmem + 256;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (nt > 0 && elect_one()) {
+      for (int t = 0; t < nt; ++t) {
+        const int s = t & 1, j0 = (t0 + t) * 64, rowj = b * p.Npad + j0, rowi = b * p.Npad + i0;
+        uint8_t* st = smem + s * stage_bytes;
+        const bool gc_on = teacher && __ldg(flags + t) != 0u;
+        mbar_wait_relaxed(&ms.empty[s], ((t >> 1) & 1) ^ 1);
+        mbar_expect_tx(&ms.full[s], ft_bytes + 2 * kChunk128 + (gc_on ? ft_bytes + kChunk128 : 0u));
+        uint8_t* sx = st + 2 * ft_bytes;
+        tma_load_2d(sx, &mapX, j0, rowi, &ms.full[s]);                           // X_IJ rows i0 .. +63
+        tma_load_2d(sx + kChunk64, &mapX, j0, rowi + 64, &ms.full[s]);           //      rows i0 + 64 .. +127
+        tma_load_2d(sx + kChunk128, &mapX, i0, rowj, &ms.full[s]);               // X_JI columns i0 .. +63
+        tma_load_2d(sx + kChunk128 + kChunk64, &mapX, i0 + 64, rowj, &ms.full[s]);
+        for (int c = 0; c < KC; ++c) tma_load_2d(st + c * kChunk64, &mapF, c * 64, rowj, &ms.full[s]);
+        if (gc_on) {
+          tma_load_2d(sx + 2 * kChunk128, &mapG, j0, rowi, &ms.full[s]);
+          tma_load_2d(sx + 2 * kChunk128 + kChunk64, &mapG, j0, rowi + 64, &ms.full[s]);
+          for (int c = 0; c < KC; ++c) tma_load_2d(st + ft_bytes + c * kChunk64, &mapT, c * 64, rowj, &ms.full[s]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ==================================
+    if (nt > 0 && elect_one()) {
+      const uint32_t idesc_k = umma_idesc_16(128, Dpad, false, true, kBf16);   // A K-major, B = F_J / T_J MN-major
+      const uint32_t idesc_m = umma_idesc_16(128, Dpad, true, true, kBf16);    // A = X_JI MN-major (the transposed tile)
+      bool d2_on = false;
+      for (int t = 0; t < nt; ++t) {
+        const int s = t & 1;
+        const uint32_t st = smem_u32(smem + s * stage_bytes), sx = st + 2 * ft_bytes;
+        const bool gc_on = teacher && __ldg(flags + t) != 0u;
+        // MN-major: 64-element MN blocks are the chunks / boxes (LBO = 8 KB), 8 K rows per 1 KB atom (SBO)
+        const uint64_t f_desc = umma_desc(st, kChunk64, 1024), t_desc = umma_desc(st + ft_bytes, kChunk64, 1024);
+        const uint64_t xij_desc = umma_desc_kmajor(sx), xji_desc = umma_desc(sx + kChunk128, kChunk64, 1024),
+                       gc_desc = umma_desc_kmajor(sx + 2 * kChunk128);
+        mbar_wait_relaxed(&ms.full[s], (t >> 1) & 1);
+        tcgen05_after_sync();
+        if (gc_on) {             // needs no fix-up: runs while the fix-up warps work on the X tiles
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            umma_bf16(tm_d2, desc_advance(gc_desc, k * 32), desc_advance(t_desc, k * 2048), idesc_k, d2_on || k != 0);
+          d2_on = true;
+        }
+        mbar_wait_relaxed(&ms.fixed[s], (t >> 1) & 1);
+        tcgen05_after_sync();
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tm_d1, desc_advance(xij_desc, k * 32), desc_advance(f_desc, k * 2048), idesc_k, (t | k) != 0);
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          umma_bf16(tm_d1, desc_advance(xji_desc, k * 2048), desc_advance(f_desc, k * 2048), idesc_m, true);
+        umma_commit(&ms.empty[s]);
+      }
+      umma_commit(&ms.df_full);
+    }
+  } else if (warp >= 4 && nt > 0) {
+    // ================================ fix-up warps, then the read-out =============
+    const int tt = threadIdx.x - 128;             // 0..511
+    const size_t off = (size_t)b * p.N;
+    const float qnan = __int_as_float(0x7fc00000);
+    const float hscale = __ldg(p.hdr);
+    const float h_mul = p.inv_tau * hscale;
+    const int splits2 = (int)__ldg(p.hdr + 1);
+    const size_t bn = (size_t)gridDim.z * p.N;    // plane stride of the statistics
+    // row j of the sample: its factor for the negative pairs, -kappa_j A_j h_mul / 256 (A = the sweep's per-split
+    // partials, added in split order)
+    auto row_factor = [&](int j) -> float {
+      if (j >= p.N) return 0.f;
+      float part[kMaxSplits];
+#pragma unroll
+      for (int q = 0; q < kMaxSplits; ++q) part[q] = q < splits2 ? __ldg(p.apart + (size_t)q * bn + off + j) : 0.f;
+      float acc = part[0];
+#pragma unroll
+      for (int q = 1; q < kMaxSplits; ++q) acc += part[q];
+      return -(__ldg(p.stat_kappa + off + j) * h_mul) * acc * (1.f / 256.f);
+    };
+    auto row_label = [&](int j) -> float { return j < p.N ? __ldg(p.labels + off + j) : qnan; };
+    // column statistics of tile t: threads 128..191 fetch the labels, 192..255 the factors
+    auto fetch = [&](int t) -> float {
+      if (tt < 128 || tt >= 256) return 0.f;
+      const int j = (t0 + t) * 64 + (tt & 63);
+      return tt < 192 ? row_label(j) : row_factor(j);
+    };
+    auto publish = [&](int slot, float v) {
+      if (tt >= 128 && tt < 192) ms.y_col[slot][tt & 63] = v;
+      else if (tt >= 192 && tt < 256) ms.s_col[slot][tt & 63] = v;
+    };
+    if (tt < 128) {
+      ms.y_own[tt] = row_label(i0 + tt);
+      ms.s_own[tt] = row_factor(i0 + tt);
+    }
+    publish(0, fetch(0));
+    asm volatile("bar.sync 1, 512;" ::: "memory");
+
+    for (int t = 0; t < nt; ++t) {
+      const int s = t & 1;
+      const float nx = fetch(t + 1 < nt ? t + 1 : t);
+      uint8_t* sx = smem + s * stage_bytes + 2 * ft_bytes;
+      mbar_wait(&ms.full[s], (t >> 1) & 1);
+      const int row = tt >> 3, uir = tt & 7;
+      const uint32_t uo = (uint32_t)((uir ^ (row & 7)) << 4);       // (row + 64) & 7 == row & 7
+      // X_IJ: tile row = row i of the CTA, columns = the tile's j
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int r = row + h * 64;
+        gb_fix_unit<kBf16>(sx + h * kChunk64 + row * 128 + uo, ms.y_own[r], ms.s_own[r], &ms.y_col[s][uir * 8]);
+      }
+      // X_JI: tile row = column j of the tile, columns = the CTA's rows i (two boxes of 64)
+#pragma unroll
+      for (int h = 0; h < 2; ++h)
+        gb_fix_unit<kBf16>(sx + kChunk128 + h * kChunk64 + row * 128 + uo, ms.y_col[s][row], ms.s_col[s][row],
+                           &ms.y_own[h * 64 + uir * 8]);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&ms.fixed[s]);
+      publish(s ^ 1, nx);
+      asm volatile("bar.sync 1, 512;" ::: "memory");
+    }
+
+    // ---- (dF1 + gcs dF2) * go -> grad_feat: the 16 warps split the Dpad columns four ways ----
+    bool any_gc = false;
+    if (teacher) {
+      for (int t = lane; t < nt; t += 32) any_gc |= __ldg(flags + t) != 0u;
+      any_gc = __any_sync(0xffffffffu, any_gc);
+    }
+    const int quarter = warp & 3, r = quarter * 32 + lane, i = i0 + r;
+    const bool row_ok = i < p.N;
+    const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
+    mbar_wait(&ms.df_full, 0);
+    tcgen05_after_sync();
+    if (p.pdl) pdl_wait();                          // the zero fill of grad_feat is complete and visible
+    const float go = __ldg(p.grad_out) / hscale;
+    const float gcs = any_gc ? 64.f * hscale * p.lambda_cross / ((float)(*p.cross_cnt) + kTiny) : 0.f;
+    const int cgrp = (warp - 4) >> 2;               // 0..3
+    const int dq = Dpad / 4;                         // columns per column group (multiple of 16)
+    for (int c0 = cgrp * dq; c0 < (cgrp + 1) * dq; c0 += 16) {
+      float v[16];
+      tmem_ld16(tm_d1 + lane_base + c0, v);
+      if (any_gc) {
+        float v2[16];
+        tmem_ld16(tm_d2 + lane_base + c0, v2);
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = fmaf(gcs, v2[c], v[c]);
+      } else {
+        tmem_ld_wait();
+      }
+      if (row_ok) {
+        float* dst = p.grad_feat + (int64_t)b * p.g_sb + (int64_t)i * p.g_sn + (int64_t)c0 * p.g_sd;
+        if (p.g_sd == 1 && ((p.g_sn | p.g_sb) & 3) == 0 &&
+            (reinterpret_cast<uintptr_t>(p.grad_feat) & 15) == 0) {  // rows contiguous and 16-byte aligned: vector stores
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float o0 = go * v[q * 4], o1 = go * v[q * 4 + 1], o2 = go * v[q * 4 + 2], o3 = go * v[q * 4 + 3];
+            if (c0 + q * 4 + 3 < p.D) {
+              if (p.splits == 1) {
+                *reinterpret_cast<float4*>(dst + q * 4) = make_float4(o0, o1, o2, o3);
+              } else {   // two partial sums onto a zero-filled buffer: a + b == b + a, still bit-reproducible
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + q * 4), "f"(o0), "f"(o1),
+                             "f"(o2), "f"(o3) : "memory");
+              }
+            } else {
+              const float o[4] = {o0, o1, o2, o3};
+              for (int k = 0; k < 4; ++k) {
+                if (c0 + q * 4 + k < p.D) {
+                  if (p.splits == 1) dst[q * 4 + k] = o[k]; else atomicAdd(dst + q * 4 + k, o[k]);
+                }
+              }
+            }
+          }
+        } else {   // columns contiguous (the caller's (D*N, 1, N) layout): a warp stores 32 consecutive rows
+#pragma unroll
+          for (int c = 0; c < 16; ++c) {
+            if (c0 + c < p.D) {
+              float* q = dst + (int64_t)c * p.g_sd;
+              if (p.splits == 1) *q = go * v[c];
+              else asm volatile("red.global.add.f32 [%0], %1;" ::"l"(q), "f"(go * v[c]) : "memory");
+            }
+          }
+        }
+      }
+    }
+  }
+  tcgen05_before_sync();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 struct TcState {
   float* hdr;
@@ -1365,6 +1853,10 @@ struct TcState {
   int* cls_hi;
   float* ys;
   float* rws;
+  // stored pairs (see the stored-pairs backward): X, Gc and the tile flags behind everything else
+  void* pair_x;
+  void* pair_gc;
+  unsigned int* gc_flag;
 };
 constexpr size_t kHdrBytes = 1024;   // keeps the operand arrays 1024-B aligned relative to the state base
 inline int npad_of(int N) { return (N + 127) / 128 * 128; }
@@ -1376,6 +1868,34 @@ constexpr int kSortPlanes = 6;
 size_t stats_bytes(int B, int N) {
   return align_up((size_t)(kNumStats + 2 * kMaxSplits + kSortPlanes) * B * N * sizeof(float), 128);
 }
+// Stored pairs: B * Npad^2 16-bit entries per matrix (X, and Gc with a teacher) + the tile flags.  On by default
+// for the per-sample loss (never for a merged batch, whose transposed tiles live on other ranks, nor for rows sorted
+// by label); DYCON_FECL_BWD=recompute selects the recomputing backward, DYCON_FECL_PAIR_GB caps the matrices (GiB).
+bool getenv_sort_on() {
+  static const bool on = [] {
+    const char* e = getenv("DYCON_FECL_SORT");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+size_t pair_matrix_bytes(int B, int N) { return align_up((size_t)B * npad_of(N) * npad_of(N) * 2, 1024); }
+size_t pair_flag_bytes(int B, int N) { return align_up((size_t)B * (npad_of(N) / 128) * (npad_of(N) / 64) * 4, 1024); }
+bool stored_pairs(int B, int N, int has_teacher) {
+  static const bool off = [] {
+    const char* e = getenv("DYCON_FECL_BWD");
+    return e && strcmp(e, "recompute") == 0;
+  }();
+  static const double cap_gb = [] {
+    const char* e = getenv("DYCON_FECL_PAIR_GB");
+    return e ? atof(e) : 16.0;
+  }();
+  if (off || getenv_sort_on()) return false;
+  return (double)pair_matrix_bytes(B, N) * (has_teacher ? 2 : 1) <= cap_gb * (double)(1ull << 30);
+}
+size_t pair_bytes(int B, int N, int has_teacher) {
+  return stored_pairs(B, N, has_teacher) ? pair_matrix_bytes(B, N) * (has_teacher ? 2 : 1) + pair_flag_bytes(B, N) : 0;
+}
+
 TcState carve(void* state, int B, int N, int D, int has_teacher) {
   char* p = reinterpret_cast<char*>(state);
   TcState s;
@@ -1394,6 +1914,11 @@ TcState carve(void* state, int B, int N, int D, int has_teacher) {
   s.cls_hi = sp + 3 * plane;
   s.ys = reinterpret_cast<float*>(sp + 4 * plane);
   s.rws = reinterpret_cast<float*>(sp + 5 * plane);
+  char* q = reinterpret_cast<char*>(state) + kHdrBytes + operand_bytes(B, N, D) * (has_teacher ? 2 : 1) +
+            align_up(stats_bytes(B, N), 1024);
+  s.pair_x = q;
+  s.pair_gc = has_teacher ? q + pair_matrix_bytes(B, N) : nullptr;
+  s.gc_flag = reinterpret_cast<unsigned int*>(q + pair_matrix_bytes(B, N) * (has_teacher ? 2 : 1));
   return s;
 }
 
@@ -1405,13 +1930,7 @@ TcState carve(void* state, int B, int N, int D, int has_teacher) {
 // extra launch (138 vs 150 us; profiles/r2_fecl_timeline.md).  DYCON_FECL_CLASSES=0 sorts but runs the general
 // pair arithmetic on every sub-tile.
 constexpr int kMaxSortRows = 49152;
-bool sort_rows(int N, bool merged) {
-  static const bool on = [] {
-    const char* e = getenv("DYCON_FECL_SORT");
-    return e && e[0] == '1';
-  }();
-  return on && !merged && N <= kMaxSortRows;
-}
+bool sort_rows(int N, bool merged) { return getenv_sort_on() && !merged && N <= kMaxSortRows; }
 bool use_classes() {
   static const bool off = [] {
     const char* e = getenv("DYCON_FECL_CLASSES");
@@ -1462,9 +1981,10 @@ int once_per_device(F f) {
 
 }  // namespace
 
-size_t fecl_tc_state_bytes(int B, int N, int D, int has_teacher) {
+size_t fecl_tc_state_bytes(int B, int N, int D, int has_teacher, bool pairs) {
   if (D % 4 != 0 || D > 256) return 0;
-  return kHdrBytes + operand_bytes(B, N, D) * (has_teacher ? 2 : 1) + stats_bytes(B, N);
+  return kHdrBytes + operand_bytes(B, N, D) * (has_teacher ? 2 : 1) + align_up(stats_bytes(B, N), 1024) +
+         (pairs ? pair_bytes(B, N, has_teacher) : 0);
 }
 size_t fecl_tc_workspace_bytes(int, int, int) { return 16 + sizeof(double) * 3 * kMaxPartials; }
 void fecl_tc_layout(int B, int N, int D, int has_teacher, size_t out[6]) {
@@ -1529,6 +2049,9 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   pk.pdl = no_pdl ? 0 : 1;
   const bool sorted = sort_rows(N, a.merge_B > 0);
   pk.rank = sorted ? s.rank : nullptr;
+  // stored pairs: the loss sweep also leaves the pair terms of the backward in the state (tc_bwd_impl decides the same way)
+  const bool store = !kBf16 && a.merge_B == 0 && row_lo == 0 && row_hi == N && !sorted && stored_pairs(B, N, p.has_teacher);
+  pk.gc_flag = (store && p.has_teacher) ? s.gc_flag : nullptr;
   cudaLaunchAttribute pdl_attr[1];
   pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
@@ -1559,11 +2082,16 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
     DYCON_CUDA(cudaLaunchKernelEx(&pcfg, pack16_kernel<kBf16>, pk));
   }
   // boxes: 128 rows (A tile), 64 rows (a sub-tile of F alone), 32 rows (F | T interleaved in teacher mode)
-  CUtensorMap mapA, mapF64, mapF32, mapT32;
+  CUtensorMap mapA, mapF64, mapF32, mapT32, mapXs, mapGs;
   if (int rc = make_tmap_16_2d(&mapA, s.F, (uint64_t)B * Npad, Dpad, 128, kBf16)) return rc;
   if (int rc = make_tmap_16_2d(&mapF64, s.F, (uint64_t)B * Npad, Dpad, 64, kBf16)) return rc;
   if (int rc = make_tmap_16_2d(&mapF32, s.F, (uint64_t)B * Npad, Dpad, 32, kBf16)) return rc;
   if (int rc = make_tmap_16_2d(&mapT32, p.has_teacher ? s.T : s.F, (uint64_t)B * Npad, Dpad, 32, kBf16)) return rc;
+  // store side of the pair matrices (dummies when nothing is stored: the kernels then never touch them)
+  if (int rc = store ? make_tmap_16_store(&mapXs, s.pair_x, (uint64_t)B * Npad, Npad, kBf16) : (mapXs = mapA, (int)DYCON_OK)) return rc;
+  if (int rc = (store && p.has_teacher) ? make_tmap_16_store(&mapGs, s.pair_gc, (uint64_t)B * Npad, Npad, kBf16)
+                                        : (mapGs = mapXs, (int)DYCON_OK))
+    return rc;
   ReduceWorkspace ws = carve_reduce_workspace(a.workspace);
   SweepParams sp;
   sp.N = N; sp.Npad = Npad; sp.KC = KC; sp.has_teacher = p.has_teacher;
@@ -1597,16 +2125,22 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   sp.stat_p = s.stats + kStatP * plane;
   sp.ticket = ws.ticket; sp.partials = ws.partials; sp.sums_out = a.sums_out; sp.loss_out = a.loss_out;
   if (a.xc) sp.x = *a.xc; else make_exchange_ctx(&sp.x, nullptr, 0, 1, nullptr, DYCON_CHANNEL_FECL, 0.0);
+  sp.pair_x = s.pair_x; sp.pair_gc = s.pair_gc; sp.gc_flag = s.gc_flag;
   // >= 120 KB of dynamic smem also pins one CTA per SM
+  // (the stored-pairs sweep trades one ring stage for 32 KB of staging tiles: never more than this)
   size_t smem = rt01 == 2 ? (size_t)2 * KC * kChunk128 + (size_t)3 * KC * kChunk64 + sizeof(SweepMisc)
                           : (size_t)KC * kChunk128 + (size_t)kSwStages * KC * kChunk64 + sizeof(SweepMisc);
+  if (store && KC < 4) smem += 32768;
   if (smem < 120 * 1024) smem = 120 * 1024;
   if (int rc = once_per_device([] {
         return set_smem(fecl_tc_sweep_kernel<0, kBf16, kNoFocal, 1>) | set_smem(fecl_tc_sweep_kernel<1, kBf16, kNoFocal, 1>) |
                set_smem(fecl_tc_sweep_kernel<2, kBf16, kNoFocal, 1>) | set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2, 1>) |
                set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 1>) | set_smem(fecl_tc_sweep_kernel<0, kBf16, kNoFocal, 2>) |
                set_smem(fecl_tc_sweep_kernel<1, kBf16, kNoFocal, 2>) | set_smem(fecl_tc_sweep_kernel<2, kBf16, kNoFocal, 2>) |
-               set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2, 2>) | set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 2>);
+               set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2, 2>) | set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 2>) |
+               set_smem(fecl_tc_sweep_kernel<2, kBf16, kNoFocal, 1, true>) | set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2, 1, true>) |
+               set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 1, true>) | set_smem(fecl_tc_sweep_kernel<2, kBf16, kNoFocal, 2, true>) |
+               set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2, 2, true>) | set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 2, true>);
       }))
     return rc;
   DYCON_REQUIRE(smem <= 227 * 1024, DYCON_ERR_UNSUPPORTED, "FeCL tensor-core fwd: %zu bytes of shared memory needed", smem);
@@ -1621,21 +2155,25 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   cfg.numAttrs = no_pdl ? 0 : 1;
   sp.pdl = no_pdl ? 0 : 1;
   const int fk = focal_kind(p.sc);
-#define DYCON_SWEEPS(RT)                                                                                             \
-  do {                                                                                                               \
-    if (a.phase_mask & 2)                                                                                            \
-      DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<0, kBf16, kNoFocal, RT>, mapA, mapF64, mapT32, sp));   \
-    if (a.phase_mask & 4)                                                                                            \
-      DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<1, kBf16, kNoFocal, RT>, mapA, mapF64, mapT32, sp));   \
-    if (!(a.phase_mask & 8)) break;                                                                                  \
-    if (fk == kNoFocal)                                                                                              \
-      DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kNoFocal, RT>, mapA, mapF2, mapT32, sp));    \
-    else if (fk == kFocalG2)                                                                                         \
-      DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kFocalG2, RT>, mapA, mapF2, mapT32, sp));    \
-    else                                                                                                             \
-      DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kFocalAny, RT>, mapA, mapF2, mapT32, sp));   \
+#define DYCON_SWEEPS(RT, ST)                                                                                             \
+  do {                                                                                                                   \
+    if (a.phase_mask & 2)                                                                                                \
+      DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<0, kBf16, kNoFocal, RT>, mapA, mapF64, mapT32, mapXs, mapGs, sp));       \
+    if (a.phase_mask & 4)                                                                                                \
+      DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<1, kBf16, kNoFocal, RT>, mapA, mapF64, mapT32, mapXs, mapGs, sp));       \
+    if (!(a.phase_mask & 8)) break;                                                                                      \
+    if (fk == kNoFocal)                                                                                                  \
+      DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kNoFocal, RT, ST>, mapA, mapF2, mapT32, mapXs, mapGs, sp));    \
+    else if (fk == kFocalG2)                                                                                             \
+      DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kFocalG2, RT, ST>, mapA, mapF2, mapT32, mapXs, mapGs, sp));    \
+    else                                                                                                                 \
+      DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<2, kBf16, kFocalAny, RT, ST>, mapA, mapF2, mapT32, mapXs, mapGs, sp));   \
   } while (0)
-  if (rt01 == 2) DYCON_SWEEPS(2); else DYCON_SWEEPS(1);
+  if (rt01 == 2) {
+    if (store) DYCON_SWEEPS(2, true); else DYCON_SWEEPS(2, false);
+  } else {
+    if (store) DYCON_SWEEPS(1, true); else DYCON_SWEEPS(1, false);
+  }
 #undef DYCON_SWEEPS
   DYCON_CUDA(cudaGetLastError());
   count_launches((a.phase_mask & 1) + ((a.phase_mask >> 1) & 1) + ((a.phase_mask >> 2) & 1) + ((a.phase_mask >> 3) & 1));
@@ -1660,6 +2198,57 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
   const int rb_lo = row_lo / 128, rbs = (row_hi + 127) / 128 - rb_lo;
   const bool dense = a.g_sb == (int64_t)gn * D && ((a.g_sn == D && a.g_sd == 1) || (a.g_sn == 1 && a.g_sd == gn));
   bp.splits = dense ? pick_splits(rbs, B) : 1;
+  static const bool no_pdl = [] {
+    const char* e = getenv("DYCON_NO_PDL");
+    return e && e[0] == '1';
+  }();
+  auto zero_fill = [&](int pdl) -> int {
+    const size_t n = (size_t)B * (row_hi - row_lo) * D;
+    const unsigned zgrid = (unsigned)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)sm_count() * 8);
+    zero_fill_kernel<<<zgrid, 256, 0, st>>>(a.grad_feat, n, pdl);
+    DYCON_CUDA(cudaGetLastError());
+    count_launches(1);
+    return DYCON_OK;
+  };
+  cudaLaunchAttribute pdl_attr[1];
+  pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
+  if (!kBf16 && a.grad_rows == 0 && row_lo == 0 && row_hi == N && !sort_rows(N, false) && stored_pairs(B, N, p.has_teacher)) {
+    // ---- stored pairs: streaming GEMM over what the loss sweep left in the state ----
+    CUtensorMap mapF, mapT, mapX, mapG;
+    if (int rc = make_tmap_16_2d(&mapF, s.F, (uint64_t)B * Npad, Dpad, 64, kBf16)) return rc;
+    if (int rc = make_tmap_16_2d(&mapT, p.has_teacher ? s.T : s.F, (uint64_t)B * Npad, Dpad, 64, kBf16)) return rc;
+    if (int rc = make_tmap_16_2d(&mapX, s.pair_x, (uint64_t)B * Npad, Npad, 64, kBf16)) return rc;
+    if (int rc = make_tmap_16_2d(&mapG, p.has_teacher ? s.pair_gc : s.pair_x, (uint64_t)B * Npad, Npad, 64, kBf16)) return rc;
+    GbParams gp;
+    gp.N = N; gp.Npad = Npad; gp.KC = KC; gp.D = D; gp.has_teacher = p.has_teacher;
+    gp.splits = bp.splits;
+    gp.pdl = (gp.splits > 1 && !no_pdl) ? 1 : 0;
+    gp.inv_tau = p.sc.inv_tau; gp.lambda_cross = p.sc.lambda_cross;
+    gp.labels = a.labels;
+    gp.apart = s.stats + (size_t)(kNumStats + kMaxSplits) * plane;
+    gp.stat_kappa = s.stats + kStatKappa * plane;
+    gp.hdr = s.hdr;
+    gp.cross_cnt = a.cross_cnt; gp.gc_flag = s.gc_flag; gp.grad_out = a.grad_out; gp.grad_feat = a.grad_feat;
+    gp.g_sb = a.g_sb; gp.g_sn = a.g_sn; gp.g_sd = a.g_sd;
+    const size_t gsmem = (size_t)kGbStages * (2 * (size_t)KC * kChunk64 + 3 * kChunk128) + sizeof(GbMisc);
+    if (int rc = once_per_device([] { return set_smem(fecl_tc_bwd_gemm_kernel<kBf16>); })) return rc;
+    DYCON_REQUIRE(gsmem <= 227 * 1024, DYCON_ERR_UNSUPPORTED, "FeCL stored-pairs bwd: %zu bytes of shared memory needed", gsmem);
+    if (gp.splits > 1) {
+      if (int rc = zero_fill(gp.pdl)) return rc;
+    }
+    cudaLaunchConfig_t gcfg = {};
+    gcfg.gridDim = dim3(Npad / 128, gp.splits, B);
+    gcfg.blockDim = dim3(kGbThreads);
+    gcfg.dynamicSmemBytes = gsmem < 120 * 1024 ? 120 * 1024 : gsmem;
+    gcfg.stream = st;
+    gcfg.attrs = pdl_attr;
+    gcfg.numAttrs = gp.pdl ? 1 : 0;
+    DYCON_CUDA(cudaLaunchKernelEx(&gcfg, fecl_tc_bwd_gemm_kernel<kBf16>, mapF, mapT, mapX, mapG, gp));
+    DYCON_CUDA(cudaGetLastError());
+    count_launches(1);
+    return DYCON_OK;
+  }
   bp.rb_lo = rb_lo; bp.row_lo = row_lo; bp.row_hi = row_hi; bp.grad_rows = a.grad_rows;
   bp.sc = p.sc;
   bp.c1 = p.sc.inv_tau * kLog2e;
@@ -1683,22 +2272,11 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
       }))
     return rc;
   DYCON_REQUIRE(smem <= 227 * 1024, DYCON_ERR_UNSUPPORTED, "FeCL tensor-core bwd: %zu bytes of shared memory needed", smem);
-  static const bool no_pdl = [] {
-    const char* e = getenv("DYCON_NO_PDL");
-    return e && e[0] == '1';
-  }();
   bp.pdl = 0;
   if (bp.splits > 1) {
     bp.pdl = no_pdl ? 0 : 1;
-    const size_t n = (size_t)B * (row_hi - row_lo) * D;
-    const unsigned zgrid = (unsigned)std::min<size_t>((n / 4 + 255) / 256 + 1, (size_t)sm_count() * 8);
-    zero_fill_kernel<<<zgrid, 256, 0, st>>>(a.grad_feat, n, bp.pdl);
-    DYCON_CUDA(cudaGetLastError());
-    count_launches(1);
+    if (int rc = zero_fill(bp.pdl)) return rc;
   }
-  cudaLaunchAttribute pdl_attr[1];
-  pdl_attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  pdl_attr[0].val.programmaticStreamSerializationAllowed = 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(rbs, bp.splits, B);
   cfg.blockDim = dim3(kBwdThreads);

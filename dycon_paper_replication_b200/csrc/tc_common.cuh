@@ -89,6 +89,18 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, int
       : "memory");
 }
 
+// 2D tile store shared -> global (bulk async-group completion).  The writers of the tile fence.proxy.async and
+// synchronise first; the issuing thread commits the group and, before the tile is overwritten, waits for the reads.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, int c0, int c1, const void* src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // 1D bulk copy global -> shared (16-byte aligned addresses, size a multiple of 16); completes tx bytes on `bar`.
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -199,6 +211,9 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int col) {
 // ---- host side: tensor maps ------------------------------------------------------------------------
 // 2D 16-bit tensor [rows][cols] (cols contiguous), box = [box_rows][64 cols], SWIZZLE_128B.
 int make_tmap_16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, bool bf16);
+// Store side of the stored-pairs matrices (tc_host.cu): 16-bit [rows][cols], box = [128 rows][16 cols] = a dense
+// 4 KB tile of 32-byte rows in shared memory, no swizzle.
+int make_tmap_16_store(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, bool bf16);
 inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   return make_tmap_16_2d(out, base, rows, cols, box_rows, true);
 }
