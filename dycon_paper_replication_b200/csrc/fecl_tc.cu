@@ -480,9 +480,11 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   //  roles derive from it -- sub-tile numbers, smem / TMEM addresses, descriptors -- lives in uniform registers)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int KC = p.KC;
-  // stored pairs: 32 KB of staging tiles for the TMA stores of X / Gc take the place of one ring stage
-  constexpr int kStages = kRT == 2 ? (kStore ? 2 : 3) : (kStore ? kSwStages - 1 : kSwStages);
-  constexpr uint32_t kStgBytes = kStore ? 32768u : 0u;
+  // pair tiles leave through the staging buffers: the stored-pairs loss sweep (X | Gc) and the similarity sweep (S | Gc)
+  constexpr bool kSt = kStore || kMode == 3;
+  // 32 KB of staging tiles for the TMA stores take the place of one ring stage
+  constexpr int kStages = kRT == 2 ? (kSt ? 2 : 3) : (kSt ? kSwStages - 1 : kSwStages);
+  constexpr uint32_t kStgBytes = kSt ? 32768u : 0u;
   constexpr int kSlotCols = 64 * kRT;
   const uint32_t a_tile = (uint32_t)KC * kChunk128, a_bytes = a_tile * kRT, stage_bytes = (uint32_t)KC * kChunk64;
   uint8_t* const sA = smem;
@@ -490,11 +492,11 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   uint8_t* const sStg = sStage + kStages * stage_bytes;      // [team][X | Gc][2 regions][128 rows][16 cols] (kStore)
   SweepMisc& ms = *reinterpret_cast<SweepMisc*>(sStg + kStgBytes);
   const int b = blockIdx.z, i0 = (blockIdx.x + p.rb_lo) * kTM * kRT, split = blockIdx.y;
-  const bool teacher_on = kMode == 2 && p.has_teacher;
+  const bool teacher_on = (kMode == 2 || kMode == 3) && p.has_teacher;
   const int tcols = teacher_on ? 32 : 64;                  // columns per sub-tile
   // sub-tiles that hold at least one real column (stored pairs: the backward reads 64-column tiles, so the
   // columns up to the next multiple of 64 are swept too -- they come out as zeros)
-  const int nt_all = kStore ? (p.N + 63) / 64 * (64 / tcols) : (p.N + tcols - 1) / tcols;
+  const int nt_all = kSt ? (p.N + 63) / 64 * (64 / tcols) : (p.N + tcols - 1) / tcols;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
@@ -505,10 +507,10 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     prefetch_tmap(&mapA);
     prefetch_tmap(&mapF);
     if (teacher_on) prefetch_tmap(&mapT);
-    if (kStore) prefetch_tmap(&mapXs), prefetch_tmap(&mapGs);
-    if (kMode == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
+    if (kSt) prefetch_tmap(&mapXs), prefetch_tmap(&mapGs);
+    if ((kMode == 0 || kMode == 3) && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
       p.hdr[0] = p.hscale;
-      p.hdr[1] = (float)p.splits;       // how many partial A_i planes the backward has to add up
+      p.hdr[1] = kMode == 3 ? 1.f : (float)p.splits;       // how many partial A_i planes the backward has to add up
     }
   }
   if (warp == 1) tmem_alloc(&ms.tmem_slot, kSwSlots * kSlotCols);
@@ -524,7 +526,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   // predecessor through the row statistics, so the TMA producer and the MMA issuers run ahead (operands and
   // class bounds come from the pack / rank kernels, which are complete once the predecessor has passed its own
   // wait) and only the epilogue warps wait, right before they first touch the statistics.
-  if (kMode == 0 && p.pdl) pdl_wait();
+  if ((kMode == 0 || kMode == 3) && p.pdl) pdl_wait();
 
   // ---- which sub-tiles this CTA walks (every agent computes the same map) ----
   RowClass rc{0, 0x7fffffff, 0};
@@ -583,7 +585,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     // (stored pairs: ONE issuer.  With three issuers and a 2- or 4-stage ring an issuer can reach use u + 1 of a
     //  stage before use u has even been loaded; its wait for phase parity p then passes at once, because the barrier
     //  has not completed phase p ^ 1 yet.  In the 3-stage ring every stage has its own issuer.)
-    constexpr int kIssuers = kStore ? 1 : 3;
+    constexpr int kIssuers = kSt ? 1 : 3;
     if (nt > 0 && warp - 1 < kIssuers && elect_one()) {
       const uint32_t idesc = umma_idesc_16(128, 64, false, false, kBf16);
       const uint64_t a_desc0 = umma_desc_kmajor(smem_u32(sA));
@@ -636,7 +638,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     const float qnan = __int_as_float(0x7fc00000);
     const float yi = row_ok ? __ldg(yb + i) : qnan;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
-    if (kMode != 0 && p.pdl) pdl_wait();          // the statistics of the previous sweep are complete from here on
+    if (kMode != 0 && kMode != 3 && p.pdl) pdl_wait();          // the statistics of the previous sweep are complete from here on
     if (tt == 0 && p.pdl) pdl_trigger();          // (after the wait) the next kernel in the stream may set up
     // this thread's columns of a sub-tile: 32 of 64 (F only), or 16 of 32 of both S and CS (teacher)
     const int cbase = kRT == 2 ? 0 : teacher_on ? chalf * 16 : chalf * 32;
@@ -647,7 +649,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       const int c = tt & 63, j = T * tcols + c;
       const bool ok = c < tcols && j < p.N;
       if (tt < 64) return ok ? __ldg(yb + j) : qnan;
-      if (kMode == 0) return 0.f;
+      if (kMode == 0 || kMode == 3) return 0.f;
       return ok ? __ldg(mb + j) * kLog2e : INFINITY;
     };
     auto publish = [&](int slot, float val) {
@@ -730,7 +732,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     for (int t = team; t < nt; t += 2, ++it) {
       const int T = tile_of(tmap, u0 + t);        // sub-tile index inside the sample
       const int slot = it & 1, a = t & (kSwSlots - 1), j0 = T * tcols;
-      const int cls = (kMode == 0 || kStore) ? kClsMixed : tile_class(rc, T, tcols, p.N, ta, tb);      // uniform over the team
+      const int cls = (kMode == 0 || kSt) ? kClsMixed : tile_class(rc, T, tcols, p.N, ta, tb);      // uniform over the team
       DYCON_TL(0, tl_e, 2 + team, t, 0);
       const float nxt = fetch(tile_of(tmap, u0 + (t + 2 < nt ? t + 2 : t)));
       mbar_wait(&ms.acc_full[a], (t / kSwSlots) & 1);
@@ -785,6 +787,21 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
                 }
               }
             }
+          } else if (kMode == 3) {   // acc0 = row max (as mode 0), and the similarities themselves go to pair_x (16-bit)
+            if (diag_here) {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) acc0 = fmaxf(acc0, c == rdiag ? 0.f : v[c]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 32; ++c) acc0 = fmaxf(acc0, v[c]);
+            }
+            uint32_t lo[8], hi[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              lo[q] = Cvt<kBf16>::two(v[2 * q], v[2 * q + 1]);
+              hi[q] = Cvt<kBf16>::two(v[16 + 2 * q], v[16 + 2 * q + 1]);
+            }
+            stage_pairs(lo, hi, j0 + (kRT == 2 ? cb : 0), false);
           } else if (kStore) {       // loss / A partials, and the pair terms of the backward go to pair_x
             uint32_t xp[16];
 #pragma unroll
@@ -854,7 +871,65 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
           }
           const int w0 = i0 + rh * kTM + quarter * 32 - j0 - cb;
           const bool diag_here = w0 + 31 >= 0 && w0 < 16;
-          if (kStore) {
+          if (kMode == 3) {
+            // similarity sweep: row max of S, S itself to pair_x, and the WHOLE cross term -- it depends on no row
+            // statistic: -log(1 - cs + 1e-18) over the hard negatives (dycon_losses.py:217-229) and pair_gc =
+            // 1 / (64 (1 - cs)) for the backward
+            if (diag_here) {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) acc0 = fmaxf(acc0, c == rdiag ? 0.f : v[c]);
+            } else {
+#pragma unroll
+              for (int c = 0; c < 16; ++c) acc0 = fmaxf(acc0, v[c]);
+            }
+            float cprod = 1.f, cmin = 1.f, nh = 0.f;
+            uint32_t xp[8], gp[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
+              const float ys[4] = {yy.x, yy.y, yy.z, yy.w};
+              float gv[4];
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                const int c = q * 4 + k;
+                const bool hard = !(ys[k] == yi) && w[c] > p.sc.cross_thresh;
+                const float fac = hard ? fmaf(-64.f, w[c], 64.f) : 1.f;
+                cmin = fminf(cmin, fac);
+                cprod *= fac;
+                nh += hard ? 1.f : 0.f;
+                gv[k] = hard ? rcp_approx(fac) : 0.f;
+              }
+              xp[q * 2] = Cvt<kBf16>::two(v[q * 4], v[q * 4 + 1]);
+              xp[q * 2 + 1] = Cvt<kBf16>::two(v[q * 4 + 2], v[q * 4 + 3]);
+              gp[q * 2] = Cvt<kBf16>::two(gv[0], gv[1]);
+              gp[q * 2 + 1] = Cvt<kBf16>::two(gv[2], gv[3]);
+            }
+            {
+              const bool rowhard = row_ok && nh > 0.f;
+              if (!rowhard) {
+#pragma unroll
+                for (int u = 0; u < 8; ++u) gp[u] = 0u;
+              }
+              if (__any_sync(0xffffffffu, rowhard) && lane == 0)
+                p.gc_flag[((size_t)b * (p.Npad >> 7) + (i >> 7)) * (p.Npad >> 6) + ((j0 + cb) >> 6)] = 1u;
+              stage_pairs(xp, gp, j0 + (kRT == 2 ? cb : 0), true);
+            }
+            acc3 += nh;
+            if (cmin > 0.f && cprod >= 1e-30f) {
+              acc2 += fmaf(-6.f, nh, lg2_approx(cprod));
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
+                const float ys[4] = {yy.x, yy.y, yy.z, yy.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  const float cs = w[q * 4 + k];
+                  if (!(ys[k] == yi) && cs > p.sc.cross_thresh) acc2 += lg2_approx((1.f - cs) + kTiny);
+                }
+              }
+            }
+          } else if (kStore) {
             // general body + the pair terms of the backward: pair_x as above, pair_gc = 1 / (64 (1 - cs)) on hard
             // negatives (the 64 of cross_pair; the backward folds it into its scalar factor)
             float cprod = 1.f, cmin = 1.f, nh = 0.f;
@@ -988,7 +1063,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       DYCON_TL(0, tl_e, 2 + team, t, 3);
     }
     DYCON_TL(0, tl_e, 2 + team, 62, 0);
-    if (kStore && tt == 0) bulk_wait0();      // this team's TMA stores are complete
+    if (kSt && tt == 0) bulk_wait0();      // this team's TMA stores are complete
 
     // ---- combine the threads that share a row (kRT = 1: 2 teams x 2 column halves; kRT = 2: the 2 teams),
     //      then the column splits ----
@@ -1002,15 +1077,19 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
       for (int u = 0; u < kWriters - 1; ++u) {
         const float4 o = *reinterpret_cast<const float4*>(xch + (u * kRows + r) * 4);
-        if (kMode == 0) acc0 = fmaxf(acc0, o.x); else acc0 += o.x;
+        if (kMode == 0 || kMode == 3) acc0 = fmaxf(acc0, o.x); else acc0 += o.x;
         acc1 += o.y; acc2 += o.z; acc3 += o.w;
       }
       // (a CTA without sub-tiles -- more splits than sub-tiles left after skipping -- still writes its zero
       //  partials: the consumers add up every split's plane)
       if (row_ok) {
-        if (kMode == 0) {
+        if (kMode == 0 || kMode == 3) {
           const float m = acc0 * p.sc.inv_tau;                           // >= 0, so the int ordering is the float ordering
           atomicMax(reinterpret_cast<int*>(p.stat_m + g), __float_as_int(m));
+          if (kMode == 3) {
+            red[1] = (double)(-kLn2 * acc2);
+            red[2] = (double)acc3;
+          }
         } else if (kMode == 1) {
           p.npart[(size_t)split * gridDim.z * p.N + g] = acc0;           // summed in split order by P2 (deterministic)
           if (!p.cls_lo) atomicAdd(p.stat_p + g, acc1);                  // integer-valued: exact in any order
@@ -1053,10 +1132,255 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       }
     }
   }
+  // similarity sweep: the LOCAL cross sums wait in sums_out[1..2] for the row kernel, whose last block adds the
+  // student sum, runs the exchange of a sharded batch and writes the loss
+  if (kMode == 3) {
+    double* scratch = reinterpret_cast<double*>(sStage + 8192);
+    double total_[3];
+    const unsigned int nblocks = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned int bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (grid_sum_last_block<3>(red, total_, p.ticket, p.partials, nblocks, bid, scratch, reinterpret_cast<int*>(sStage + 12288)) &&
+        threadIdx.x == 0) {
+      p.sums_out[1] = total_[1];
+      p.sums_out[2] = total_[2];
+    }
+  }
   DYCON_TL(0, tl_on && warp == 4, 2, 63, 0);
   tcgen05_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, kSwSlots * kSlotCols);
+}
+
+// =================================================================================================
+//  Row kernel: everything of the student term that needs the row statistics, from the stored similarities
+// =================================================================================================
+// The similarity sweep (kMode 3) has left S = F F^T in pair_x as 16-bit numbers (rounding S to fp16 costs less than
+// the rounding of the operands did: |dS| <= 2.4e-4 against a logit scale of 1/tau) together with every row maximum
+// m.  What remains of the forward -- n_i, kappa_i, the row losses, A_i -- and the per-pair gradient terms X need
+// complete ROWS, not tiles: a warp owns a row, keeps its e_ij = 2^(S_ij c1 - m2_j) in registers and walks it three
+// times,
+//   pass 1   n_i = sum of the negatives' e_ij, P_i = number of same-label columns        (dycon_losses.py:183-184,192)
+//   pass 2   positives: phi(d_ij) -> row loss, A_i, X_ij = kappa_i h phi'(d) d (1 - d)     (:186-206)
+//   pass 3   negatives: X_ij = -kappa_i A_i h e_ij                                        (A_i is complete now)
+// and writes X over S in place.  No grid-wide dependency between the passes (a row is warp-local), no tensor core,
+// no TMEM round trip: a plain SIMT kernel at full occupancy, where MUFU and issue slots overlap.  The backward
+// then is a pure streaming GEMM over X (no fix-up).  Columns are handled in groups of eight (one 16-byte load per
+// lane and 256-column chunk); kChunks = ceil(Npad / 256) <= 8 keeps a row in registers (N <= 2048; longer rows use
+// the three-sweep forward).
+constexpr int kRowThreads = 256;
+constexpr int kRowMaxChunks = 8;
+
+struct RowParams {
+  int N, Npad, ncol;         // ncol = the columns the similarity sweep wrote (N rounded up to 64)
+  int rows_per_cta;
+  int pdl;
+  float c1, gamma, kh, inv_rows;      // kh = inv_tau * hscale
+  double inv_rows_d;
+  float lambda_cross;
+  int has_teacher;
+  const float* labels;
+  const float* row_weight;
+  const float* stat_m;
+  void* pair_x;              // in: S (16-bit), out: X
+  float* stat_n;
+  float* stat_kappa;
+  float* stat_a;             // plane 0 of the partial-A planes (hdr[1] = 1)
+  unsigned int* ticket;
+  double* partials;
+  double* sums_out;
+  float* loss_out;
+  ExchangeCtx x;
+};
+
+// The student terms of one positive pair from e = e_ij and n = n_i (pos_fwd_x without the cross factor):
+// phi2 (phi = -ln2 phi2), the A-summand phi'(d) d / T and px = phi'(d) d (1 - d).
+template <int kFocal>
+__device__ __forceinline__ void pos_terms(float e, float n, float gamma, float& phi2, float& a_term, float& px) {
+  const float T = e + n;
+  const float rT = rcp_approx(T);
+  const float d = e * rT;
+  const float L = lg2_approx(fmaxf(d, 1e-30f));      // log2 d (finite even where e underflows)
+  if (kFocal == kNoFocal) {
+    phi2 = L;
+    a_term = -rT;
+    px = -(n * rT);                       // -(1 - d)
+  } else {
+    float omd = 1.f - d;
+    const float w1 = kFocal == kFocalG2 ? omd : pow_gm1(omd, gamma);
+    const float w = w1 * omd;
+    const float y = fmaf(gamma * kLn2 * d, L, -omd);
+    phi2 = L * w;
+    a_term = w1 * y * rT;
+    px = w * y;
+  }
+}
+
+// c ? a : b as ONE selp: left to itself nvcc turns the nested selects of the pair loops into a branch region per pair
+// (BSSY / BRA / BSYNC), which serialises the MUFU latencies of the 56 pairs a lane walks
+__device__ __forceinline__ float fsel(bool c, float a, float b) {
+  float r;
+  asm("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %3, 0;\n\tselp.f32 %0, %1, %2, p;\n\t}" : "=f"(r) : "f"(a), "f"(b), "r"((int)c));
+  return r;
+}
+
+template <int kFocal, int kChunks>
+__global__ void __launch_bounds__(kRowThreads, 2)
+fecl_row_pairs_kernel(const RowParams p) {
+  // column statistics of the sample, permuted so that the two 16-byte reads of a lane's group of eight columns are
+  // conflict-free: column 256 k + 8 l + q lives at [k][q >> 2][l][q & 3]
+  extern __shared__ __align__(16) float rp_smem[];
+  float* const ys = rp_smem;                       // label (padding: NaN -- never "same")
+  float* const nm2 = rp_smem + kChunks * 256;      // -m_j log2(e) (padding: -inf -> e = 0)
+  __shared__ double rp_scratch[32];
+  __shared__ int rp_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int b = blockIdx.y, N = p.N, Npad = p.Npad;
+  const size_t off = (size_t)b * N;
+  const float qnan = __int_as_float(0x7fc00000);
+  if (p.pdl) pdl_wait();                           // row maxima and similarities of the sweep are complete
+  if (tid == 0 && p.pdl) pdl_trigger();
+  for (int j = tid; j < kChunks * 256; j += kRowThreads) {
+    const int k = j >> 8, l = (j >> 3) & 31, q = j & 7;
+    const int o = k * 256 + (q >> 2) * 128 + l * 4 + (q & 3);
+    ys[o] = j < N ? __ldg(p.labels + off + j) : qnan;
+    nm2[o] = j < N ? -(__ldcg(p.stat_m + off + j) * kLog2e) : -INFINITY;
+  }
+  __syncthreads();
+
+  const int r0 = blockIdx.x * p.rows_per_cta;
+  const int r1 = min(r0 + p.rows_per_cta, p.ncol);     // rows up to ncol are read (as X_JI tiles) by the backward
+  double red[1] = {0.0};
+  for (int i = r0 + warp; i < r1; i += kRowThreads / 32) {
+    uint4* row = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.pair_x) + ((size_t)b * Npad + i) * Npad);
+    if (i >= N) {                                   // padded rows: X = 0
+#pragma unroll
+      for (int k = 0; k < kChunks; ++k) {
+        const int c0 = k * 256 + lane * 8;
+        if (c0 < p.ncol) row[c0 >> 3] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      continue;
+    }
+    uint4 sv[kChunks];
+#pragma unroll
+    for (int k = 0; k < kChunks; ++k) {
+      const int c0 = k * 256 + lane * 8;
+      sv[k] = c0 < p.ncol ? __ldcg(row + (c0 >> 3)) : make_uint4(0u, 0u, 0u, 0u);
+    }
+    const float yi = __ldg(p.labels + off + i);
+    const float rw = p.row_weight ? __ldg(p.row_weight + off + i) : 1.f;
+    // the diagonal pair (i, i) belongs to lane (i / 8) % 32: it counts as a same-label column (P_i), carries neither
+    // loss nor gradient (l_ii is multiplied by 0, dycon_losses.py:176-178).  The pair loops treat it like any positive
+    // pair; its terms are taken out of the row sums afterwards and its X is cleared after the row's stores.
+    const bool diag_lane = ((i >> 3) & 31) == lane;
+
+    // ---- pass 1: e_ij, n_i, P_i ----
+    float e[kChunks * 8];
+    float n_i = 0.f, cnt = 0.f;
+#pragma unroll
+    for (int k = 0; k < kChunks; ++k) {
+      const uint32_t w4[4] = {sv[k].x, sv[k].y, sv[k].z, sv[k].w};
+      const float4 ya = *reinterpret_cast<const float4*>(ys + k * 256 + lane * 4);
+      const float4 yb = *reinterpret_cast<const float4*>(ys + k * 256 + 128 + lane * 4);
+      const float4 ma = *reinterpret_cast<const float4*>(nm2 + k * 256 + lane * 4);
+      const float4 mb = *reinterpret_cast<const float4*>(nm2 + k * 256 + 128 + lane * 4);
+      const float yy[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+      const float mm[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+#pragma unroll
+      for (int q2 = 0; q2 < 4; ++q2) {
+        const float2 s2 = __half22float2(*reinterpret_cast<const __half2*>(&w4[q2]));
+        const float ea = ex2_approx(fmaf(s2.x, p.c1, mm[2 * q2])), eb = ex2_approx(fmaf(s2.y, p.c1, mm[2 * q2 + 1]));
+        e[k * 8 + 2 * q2] = ea;
+        e[k * 8 + 2 * q2 + 1] = eb;
+        const bool sa = yy[2 * q2] == yi, sb = yy[2 * q2 + 1] == yi;
+        n_i += fsel(sa, 0.f, ea);
+        n_i += fsel(sb, 0.f, eb);
+        cnt += fsel(sa, 1.f, 0.f);
+        cnt += fsel(sb, 1.f, 0.f);
+      }
+    }
+    n_i = warp_sum(n_i);
+    cnt = warp_sum(cnt);
+    // kappa_i = r_i c_i / (B N),  c_i = 1/(P_i - 1 + 1e-18)   (dycon_losses.py:192)
+    const float kappa = rw / ((cnt - 1.f) + kTiny) * p.inv_rows;
+    const float kx = kappa * p.kh;
+
+    // ---- pass 2: the positives ----
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kChunks; ++k) {
+      const float4 ya = *reinterpret_cast<const float4*>(ys + k * 256 + lane * 4);
+      const float4 yb = *reinterpret_cast<const float4*>(ys + k * 256 + 128 + lane * 4);
+      const float yy[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        float phi2, at, px;
+        pos_terms<kFocal>(e[k * 8 + q], n_i, p.gamma, phi2, at, px);
+        const bool same = yy[q] == yi;                  // select, never multiply: the unused branch may be NaN
+        acc0 += fsel(same, phi2, 0.f);
+        acc1 += fsel(same, at, 0.f);
+        e[k * 8 + q] = fsel(same, px * kx, e[k * 8 + q]);
+      }
+    }
+    {                                                   // the diagonal's terms: e_ii = 2^(S_ii c1 - m2_i)
+      const __half sd = reinterpret_cast<const __half*>(row)[i];     // (re-read before the stores below overwrite it)
+      float phi2, at, px;
+      pos_terms<kFocal>(ex2_approx(fmaf(__half2float(sd), p.c1, -(__ldcg(p.stat_m + off + i) * kLog2e))), n_i, p.gamma, phi2, at, px);
+      acc0 -= fsel(diag_lane, phi2, 0.f);
+      acc1 -= fsel(diag_lane, at, 0.f);
+    }
+    acc0 = warp_sum(acc0);
+    acc1 = warp_sum(acc1);
+    const float fneg = -(kx * acc1);                   // negatives: -kappa_i A_i h e_ij
+
+    // ---- pass 3: the negatives, and X over S ----
+#pragma unroll
+    for (int k = 0; k < kChunks; ++k) {
+      const float4 ya = *reinterpret_cast<const float4*>(ys + k * 256 + lane * 4);
+      const float4 yb = *reinterpret_cast<const float4*>(ys + k * 256 + 128 + lane * 4);
+      const float yy[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+      uint32_t o4[4];
+#pragma unroll
+      for (int q2 = 0; q2 < 4; ++q2) {
+        const float xa = e[k * 8 + 2 * q2] * fsel(yy[2 * q2] == yi, 1.f, fneg);
+        const float xb = e[k * 8 + 2 * q2 + 1] * fsel(yy[2 * q2 + 1] == yi, 1.f, fneg);
+        o4[q2] = Cvt<false>::two(xa, xb);
+      }
+      const int c0 = k * 256 + lane * 8;
+      if (c0 < p.ncol) row[c0 >> 3] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
+    }
+    if (diag_lane) reinterpret_cast<uint16_t*>(row)[i] = 0;        // same thread, after its vector store: program order
+    if (lane == 0) {
+      p.stat_n[off + i] = n_i;
+      p.stat_kappa[off + i] = kappa;
+      p.stat_a[off + i] = acc1;
+      red[0] += (double)(kappa * (-kLn2 * acc0));
+    }
+  }
+
+  // ---- grid sum of the student term; the last block adds the cross sums of the sweep, runs the exchange of a
+  //      sharded batch and writes the loss (same protocol as the tail of the loss sweep) ----
+  double total_[1];
+  const unsigned int nblocks = gridDim.x * gridDim.y, bid = blockIdx.y * gridDim.x + blockIdx.x;
+  if (grid_sum_last_block<1>(red, total_, p.ticket, p.partials, nblocks, bid, rp_scratch, &rp_last) && warp == 0) {
+    double t0 = __shfl_sync(0xffffffffu, total_[0], 0);
+    double t1 = __ldcg(p.sums_out + 1), t2 = __ldcg(p.sums_out + 2);
+    if (p.x.world > 1) {
+      const double tot = exchange_warp(p.x, lane == 0 ? t0 : lane == 1 ? t1 : t2, 3);
+      t0 = __shfl_sync(0xffffffffu, tot, 0);
+      t1 = __shfl_sync(0xffffffffu, tot, 1);
+      t2 = __shfl_sync(0xffffffffu, tot, 2);
+    }
+    if (lane == 0) {
+      const double student = t0 / p.inv_rows_d;
+      p.sums_out[0] = student;
+      p.sums_out[1] = t1;
+      p.sums_out[2] = t2;
+      if (p.loss_out) {
+        const double cross = p.has_teacher ? t1 / (t2 + 1e-18) : 0.0;
+        *p.loss_out = (float)(student * p.inv_rows_d + (double)p.lambda_cross * cross);
+      }
+    }
+  }
 }
 
 // =================================================================================================
@@ -1560,6 +1884,7 @@ constexpr int kGbStages = 2;
 struct GbParams {
   int N, Npad, KC, D, has_teacher;
   int splits, pdl;
+  int fixup;           // 0: X is final (written by the row kernel) -- a pure streaming GEMM
   float inv_tau, lambda_cross;
   const float* labels;
   const float* apart;
@@ -1695,8 +2020,10 @@ fecl_tc_bwd_gemm_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_c
             umma_bf16(tm_d2, desc_advance(gc_desc, k * 32), desc_advance(t_desc, k * 2048), idesc_k, d2_on || k != 0);
           d2_on = true;
         }
-        mbar_wait_relaxed(&ms.fixed[s], (t >> 1) & 1);
-        tcgen05_after_sync();
+        if (p.fixup) {
+          mbar_wait_relaxed(&ms.fixed[s], (t >> 1) & 1);
+          tcgen05_after_sync();
+        }
 #pragma unroll
         for (int k = 0; k < 4; ++k)
           umma_bf16(tm_d1, desc_advance(xij_desc, k * 32), desc_advance(f_desc, k * 2048), idesc_k, (t | k) != 0);
@@ -1739,14 +2066,16 @@ fecl_tc_bwd_gemm_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_c
       if (tt >= 128 && tt < 192) ms.y_col[slot][tt & 63] = v;
       else if (tt >= 192 && tt < 256) ms.s_col[slot][tt & 63] = v;
     };
+    if (p.fixup) {
     if (tt < 128) {
       ms.y_own[tt] = row_label(i0 + tt);
       ms.s_own[tt] = row_factor(i0 + tt);
     }
     publish(0, fetch(0));
     asm volatile("bar.sync 1, 512;" ::: "memory");
+    }
 
-    for (int t = 0; t < nt; ++t) {
+    for (int t = 0; p.fixup && t < nt; ++t) {
       const int s = t & 1;
       const float nx = fetch(t + 1 < nt ? t + 1 : t);
       uint8_t* sx = smem + s * stage_bytes + 2 * ft_bytes;
@@ -1891,6 +2220,15 @@ bool stored_pairs(int B, int N, int has_teacher) {
   }();
   if (off || getenv_sort_on()) return false;
   return (double)pair_matrix_bytes(B, N) * (has_teacher ? 2 : 1) <= cap_gb * (double)(1ull << 30);
+}
+// Similarity sweep + row kernel + pure-GEMM backward (the default where pairs are stored and a row fits the row
+// kernel's registers); DYCON_FECL_FWD=sweeps keeps the three-sweep forward with the fix-up backward.
+bool fused_rows(int B, int N, int has_teacher) {
+  static const bool off = [] {
+    const char* e = getenv("DYCON_FECL_FWD");
+    return e && strcmp(e, "sweeps") == 0;
+  }();
+  return !off && stored_pairs(B, N, has_teacher) && npad_of(N) <= 256 * kRowMaxChunks;
 }
 size_t pair_bytes(int B, int N, int has_teacher) {
   return stored_pairs(B, N, has_teacher) ? pair_matrix_bytes(B, N) * (has_teacher ? 2 : 1) + pair_flag_bytes(B, N) : 0;
@@ -2140,7 +2478,8 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
                set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2, 2>) | set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 2>) |
                set_smem(fecl_tc_sweep_kernel<2, kBf16, kNoFocal, 1, true>) | set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2, 1, true>) |
                set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 1, true>) | set_smem(fecl_tc_sweep_kernel<2, kBf16, kNoFocal, 2, true>) |
-               set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2, 2, true>) | set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 2, true>);
+               set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalG2, 2, true>) | set_smem(fecl_tc_sweep_kernel<2, kBf16, kFocalAny, 2, true>) |
+               set_smem(fecl_tc_sweep_kernel<3, kBf16, kNoFocal, 1>) | set_smem(fecl_tc_sweep_kernel<3, kBf16, kNoFocal, 2>);
       }))
     return rc;
   DYCON_REQUIRE(smem <= 227 * 1024, DYCON_ERR_UNSUPPORTED, "FeCL tensor-core fwd: %zu bytes of shared memory needed", smem);
@@ -2155,6 +2494,56 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   cfg.numAttrs = no_pdl ? 0 : 1;
   sp.pdl = no_pdl ? 0 : 1;
   const int fk = focal_kind(p.sc);
+  if (!kBf16 && store && fused_rows(B, N, p.has_teacher)) {
+    // ---- similarity sweep (row max, S -> pair_x, the whole cross term) + row kernel (n, kappa, loss, A, X over S) ----
+    if (rt01 == 2)
+      DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<3, kBf16, kNoFocal, 2>, mapA, mapF2, mapT32, mapXs, mapGs, sp));
+    else
+      DYCON_CUDA(cudaLaunchKernelEx(&cfg, fecl_tc_sweep_kernel<3, kBf16, kNoFocal, 1>, mapA, mapF2, mapT32, mapXs, mapGs, sp));
+    RowParams rp;
+    rp.N = N; rp.Npad = Npad; rp.ncol = (N + 63) / 64 * 64;
+    const int chunks = (Npad + 255) / 256;
+    int want = 2 * sm_count() / B;                       // CTAs per sample: two resident CTAs per SM over the batch
+    if (want < 1) want = 1;
+    rp.rows_per_cta = ((rp.ncol + want - 1) / want + 7) / 8 * 8;
+    rp.pdl = no_pdl ? 0 : 1;
+    rp.c1 = sp.c1; rp.gamma = p.sc.gamma; rp.kh = p.sc.inv_tau * sp.hscale; rp.inv_rows = (float)p.inv_rows;
+    rp.inv_rows_d = p.inv_rows; rp.lambda_cross = p.sc.lambda_cross; rp.has_teacher = p.has_teacher;
+    rp.labels = a.labels; rp.row_weight = a.row_weight; rp.stat_m = sp.stat_m; rp.pair_x = s.pair_x;
+    rp.stat_n = sp.stat_n; rp.stat_kappa = sp.stat_kappa; rp.stat_a = sp.apart;
+    rp.ticket = ws.ticket; rp.partials = ws.partials; rp.sums_out = a.sums_out; rp.loss_out = a.loss_out;
+    rp.x = sp.x;
+    cudaLaunchConfig_t rcfg = {};
+    rcfg.gridDim = dim3((rp.ncol + rp.rows_per_cta - 1) / rp.rows_per_cta, B);
+    rcfg.blockDim = dim3(kRowThreads);
+    rcfg.dynamicSmemBytes = (size_t)chunks * 256 * 2 * sizeof(float);
+    rcfg.stream = st;
+    rcfg.attrs = pdl_attr;
+    rcfg.numAttrs = no_pdl ? 0 : 1;
+    DYCON_REQUIRE((long long)rcfg.gridDim.x * B <= kMaxPartials, DYCON_ERR_UNSUPPORTED, "FeCL row kernel: %u x %d CTAs", rcfg.gridDim.x, B);
+#define DYCON_ROWK(FK, CH) DYCON_CUDA(cudaLaunchKernelEx(&rcfg, fecl_row_pairs_kernel<FK, CH>, rp))
+#define DYCON_ROWS(CH)                                                          \
+  do {                                                                          \
+    if (fk == kNoFocal) DYCON_ROWK(kNoFocal, CH);                               \
+    else if (fk == kFocalG2) DYCON_ROWK(kFocalG2, CH);                          \
+    else DYCON_ROWK(kFocalAny, CH);                                             \
+  } while (0)
+    switch (chunks) {
+      case 1: DYCON_ROWS(1); break;
+      case 2: DYCON_ROWS(2); break;
+      case 3: DYCON_ROWS(3); break;
+      case 4: DYCON_ROWS(4); break;
+      case 5: DYCON_ROWS(5); break;
+      case 6: DYCON_ROWS(6); break;
+      case 7: DYCON_ROWS(7); break;
+      default: DYCON_ROWS(8); break;
+    }
+#undef DYCON_ROWS
+#undef DYCON_ROWK
+    DYCON_CUDA(cudaGetLastError());
+    count_launches(3);
+    return DYCON_OK;
+  }
 #define DYCON_SWEEPS(RT, ST)                                                                                             \
   do {                                                                                                                   \
     if (a.phase_mask & 2)                                                                                                \
@@ -2223,6 +2612,7 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
     GbParams gp;
     gp.N = N; gp.Npad = Npad; gp.KC = KC; gp.D = D; gp.has_teacher = p.has_teacher;
     gp.splits = bp.splits;
+    gp.fixup = fused_rows(B, N, p.has_teacher) ? 0 : 1;
     gp.pdl = (gp.splits > 1 && !no_pdl) ? 1 : 0;
     gp.inv_tau = p.sc.inv_tau; gp.lambda_cross = p.sc.lambda_cross;
     gp.labels = a.labels;

@@ -339,3 +339,22 @@ def test_label_sorted_variant_in_a_subprocess():
                           "-p", "no:cacheprovider"], env=env, capture_output=True, text=True, cwd=os.path.dirname(here))
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     assert " passed" in out.stdout and "failed" not in out.stdout.splitlines()[-1]
+
+
+@pytest.mark.parametrize("env", [{"DYCON_FECL_FWD": "sweeps"}, {"DYCON_FECL_BWD": "recompute"}],
+                         ids=["three_sweeps_fixup_backward", "recomputing_backward"])
+def test_older_fp16_paths_in_a_subprocess(env):
+    """The default fp16 path is similarity sweep + row kernel + pure-GEMM backward.  The paths it replaced stay in the
+    library -- the three-sweep forward with stored pairs and a fix-up backward (longer rows than the row kernel holds
+    use it; DYCON_FECL_FWD=sweeps forces it) and the recomputing backward (bf16, global negatives, sorted rows;
+    DYCON_FECL_BWD=recompute forces it).  The switches are read once per process: child processes run the parity cases."""
+    import os
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sel = "test_golden or test_ragged or test_backward_work_split or test_single_class"
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(here, "test_gpu_fecl.py"), "-x", "-q", "-k", sel,
+                          "-p", "no:cacheprovider"], env=dict(os.environ, **env), capture_output=True, text=True,
+                         cwd=os.path.dirname(here))
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    assert " passed" in out.stdout and "failed" not in out.stdout.splitlines()[-1]
