@@ -726,18 +726,27 @@ def run_ours(args):
             e2e_step(k)
         e2e_drain()
         fence()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # The copies share the host's PCIe complex with whatever else runs on it: on the pool's boxes the same build gives
+        # 1.45 ms and 2.5 ms per step minutes apart.  K steps are timed three times over; the MEDIAN repetition is the
+        # number, all three are reported, and so is the count of device allocations inside the timed regions (0: the
+        # caching allocator reuses the state buffers, no cudaMalloc stalls the streams).
+        reps = []
+        allocs0 = torch.cuda.memory_stats(dev).get("num_device_alloc", 0)
         w0 = time.time()
-        e0.record()
-        for k in range(args.steps):
-            e2e_step(k)
-        e2e_drain()
-        e1.record()
-        fence()
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for k in range(args.steps):
+                e2e_step(k)
+            e2e_drain()
+            e1.record()
+            fence()
+            reps.append(e0.elapsed_time(e1))
         w1 = time.time()
+        allocs = torch.cuda.memory_stats(dev).get("num_device_alloc", 0) - allocs0
         if sampler:
             sampler.window(w0, w1)
-        ms_e2e = e0.elapsed_time(e1)
+        ms_e2e = sorted(reps)[1]
         if world > 1:
             t = torch.tensor([ms_e2e], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -745,6 +754,8 @@ def run_ours(args):
         e2e = {"value": voxels * world / (ms_e2e / args.steps * 1e-3), "unit": "voxels/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps,
                "h2d_gbs_plain_copy": h2d_gbs, "gpu_numa_node": numa.node,
+               "repetitions_ms_per_step": [r / args.steps for r in reps], "value_is": "median of the three repetitions",
+               "device_allocs_in_timed_regions": int(allocs),
                "note": "pinned host inputs copied in, loss + both gradients copied out, every step; copies of "
                        "neighbouring steps overlap the kernels (3 streams, 2 buffer sets)"}
 

@@ -19,12 +19,14 @@ PKG = os.path.dirname(HERE)
 ROOT = os.path.dirname(PKG)
 # DYCON_TIMELINE=1 builds the measurement variant beside the product library (selected at run time with
 # DYCON_SO_VARIANT=timeline, see _lib.py)
-SO = os.path.join(PKG, "_dycon_b200_timeline.so" if os.environ.get("DYCON_TIMELINE") == "1" else "_dycon_b200.so")
+# DYCON_VARIANT=name DYCON_VARIANT_FLAGS="-DX=1 ..." builds an experiment variant _dycon_b200_<name>.so the same way
+_VARIANT = "timeline" if os.environ.get("DYCON_TIMELINE") == "1" else os.environ.get("DYCON_VARIANT", "")
+SO = os.path.join(PKG, f"_dycon_b200_{_VARIANT}.so" if _VARIANT else "_dycon_b200.so")
 STAMP = SO + ".hash"
 SOURCES = ["api.cu", "uncl.cu", "segcons.cu", "prep.cu", "ema.cu", "sgd_ema.cu", "exchange.cu", "fecl_api.cu", "fecl_simt.cu", "fecl_tc.cu", "tc_host.cu"]
 HEADERS = ["common.cuh", "exchange.cuh", "fecl_math.cuh", "fecl_internal.h", "tc_common.cuh", os.path.join(ROOT, "include", "dycon_b200.h")]
 # DYCON_TIMELINE=1: a measurement build whose FeCL kernels record device-clock stamps (tools/timeline.py)
-_EXTRA = ["-DDYCON_TIMELINE"] if os.environ.get("DYCON_TIMELINE") == "1" else []
+_EXTRA = ["-DDYCON_TIMELINE"] if os.environ.get("DYCON_TIMELINE") == "1" else os.environ.get("DYCON_VARIANT_FLAGS", "").split()
 NVCC_FLAGS = _EXTRA + [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "--use_fast_math" if False else "-DDYCON_NO_GLOBAL_FAST_MATH",   # fast intrinsics are chosen per call site
@@ -56,7 +58,7 @@ def build(force=False, verbose=False):
     if not force and os.path.exists(SO) and os.path.exists(STAMP) and open(STAMP).read().strip() == digest:
         return SO
     objs = []
-    build_dir = os.path.join(ROOT, "build", "obj_timeline" if _EXTRA else "obj")
+    build_dir = os.path.join(ROOT, "build", f"obj_{_VARIANT}" if _VARIANT else "obj")
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for s in sources:

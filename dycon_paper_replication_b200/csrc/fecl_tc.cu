@@ -58,6 +58,12 @@ constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// Tests as 1.0f / 0.0f masks (one FSET each, no predicate): with dozens of pairs per lane in flight ptxas otherwise parks
+// the predicates in bit masks, two LOP3 per pair to build and two more to read.  NaN labels compare unequal to everything
+// (mask_ne is the unordered test), a NaN similarity is never above a threshold.
+__device__ __forceinline__ float mask_eq(float a, float b) { float r; asm("set.eq.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float mask_ne(float a, float b) { float r; asm("set.neu.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ float mask_gt(float a, float b) { float r; asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b)); return r; }
 // Focal variants are compile-time (a runtime `if (focal)` / gamma test per pair costs branches in the
 // hottest loop): 0 = no focal weight, 1 = gamma == 2 (the scripts' value), 2 = any gamma.
 enum { kNoFocal = 0, kFocalG2 = 1, kFocalAny = 2 };
@@ -546,7 +552,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   }
   const int u0 = (int)((long long)split * tmap.count / p.splits), u1 = (int)((long long)(split + 1) * tmap.count / p.splits);
   const int nt = u1 - u0;
-  const bool tl_on = kMode == 2 && blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 1 && lane == 0;   // (timeline build only)
+  const bool tl_on = (kMode == 2 || kMode == 3) && blockIdx.x == 1 && blockIdx.y == 1 && blockIdx.z == 1 && lane == 0;   // (timeline build only)
   (void)tl_on;
 
   if (warp == 0) {
@@ -725,6 +731,30 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
         bulk_commit();
       }
     };
+    // The similarity sweep (kMode 3) stages per WARP: its 32 rows x 16 columns of each buffer (1 KB + 1 KB of the 32 KB)
+    // leave through TMA stores that lane 0 issues -- no team barrier, and a warp only ever waits for its own previous
+    // stores (the team-wide version above spent a third of the sweep in its two barriers per chunk, every thread waiting
+    // for the slowest warp and for the TMA unit to have read the tile).
+    uint8_t* const wbuf = sStg + (warp - 4) * 2048;
+    const int w_row0 = x_row0 + rh * kTM + quarter * 32;        // row (of the whole matrix) of this warp's lane 0
+    const bool w_rows_ok = kRT == 1 || rh == 0 || x_two;
+    auto stage_warp = [&](const uint32_t (&a)[8], const uint32_t (&g)[8], int col_a, const CUtensorMap* mg, int col_g) {
+      if (lane == 0) bulk_wait_read0();      // the previous chunk's stores have read this warp's tiles
+      __syncwarp();
+      uint4* dx = reinterpret_cast<uint4*>(wbuf + lane * 32);
+      dx[0] = make_uint4(a[0], a[1], a[2], a[3]);
+      dx[1] = make_uint4(a[4], a[5], a[6], a[7]);
+      uint4* dg = reinterpret_cast<uint4*>(wbuf + 1024 + lane * 32);
+      dg[0] = make_uint4(g[0], g[1], g[2], g[3]);
+      dg[1] = make_uint4(g[4], g[5], g[6], g[7]);
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0 && w_rows_ok) {
+        tma_store_2d(&mapXs, col_a, w_row0, wbuf);
+        tma_store_2d(mg, col_g, w_row0, wbuf + 1024);
+        bulk_commit();
+      }
+    };
     if (team < nt) publish(0, fetch(tile_of(tmap, u0 + team)));
     sw_team_barrier(team);
     float acc0 = 0.f, acc1 = 0.f, acc2 = 0.f, acc3 = 0.f;
@@ -801,7 +831,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
               lo[q] = Cvt<kBf16>::two(v[2 * q], v[2 * q + 1]);
               hi[q] = Cvt<kBf16>::two(v[16 + 2 * q], v[16 + 2 * q + 1]);
             }
-            stage_pairs(lo, hi, j0 + (kRT == 2 ? cb : 0), false);
+            stage_warp(lo, hi, j0 + cb, &mapXs, j0 + cb + 16);
           } else if (kStore) {       // loss / A partials, and the pair terms of the backward go to pair_x
             uint32_t xp[16];
 #pragma unroll
@@ -882,29 +912,39 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 #pragma unroll
               for (int c = 0; c < 16; ++c) acc0 = fmaxf(acc0, v[c]);
             }
-            float cprod = 1.f, cmin = 1.f, nh = 0.f;
             uint32_t xp[8], gp[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              xp[q] = Cvt<kBf16>::two(v[2 * q], v[2 * q + 1]);
+              gp[q] = 0u;
+            }
+            // label masks (1.0f where the labels differ; the pair arithmetic below runs on pairs of columns in packed
+            // fp32).  A chunk in which NO row of the warp meets a column of another label -- most chunks of a sample
+            // whose foreground is a compact region -- carries no cross term at all: warp-uniform skip.
+            float2 df[8], nd2 = make_float2(0.f, 0.f);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
               const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
-              const float ys[4] = {yy.x, yy.y, yy.z, yy.w};
-              float gv[4];
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                const int c = q * 4 + k;
-                const bool hard = !(ys[k] == yi) && w[c] > p.sc.cross_thresh;
-                const float fac = hard ? fmaf(-64.f, w[c], 64.f) : 1.f;
-                cmin = fminf(cmin, fac);
-                cprod *= fac;
-                nh += hard ? 1.f : 0.f;
-                gv[k] = hard ? rcp_approx(fac) : 0.f;
-              }
-              xp[q * 2] = Cvt<kBf16>::two(v[q * 4], v[q * 4 + 1]);
-              xp[q * 2 + 1] = Cvt<kBf16>::two(v[q * 4 + 2], v[q * 4 + 3]);
-              gp[q * 2] = Cvt<kBf16>::two(gv[0], gv[1]);
-              gp[q * 2 + 1] = Cvt<kBf16>::two(gv[2], gv[3]);
+              df[2 * q] = make_float2(mask_ne(yy.x, yi), mask_ne(yy.y, yi));
+              df[2 * q + 1] = make_float2(mask_ne(yy.z, yi), mask_ne(yy.w, yi));
+              nd2 = __fadd2_rn(nd2, __fadd2_rn(df[2 * q], df[2 * q + 1]));
             }
-            {
+            if (__any_sync(0xffffffffu, row_ok && nd2.x + nd2.y > 0.f)) {
+              float cmin = 1.f;
+              float2 cprod2 = make_float2(1.f, 1.f), nh2 = make_float2(0.f, 0.f);
+#pragma unroll
+              for (int q = 0; q < 8; ++q) {
+                const float2 cs2 = make_float2(w[2 * q], w[2 * q + 1]);
+                const float2 hard = __fmul2_rn(df[q], make_float2(mask_gt(cs2.x, p.sc.cross_thresh), mask_gt(cs2.y, p.sc.cross_thresh)));
+                // fac = 64 (1 - cs) on a hard negative, else 1
+                const float2 fac = __ffma2_rn(hard, __ffma2_rn(cs2, make_float2(-64.f, -64.f), make_float2(63.f, 63.f)), make_float2(1.f, 1.f));
+                cmin = fminf(cmin, fminf(fac.x, fac.y));
+                cprod2 = __fmul2_rn(cprod2, fac);
+                nh2 = __fadd2_rn(nh2, hard);
+                const float2 gv = __fmul2_rn(hard, make_float2(rcp_approx(fac.x), rcp_approx(fac.y)));
+                gp[q] = Cvt<kBf16>::two(gv.x, gv.y);
+              }
+              const float nh = nh2.x + nh2.y, cprod = cprod2.x * cprod2.y;
               const bool rowhard = row_ok && nh > 0.f;
               if (!rowhard) {
 #pragma unroll
@@ -912,23 +952,25 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
               }
               if (__any_sync(0xffffffffu, rowhard) && lane == 0)
                 p.gc_flag[((size_t)b * (p.Npad >> 7) + (i >> 7)) * (p.Npad >> 6) + ((j0 + cb) >> 6)] = 1u;
-              stage_pairs(xp, gp, j0 + (kRT == 2 ? cb : 0), true);
-            }
-            acc3 += nh;
-            if (cmin > 0.f && cprod >= 1e-30f) {
-              acc2 += fmaf(-6.f, nh, lg2_approx(cprod));
-            } else {
+              acc3 += nh;
+              if (cmin > 0.f && cprod >= 1e-30f) {
+                acc2 += fmaf(-6.f, nh, lg2_approx(cprod));
+              } else {
+                // rare: a pair with cs >= 1 (NaN / log(1e-18), as in the reference) or collapsed pairs whose product
+                // underflows -- one log per pair
 #pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
-                const float ys[4] = {yy.x, yy.y, yy.z, yy.w};
+                for (int q = 0; q < 4; ++q) {
+                  const float4 yy = *reinterpret_cast<const float4*>(cy + q * 4);
+                  const float ys[4] = {yy.x, yy.y, yy.z, yy.w};
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                  const float cs = w[q * 4 + k];
-                  if (!(ys[k] == yi) && cs > p.sc.cross_thresh) acc2 += lg2_approx((1.f - cs) + kTiny);
+                  for (int k = 0; k < 4; ++k) {
+                    const float cs = w[q * 4 + k];
+                    if (!(ys[k] == yi) && cs > p.sc.cross_thresh) acc2 += lg2_approx((1.f - cs) + kTiny);
+                  }
                 }
               }
             }
+            stage_warp(xp, gp, j0 + cb, &mapGs, j0 + cb);
           } else if (kStore) {
             // general body + the pair terms of the backward: pair_x as above, pair_gc = 1 / (64 (1 - cs)) on hard
             // negatives (the 64 of cross_pair; the backward folds it into its scalar factor)
@@ -1063,7 +1105,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
       DYCON_TL(0, tl_e, 2 + team, t, 3);
     }
     DYCON_TL(0, tl_e, 2 + team, 62, 0);
-    if (kSt && tt == 0) bulk_wait0();      // this team's TMA stores are complete
+    if (kMode == 3 ? lane == 0 : (kStore && tt == 0)) bulk_wait0();      // this warp's / team's TMA stores are complete
 
     // ---- combine the threads that share a row (kRT = 1: 2 teams x 2 column halves; kRT = 2: the 2 teams),
     //      then the column splits ----
@@ -1167,7 +1209,15 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
 // then is a pure streaming GEMM over X (no fix-up).  Columns are handled in groups of eight (one 16-byte load per
 // lane and 256-column chunk); kChunks = ceil(Npad / 256) <= 8 keeps a row in registers (N <= 2048; longer rows use
 // the three-sweep forward).
-constexpr int kRowThreads = 256;
+// Threads per CTA x resident CTAs per SM.  Measured on the B200 at the BraTS19 shape (forward, us): 256 x 1 -> 55.6,
+// 256 x 2 -> 57.7, 128 x 3 -> 57.7, 128 x 4 -> 61.2: eight warps per SM with the whole register file (no spills, the pair
+// loops interleaved as deep as ptxas likes) beat sixteen warps at 128 registers.
+#ifndef DYCON_ROW_THREADS
+#define DYCON_ROW_THREADS 256
+#define DYCON_ROW_MINB 1
+#endif
+constexpr int kRowThreads = DYCON_ROW_THREADS;
+constexpr int kRowMinBlocks = DYCON_ROW_MINB;
 constexpr int kRowMaxChunks = 8;
 
 struct RowParams {
@@ -1215,6 +1265,39 @@ __device__ __forceinline__ void pos_terms(float e, float n, float gamma, float& 
   }
 }
 
+// The same on a pair of columns in packed fp32: from d = e / T, L = log2 d and rT = 1 / T.
+template <int kFocal>
+__device__ __forceinline__ void pos_tail2(float2 d, float2 L, float2 rT, float2 n, float gamma, float2& phi2, float2& a_term,
+                                          float2& px) {
+  if (kFocal == kNoFocal) {
+    phi2 = L;
+    a_term = make_float2(-rT.x, -rT.y);
+    const float2 nr = __fmul2_rn(n, rT);
+    px = make_float2(-nr.x, -nr.y);
+  } else {
+    float2 omd = __fadd2_rn(make_float2(1.f, 1.f), make_float2(-d.x, -d.y));
+    float2 w1 = omd;
+    if (kFocal != kFocalG2) {
+      w1.x = pow_gm1(omd.x, gamma);      // (clamps omd at 0)
+      w1.y = pow_gm1(omd.y, gamma);
+    }
+    const float gl = gamma * kLn2;
+    const float2 w = __fmul2_rn(w1, omd);
+    const float2 y = __ffma2_rn(__fmul2_rn(make_float2(gl, gl), d), L, make_float2(-omd.x, -omd.y));
+    phi2 = __fmul2_rn(L, w);
+    a_term = __fmul2_rn(__fmul2_rn(w1, y), rT);
+    px = __fmul2_rn(w, y);
+  }
+}
+// d, L, rT through the special-function unit: one MUFU.RCP and one MUFU.LG2 per pair (any n).
+template <int kFocal>
+__device__ __forceinline__ void pos_terms2(float2 e, float2 n, float gamma, float2& phi2, float2& a_term, float2& px) {
+  const float2 T = __fadd2_rn(e, n);
+  const float2 rT = make_float2(rcp_approx(T.x), rcp_approx(T.y));
+  const float2 d = __fmul2_rn(e, rT);
+  const float2 L = make_float2(lg2_approx(fmaxf(d.x, 1e-30f)), lg2_approx(fmaxf(d.y, 1e-30f)));
+  pos_tail2<kFocal>(d, L, rT, n, gamma, phi2, a_term, px);
+}
 // c ? a : b as ONE selp: left to itself nvcc turns the nested selects of the pair loops into a branch region per pair
 // (BSSY / BRA / BSYNC), which serialises the MUFU latencies of the 56 pairs a lane walks
 __device__ __forceinline__ float fsel(bool c, float a, float b) {
@@ -1223,33 +1306,75 @@ __device__ __forceinline__ float fsel(bool c, float a, float b) {
   return r;
 }
 
+__device__ __forceinline__ void rp_cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+
+
 template <int kFocal, int kChunks>
-__global__ void __launch_bounds__(kRowThreads, 2)
+__global__ void __launch_bounds__(kRowThreads, kRowMinBlocks)
 fecl_row_pairs_kernel(const RowParams p) {
   // column statistics of the sample, permuted so that the two 16-byte reads of a lane's group of eight columns are
   // conflict-free: column 256 k + 8 l + q lives at [k][q >> 2][l][q & 3]
   extern __shared__ __align__(16) float rp_smem[];
   float* const ys = rp_smem;                       // label (padding: NaN -- never "same")
   float* const nm2 = rp_smem + kChunks * 256;      // -m_j log2(e) (padding: -inf -> e = 0)
+  // per warp: the NEXT row of S, fetched with cp.async while the current row is being worked on (a warp walks its rows
+  // one after the other, four warps per scheduler: without the prefetch a third of the kernel is load latency)
+  uint8_t* const wb = reinterpret_cast<uint8_t*>(rp_smem + 2 * kChunks * 256) + (threadIdx.x >> 5) * (kChunks * 512);
   __shared__ double rp_scratch[32];
   __shared__ int rp_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.y, N = p.N, Npad = p.Npad;
   const size_t off = (size_t)b * N;
   const float qnan = __int_as_float(0x7fc00000);
-  if (p.pdl) pdl_wait();                           // row maxima and similarities of the sweep are complete
-  if (tid == 0 && p.pdl) pdl_trigger();
-  for (int j = tid; j < kChunks * 256; j += kRowThreads) {
-    const int k = j >> 8, l = (j >> 3) & 31, q = j & 7;
-    const int o = k * 256 + (q >> 2) * 128 + l * 4 + (q & 3);
-    ys[o] = j < N ? __ldg(p.labels + off + j) : qnan;
-    nm2[o] = j < N ? -(__ldcg(p.stat_m + off + j) * kLog2e) : -INFINITY;
-  }
-  __syncthreads();
-
   const int r0 = blockIdx.x * p.rows_per_cta;
   const int r1 = min(r0 + p.rows_per_cta, p.ncol);     // rows up to ncol are read (as X_JI tiles) by the backward
   double red[1] = {0.0};
+  auto prefetch = [&](int r) {
+    if (r < r1 && r < N) {
+      const uint8_t* src = reinterpret_cast<const uint8_t*>(p.pair_x) + ((size_t)b * Npad + r) * Npad * 2;
+#pragma unroll
+      for (int k = 0; k < kChunks; ++k) {
+        const int c0 = k * 256 + lane * 8;
+        if (c0 < p.ncol) rp_cp_async16(wb + c0 * 2, src + c0 * 2);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // the labels are inputs of the step: fetched while the sweep still runs (programmatic dependent launch)
+  // (all loads of a thread first, then the stores: one memory round trip per array, not one per element)
+  constexpr int kFill = kChunks * 256 / kRowThreads;
+  {
+    float v[kFill];
+#pragma unroll
+    for (int u = 0; u < kFill; ++u) {
+      const int j = tid + u * kRowThreads;
+      v[u] = j < N ? __ldg(p.labels + off + j) : qnan;
+    }
+#pragma unroll
+    for (int u = 0; u < kFill; ++u) {
+      const int j = tid + u * kRowThreads, k = j >> 8, l = (j >> 3) & 31, q = j & 7;
+      ys[k * 256 + (q >> 2) * 128 + l * 4 + (q & 3)] = v[u];
+    }
+  }
+  if (p.pdl) pdl_wait();                           // row maxima and similarities of the sweep are complete
+  if (tid == 0 && p.pdl) pdl_trigger();
+  prefetch(r0 + warp);                             // the first row travels while the column statistics are set up
+  {
+    float v[kFill];
+#pragma unroll
+    for (int u = 0; u < kFill; ++u) {
+      const int j = tid + u * kRowThreads;
+      v[u] = j < N ? __ldcg(p.stat_m + off + j) : INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < kFill; ++u) {
+      const int j = tid + u * kRowThreads, k = j >> 8, l = (j >> 3) & 31, q = j & 7;
+      nm2[k * 256 + (q >> 2) * 128 + l * 4 + (q & 3)] = -(v[u] * kLog2e);
+    }
+  }
+  __syncthreads();
   for (int i = r0 + warp; i < r1; i += kRowThreads / 32) {
     uint4* row = reinterpret_cast<uint4*>(reinterpret_cast<__half*>(p.pair_x) + ((size_t)b * Npad + i) * Npad);
     if (i >= N) {                                   // padded rows: X = 0
@@ -1260,12 +1385,17 @@ fecl_row_pairs_kernel(const RowParams p) {
       }
       continue;
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();                                   // (the diagonal below was fetched by another lane)
     uint4 sv[kChunks];
 #pragma unroll
     for (int k = 0; k < kChunks; ++k) {
       const int c0 = k * 256 + lane * 8;
-      sv[k] = c0 < p.ncol ? __ldcg(row + (c0 >> 3)) : make_uint4(0u, 0u, 0u, 0u);
+      sv[k] = c0 < p.ncol ? *reinterpret_cast<const uint4*>(wb + c0 * 2) : make_uint4(0u, 0u, 0u, 0u);
     }
+    const __half s_diag = *reinterpret_cast<const __half*>(wb + i * 2);
+    __syncwarp();                                   // every lane has read: the buffer may take the next row
+    prefetch(i + kRowThreads / 32);
     const float yi = __ldg(p.labels + off + i);
     const float rw = p.row_weight ? __ldg(p.row_weight + off + i) : 1.f;
     // the diagonal pair (i, i) belongs to lane (i / 8) % 32: it counts as a same-label column (P_i), carries neither
@@ -1273,9 +1403,12 @@ fecl_row_pairs_kernel(const RowParams p) {
     // pair; its terms are taken out of the row sums afterwards and its X is cleared after the row's stores.
     const bool diag_lane = ((i >> 3) & 31) == lane;
 
+    // The pair arithmetic runs on PAIRS of columns in packed fp32 (FFMA2 / FMUL2 / FADD2: two lanes' worth of fp32 per
+    // issue slot); MUFU, the label masks and the 16-bit conversions stay scalar.
     // ---- pass 1: e_ij, n_i, P_i ----
-    float e[kChunks * 8];
-    float n_i = 0.f, cnt = 0.f;
+    float2 e[kChunks * 4];
+    float2 n2 = make_float2(0.f, 0.f), cnt2 = make_float2(0.f, 0.f);   // cnt: columns with a DIFFERENT label (padding included)
+    const float2 c1c1 = make_float2(p.c1, p.c1);
 #pragma unroll
     for (int k = 0; k < kChunks; ++k) {
       const uint32_t w4[4] = {sv[k].x, sv[k].y, sv[k].z, sv[k].w};
@@ -1283,67 +1416,76 @@ fecl_row_pairs_kernel(const RowParams p) {
       const float4 yb = *reinterpret_cast<const float4*>(ys + k * 256 + 128 + lane * 4);
       const float4 ma = *reinterpret_cast<const float4*>(nm2 + k * 256 + lane * 4);
       const float4 mb = *reinterpret_cast<const float4*>(nm2 + k * 256 + 128 + lane * 4);
-      const float yy[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
-      const float mm[8] = {ma.x, ma.y, ma.z, ma.w, mb.x, mb.y, mb.z, mb.w};
+      const float2 yy[4] = {make_float2(ya.x, ya.y), make_float2(ya.z, ya.w), make_float2(yb.x, yb.y), make_float2(yb.z, yb.w)};
+      const float2 mm[4] = {make_float2(ma.x, ma.y), make_float2(ma.z, ma.w), make_float2(mb.x, mb.y), make_float2(mb.z, mb.w)};
 #pragma unroll
       for (int q2 = 0; q2 < 4; ++q2) {
-        const float2 s2 = __half22float2(*reinterpret_cast<const __half2*>(&w4[q2]));
-        const float ea = ex2_approx(fmaf(s2.x, p.c1, mm[2 * q2])), eb = ex2_approx(fmaf(s2.y, p.c1, mm[2 * q2 + 1]));
-        e[k * 8 + 2 * q2] = ea;
-        e[k * 8 + 2 * q2 + 1] = eb;
-        const bool sa = yy[2 * q2] == yi, sb = yy[2 * q2 + 1] == yi;
-        n_i += fsel(sa, 0.f, ea);
-        n_i += fsel(sb, 0.f, eb);
-        cnt += fsel(sa, 1.f, 0.f);
-        cnt += fsel(sb, 1.f, 0.f);
+        const float2 tl = __ffma2_rn(__half22float2(*reinterpret_cast<const __half2*>(&w4[q2])), c1c1, mm[q2]);
+        const float2 ev = make_float2(ex2_approx(tl.x), ex2_approx(tl.y));            // padded columns: e = 0
+        e[k * 4 + q2] = ev;
+        const float2 df = make_float2(mask_ne(yy[q2].x, yi), mask_ne(yy[q2].y, yi));
+        n2 = __ffma2_rn(df, ev, n2);
+        cnt2 = __fadd2_rn(cnt2, df);
       }
     }
-    n_i = warp_sum(n_i);
-    cnt = warp_sum(cnt);
+    const float n_i = warp_sum(n2.x + n2.y);
+    const float cnt = (float)(kChunks * 256) - warp_sum(cnt2.x + cnt2.y);       // P_i: same-label columns (exact: small integers)
     // kappa_i = r_i c_i / (B N),  c_i = 1/(P_i - 1 + 1e-18)   (dycon_losses.py:192)
     const float kappa = rw / ((cnt - 1.f) + kTiny) * p.inv_rows;
     const float kx = kappa * p.kh;
 
     // ---- pass 2: the positives ----
-    float acc0 = 0.f, acc1 = 0.f;
+    // (the label tests are repeated in every pass from the labels in shared memory; an opaque copy of y_i per pass keeps
+    //  the compiler from carrying 56 masks from pass to pass in registers)
+    // T = e + n is taken with n + 1e-30: the terms of EVERY pair stay finite (a padded column of a row without negatives
+    // has e = n = 0), so that the masks may multiply instead of select -- the reference adds 1e-18 there (:186-187)
+    const float n_t = n_i + 1e-30f;
+    const float2 nt2 = make_float2(n_t, n_t), kx2 = make_float2(kx, kx);
+    float yi2 = yi, yi3 = yi;
+    asm volatile("" : "+f"(yi2));
+    asm volatile("" : "+f"(yi3));
+    float2 a0 = make_float2(0.f, 0.f), a1 = make_float2(0.f, 0.f);
 #pragma unroll
     for (int k = 0; k < kChunks; ++k) {
       const float4 ya = *reinterpret_cast<const float4*>(ys + k * 256 + lane * 4);
       const float4 yb = *reinterpret_cast<const float4*>(ys + k * 256 + 128 + lane * 4);
-      const float yy[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+      const float2 yy[4] = {make_float2(ya.x, ya.y), make_float2(ya.z, ya.w), make_float2(yb.x, yb.y), make_float2(yb.z, yb.w)};
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        float phi2, at, px;
-        pos_terms<kFocal>(e[k * 8 + q], n_i, p.gamma, phi2, at, px);
-        const bool same = yy[q] == yi;                  // select, never multiply: the unused branch may be NaN
-        acc0 += fsel(same, phi2, 0.f);
-        acc1 += fsel(same, at, 0.f);
-        e[k * 8 + q] = fsel(same, px * kx, e[k * 8 + q]);
+      for (int q2 = 0; q2 < 4; ++q2) {
+        float2 phi2, at, px;
+        pos_terms2<kFocal>(e[k * 4 + q2], nt2, p.gamma, phi2, at, px);
+        const float2 same = make_float2(mask_eq(yy[q2].x, yi2), mask_eq(yy[q2].y, yi2));
+        a0 = __ffma2_rn(same, phi2, a0);
+        a1 = __ffma2_rn(same, at, a1);
+        const float2 ev = e[k * 4 + q2];
+        e[k * 4 + q2] = __ffma2_rn(same, __ffma2_rn(px, kx2, make_float2(-ev.x, -ev.y)), ev);    // positives: kappa h px; negatives keep e
       }
     }
+    float acc0 = a0.x + a0.y, acc1 = a1.x + a1.y;
     {                                                   // the diagonal's terms: e_ii = 2^(S_ii c1 - m2_i)
-      const __half sd = reinterpret_cast<const __half*>(row)[i];     // (re-read before the stores below overwrite it)
       float phi2, at, px;
-      pos_terms<kFocal>(ex2_approx(fmaf(__half2float(sd), p.c1, -(__ldcg(p.stat_m + off + i) * kLog2e))), n_i, p.gamma, phi2, at, px);
+      pos_terms<kFocal>(ex2_approx(fmaf(__half2float(s_diag), p.c1, -(__ldcg(p.stat_m + off + i) * kLog2e))), n_t, p.gamma, phi2, at, px);
       acc0 -= fsel(diag_lane, phi2, 0.f);
       acc1 -= fsel(diag_lane, at, 0.f);
     }
     acc0 = warp_sum(acc0);
     acc1 = warp_sum(acc1);
-    const float fneg = -(kx * acc1);                   // negatives: -kappa_i A_i h e_ij
+    if (cnt <= 1.f) acc0 = acc1 = 0.f;                  // a row alone in its class has no positive pair: exactly 0 (kappa is ~1e18 there)
+    const float fneg1 = -(kx * acc1) - 1.f;            // negatives: -kappa_i A_i h e_ij (as a factor 1 + mask (f - 1))
+    const float2 fn2 = make_float2(fneg1, fneg1), one2 = make_float2(1.f, 1.f);
 
     // ---- pass 3: the negatives, and X over S ----
 #pragma unroll
     for (int k = 0; k < kChunks; ++k) {
       const float4 ya = *reinterpret_cast<const float4*>(ys + k * 256 + lane * 4);
       const float4 yb = *reinterpret_cast<const float4*>(ys + k * 256 + 128 + lane * 4);
-      const float yy[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+      const float2 yy[4] = {make_float2(ya.x, ya.y), make_float2(ya.z, ya.w), make_float2(yb.x, yb.y), make_float2(yb.z, yb.w)};
       uint32_t o4[4];
 #pragma unroll
       for (int q2 = 0; q2 < 4; ++q2) {
-        const float xa = e[k * 8 + 2 * q2] * fsel(yy[2 * q2] == yi, 1.f, fneg);
-        const float xb = e[k * 8 + 2 * q2 + 1] * fsel(yy[2 * q2 + 1] == yi, 1.f, fneg);
-        o4[q2] = Cvt<false>::two(xa, xb);
+        const float2 df = make_float2(mask_ne(yy[q2].x, yi3), mask_ne(yy[q2].y, yi3));
+        const float2 xv = __fmul2_rn(e[k * 4 + q2], __ffma2_rn(df, fn2, one2));
+        o4[q2] = Cvt<false>::two(xv.x, xv.y);
       }
       const int c0 = k * 256 + lane * 8;
       if (c0 < p.ncol) row[c0 >> 3] = make_uint4(o4[0], o4[1], o4[2], o4[3]);
@@ -1955,6 +2097,8 @@ fecl_tc_bwd_gemm_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_c
   const int nt = t1 - t0;
   const bool teacher = p.has_teacher != 0;
   const unsigned int* flags = p.gc_flag + ((size_t)b * (p.Npad >> 7) + blockIdx.x) * (p.Npad >> 6) + t0;
+  const bool gtl_on = blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 1 && lane == 0;     // (timeline build only)
+  (void)gtl_on;
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
@@ -1984,6 +2128,7 @@ fecl_tc_bwd_gemm_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_c
         uint8_t* st = smem + s * stage_bytes;
         const bool gc_on = teacher && __ldg(flags + t) != 0u;
         mbar_wait_relaxed(&ms.empty[s], ((t >> 1) & 1) ^ 1);
+        DYCON_TL(1, gtl_on, 0, t, 0);
         mbar_expect_tx(&ms.full[s], ft_bytes + 2 * kChunk128 + (gc_on ? ft_bytes + kChunk128 : 0u));
         uint8_t* sx = st + 2 * ft_bytes;
         tma_load_2d(sx, &mapX, j0, rowi, &ms.full[s]);                           // X_IJ rows i0 .. +63
@@ -2013,6 +2158,7 @@ fecl_tc_bwd_gemm_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_c
         const uint64_t xij_desc = umma_desc_kmajor(sx), xji_desc = umma_desc(sx + kChunk128, kChunk64, 1024),
                        gc_desc = umma_desc_kmajor(sx + 2 * kChunk128);
         mbar_wait_relaxed(&ms.full[s], (t >> 1) & 1);
+        DYCON_TL(1, gtl_on, 1, t, 0);
         tcgen05_after_sync();
         if (gc_on) {             // needs no fix-up: runs while the fix-up warps work on the X tiles
 #pragma unroll
@@ -2031,6 +2177,7 @@ fecl_tc_bwd_gemm_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_c
         for (int k = 0; k < 4; ++k)
           umma_bf16(tm_d1, desc_advance(xji_desc, k * 2048), desc_advance(f_desc, k * 2048), idesc_m, true);
         umma_commit(&ms.empty[s]);
+        DYCON_TL(1, gtl_on, 1, t, 2);
       }
       umma_commit(&ms.df_full);
     }
@@ -2110,6 +2257,7 @@ fecl_tc_bwd_gemm_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_c
     const bool row_ok = i < p.N;
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     mbar_wait(&ms.df_full, 0);
+    DYCON_TL(1, gtl_on && warp == 4, 2, 62, 1);
     tcgen05_after_sync();
     if (p.pdl) pdl_wait();                          // the zero fill of grad_feat is complete and visible
     const float go = __ldg(p.grad_out) / hscale;
@@ -2164,6 +2312,7 @@ fecl_tc_bwd_gemm_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_c
       }
     }
   }
+  DYCON_TL(1, gtl_on && warp == 4, 2, 63, 0);
   tcgen05_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
@@ -2426,8 +2575,10 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   if (int rc = make_tmap_16_2d(&mapF32, s.F, (uint64_t)B * Npad, Dpad, 32, kBf16)) return rc;
   if (int rc = make_tmap_16_2d(&mapT32, p.has_teacher ? s.T : s.F, (uint64_t)B * Npad, Dpad, 32, kBf16)) return rc;
   // store side of the pair matrices (dummies when nothing is stored: the kernels then never touch them)
-  if (int rc = store ? make_tmap_16_store(&mapXs, s.pair_x, (uint64_t)B * Npad, Npad, kBf16) : (mapXs = mapA, (int)DYCON_OK)) return rc;
-  if (int rc = (store && p.has_teacher) ? make_tmap_16_store(&mapGs, s.pair_gc, (uint64_t)B * Npad, Npad, kBf16)
+  // (the similarity sweep stages per warp: 32-row boxes; the stored-pairs loss sweep per team: 128-row boxes)
+  const uint32_t sbox = (!kBf16 && store && fused_rows(B, N, p.has_teacher)) ? 32u : 128u;
+  if (int rc = store ? make_tmap_16_store(&mapXs, s.pair_x, (uint64_t)B * Npad, Npad, kBf16, sbox) : (mapXs = mapA, (int)DYCON_OK)) return rc;
+  if (int rc = (store && p.has_teacher) ? make_tmap_16_store(&mapGs, s.pair_gc, (uint64_t)B * Npad, Npad, kBf16, sbox)
                                         : (mapGs = mapXs, (int)DYCON_OK))
     return rc;
   ReduceWorkspace ws = carve_reduce_workspace(a.workspace);
@@ -2503,9 +2654,10 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
     RowParams rp;
     rp.N = N; rp.Npad = Npad; rp.ncol = (N + 63) / 64 * 64;
     const int chunks = (Npad + 255) / 256;
-    int want = 2 * sm_count() / B;                       // CTAs per sample: two resident CTAs per SM over the batch
+    int want = kRowMinBlocks * sm_count() / B;           // CTAs per sample: the resident CTAs of every SM over the batch
     if (want < 1) want = 1;
-    rp.rows_per_cta = ((rp.ncol + want - 1) / want + 7) / 8 * 8;
+    constexpr int kRowWarps = kRowThreads / 32;
+    rp.rows_per_cta = ((rp.ncol + want - 1) / want + kRowWarps - 1) / kRowWarps * kRowWarps;
     rp.pdl = no_pdl ? 0 : 1;
     rp.c1 = sp.c1; rp.gamma = p.sc.gamma; rp.kh = p.sc.inv_tau * sp.hscale; rp.inv_rows = (float)p.inv_rows;
     rp.inv_rows_d = p.inv_rows; rp.lambda_cross = p.sc.lambda_cross; rp.has_teacher = p.has_teacher;
@@ -2516,12 +2668,21 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
     cudaLaunchConfig_t rcfg = {};
     rcfg.gridDim = dim3((rp.ncol + rp.rows_per_cta - 1) / rp.rows_per_cta, B);
     rcfg.blockDim = dim3(kRowThreads);
-    rcfg.dynamicSmemBytes = (size_t)chunks * 256 * 2 * sizeof(float);
+    rcfg.dynamicSmemBytes = (size_t)chunks * 256 * 2 * sizeof(float) + (size_t)(kRowThreads / 32) * chunks * 512;
     rcfg.stream = st;
     rcfg.attrs = pdl_attr;
     rcfg.numAttrs = no_pdl ? 0 : 1;
     DYCON_REQUIRE((long long)rcfg.gridDim.x * B <= kMaxPartials, DYCON_ERR_UNSUPPORTED, "FeCL row kernel: %u x %d CTAs", rcfg.gridDim.x, B);
-#define DYCON_ROWK(FK, CH) DYCON_CUDA(cudaLaunchKernelEx(&rcfg, fecl_row_pairs_kernel<FK, CH>, rp))
+#define DYCON_ROWK(FK, CH)                                                                                                 \
+  do {                                                                                                                     \
+    if (int rc = once_per_device([] {                                                                                      \
+          DYCON_CUDA(cudaFuncSetAttribute(fecl_row_pairs_kernel<FK, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                          CH * 2048 + (kRowThreads / 32) * CH * 512));                                     \
+          return (int)DYCON_OK;                                                                                            \
+        }))                                                                                                                \
+      return rc;                                                                                                           \
+    DYCON_CUDA(cudaLaunchKernelEx(&rcfg, fecl_row_pairs_kernel<FK, CH>, rp));                                              \
+  } while (0)
 #define DYCON_ROWS(CH)                                                          \
   do {                                                                          \
     if (fk == kNoFocal) DYCON_ROWK(kNoFocal, CH);                               \

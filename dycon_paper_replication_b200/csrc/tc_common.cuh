@@ -213,7 +213,7 @@ __device__ __forceinline__ uint32_t sw128_offset(int row, int col) {
 int make_tmap_16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows, bool bf16);
 // Store side of the stored-pairs matrices (tc_host.cu): 16-bit [rows][cols], box = [128 rows][16 cols] = a dense
 // 4 KB tile of 32-byte rows in shared memory, no swizzle.
-int make_tmap_16_store(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, bool bf16);
+int make_tmap_16_store(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, bool bf16, uint32_t box_rows = 128);
 inline int make_tmap_bf16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
   return make_tmap_16_2d(out, base, rows, cols, box_rows, true);
 }

@@ -67,11 +67,12 @@ int make_tmap_16_2d(CUtensorMap* out, const void* base, uint64_t rows, uint64_t 
   return DYCON_OK;
 }
 
-// Store side of the stored-pairs matrices of the FeCL loss sweep: box = [128 rows][16 cols], no swizzle (the staging
-// tile in shared memory is dense, 32-byte rows).
-int make_tmap_16_store(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, bool bf16) {
+// Store side of the pair matrices of the FeCL sweeps: box = [box_rows][16 cols], no swizzle (the staging tile in shared
+// memory is dense, 32-byte rows): 128 rows for the team-wide staging tiles of the stored-pairs loss sweep, 32 rows for the
+// warp-private tiles of the similarity sweep.
+int make_tmap_16_store(CUtensorMap* out, const void* base, uint64_t rows, uint64_t cols, bool bf16, uint32_t box_rows) {
   static thread_local TmapCache cache;
-  const TmapKey k{base, rows, cols, 0xffffffffu, bf16};
+  const TmapKey k{base, rows, cols, box_rows, bf16};
   for (int i = 0; i < cache.n; ++i) {
     if (cache.key[i] == k) {
       *out = cache.map[i];
@@ -80,10 +81,11 @@ int make_tmap_16_store(CUtensorMap* out, const void* base, uint64_t rows, uint64
   }
   auto fn = encode_fn();
   DYCON_REQUIRE(fn != nullptr, DYCON_ERR_DEVICE, "cuTensorMapEncodeTiled is not available from this driver");
-  DYCON_REQUIRE(aligned(base, 128) && cols % 16 == 0 && rows > 0, DYCON_ERR_ARG, "store tensor map: bad base / cols");
+  DYCON_REQUIRE(aligned(base, 128) && cols % 16 == 0 && rows > 0 && box_rows >= 1 && box_rows <= 256, DYCON_ERR_ARG,
+                "store tensor map: bad base / cols / box");
   const cuuint64_t dims[2] = {cols, rows};
   const cuuint64_t strides[1] = {cols * 2};
-  const cuuint32_t box[2] = {16, 128};
+  const cuuint32_t box[2] = {16, box_rows};
   const cuuint32_t elem_strides[2] = {1, 1};
   CUresult r = fn(out, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, elem_strides,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

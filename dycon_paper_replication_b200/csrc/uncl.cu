@@ -98,6 +98,63 @@ __device__ __forceinline__ void voxel2(float s0, float s1, float t0, float t1, f
   u = S.p_hi * S.p_lo * g1_minus_g0;
 }
 
+// ---- the same for TWO voxels in packed fp32 (FFMA2 / FMUL2 / FADD2: one issue slot for both; sm_100) --------------
+// The C == 2 forward sits between the XU pipe (10 MUFU per voxel) and the issue slots (~80 instructions per voxel): the
+// packed form halves the fp32 share of the latter.  Same operations in the same order as voxel2 -- every packed
+// instruction is the IEEE operation on both halves -- so the results are bit-identical to the scalar form.
+__device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+__device__ __forceinline__ float2 sel2(bool cx, bool cy, float2 a, float2 b) { return make_float2(cx ? a.x : b.x, cy ? a.y : b.y); }
+struct TwoClass2 {
+  float2 p_hi, p_lo, e, x, y, yh, lx, H2;
+  bool hi_x, hi_y;      // hi_is_1 of the two voxels
+};
+__device__ __forceinline__ void two_class_begin2(float2 x0, float2 x1, TwoClass2& o, float2& ope) {
+  const float2 d = __fadd2_rn(x1, neg2(x0));
+  const float2 a = make_float2(fabsf(d.x), fabsf(d.y));
+  o.hi_x = d.x >= 0.f;
+  o.hi_y = d.y >= 0.f;
+  const float2 t = __fmul2_rn(neg2(a), f2(kLog2e));
+  o.e = __fadd2_rn(make_float2(ex2_approx(t.x), ex2_approx(t.y)), __fadd2_rn(a, neg2(a)));   // (a - a): +-inf logits -> NaN
+  ope = __fadd2_rn(f2(1.f), o.e);
+  o.y = __fmul2_rn(f2(kEps), ope);
+  o.x = __fadd2_rn(o.e, o.y);
+}
+__device__ __forceinline__ void two_class_finish2(TwoClass2& o, float2 ope, float2 r_ope) {
+  o.p_hi = r_ope;
+  o.p_lo = __fmul2_rn(o.e, r_ope);
+  const float2 l1 = make_float2(lg2_approx(ope.x), lg2_approx(ope.y));
+  o.lx = make_float2(lg2_approx(o.x.x), lg2_approx(o.x.y));
+  o.yh = __fmul2_rn(__fmul2_rn(f2(kLog2e), o.y), __ffma2_rn(f2(-0.5f), o.y, f2(1.f)));
+  o.H2 = __ffma2_rn(neg2(o.p_lo), o.lx, __ffma2_rn(neg2(o.p_hi), o.yh, l1));
+}
+__device__ __forceinline__ void voxel2x2(float2 s0, float2 s1, float2 t0, float2 t1, float beta, float2& qw, float2& h2,
+                                         float2& u) {
+  TwoClass2 S, T;
+  float2 as, at;
+  two_class_begin2(s0, s1, S, as);
+  two_class_begin2(t0, t1, T, at);
+  const float2 p12 = __fmul2_rn(as, at);
+  const float2 pr = __fmul2_rn(p12, S.x);
+  const float2 r = make_float2(rcp_approx(pr.x), rcp_approx(pr.y));
+  const float2 r_x = __fmul2_rn(r, p12), r12 = __fmul2_rn(r, S.x);
+  two_class_finish2(S, as, __fmul2_rn(r12, at));
+  two_class_finish2(T, at, __fmul2_rn(r12, as));
+  const float2 bs = __fmul2_rn(f2(beta), S.H2), bt = __fmul2_rn(f2(beta), T.H2);
+  const float2 es = make_float2(ex2_approx(bs.x), ex2_approx(bs.y)), et = make_float2(ex2_approx(bt.x), ex2_approx(bt.y));
+  const float2 ws = __fadd2_rn(es, et);
+  const float2 w = make_float2(rcp_approx(ws.x), rcp_approx(ws.y));
+  const float2 d = __fadd2_rn(sel2(S.hi_x, S.hi_y, S.p_hi, S.p_lo), neg2(sel2(T.hi_x, T.hi_y, T.p_hi, T.p_lo)));   // ps1 - pt1
+  const float2 dw = __fmul2_rn(d, w);
+  qw = __fmul2_rn(__fmul2_rn(f2(2.f), d), dw);
+  h2 = __fadd2_rn(S.H2, T.H2);
+  const float2 dl_dh = __ffma2_rn(__fmul2_rn(f2(-beta), __fmul2_rn(__fmul2_rn(f2(2.f), dw), dw)), es, f2(beta));
+  const float2 r_hi = __ffma2_rn(neg2(S.y), __fadd2_rn(f2(1.f), neg2(S.y)), f2(1.f)), r_lo = __fmul2_rn(S.e, r_x);
+  const float2 hml = __ffma2_rn(f2(kLn2), __fadd2_rn(S.yh, neg2(S.lx)), __fadd2_rn(r_hi, neg2(r_lo)));
+  const float2 g = __ffma2_rn(neg2(dl_dh), sel2(S.hi_x, S.hi_y, hml, neg2(hml)), __fmul2_rn(f2(4.f), dw));
+  u = __fmul2_rn(__fmul2_rn(S.p_hi, S.p_lo), g);
+}
+
 template <int kVec>
 struct Pack;
 template <>
@@ -281,14 +338,15 @@ uncl_fwd_c2_pipe_kernel(const float* __restrict__ s, const float* __restrict__ t
       const float4* src = ring + (size_t)(it % kPipeStages) * 4 * kThreads + tid;
       const float4 a0 = src[0], a1 = src[kThreads], b0 = src[2 * kThreads], b1 = src[3 * kThreads];
       float4 uo;
-      float qsum = 0.f, hsum = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        float qw, h2, u;
-        voxel2(elem(a0, k), elem(a1, k), elem(b0, k), elem(b1, k), beta, qw, h2, u);
-        qsum += qw;
-        hsum += h2;
-        set_elem(uo, k, u);
+      float qsum, hsum;
+      {
+        float2 qa, ha, ua, qb, hb, ub;
+        voxel2x2(make_float2(a0.x, a0.y), make_float2(a1.x, a1.y), make_float2(b0.x, b0.y), make_float2(b1.x, b1.y), beta, qa, ha, ua);
+        voxel2x2(make_float2(a0.z, a0.w), make_float2(a1.z, a1.w), make_float2(b0.z, b0.w), make_float2(b1.z, b1.w), beta, qb, hb, ub);
+        // (the scalar form's order of the four additions)
+        qsum = (((0.f + qa.x) + qa.y) + qb.x) + qb.y;
+        hsum = (((0.f + ha.x) + ha.y) + hb.x) + hb.y;
+        uo = make_float4(ua.x, ua.y, ub.x, ub.y);
       }
       *reinterpret_cast<float4*>(stash + (int64_t)cur.b * V + v) = uo;   // default policy: re-read by the backward from L2
       acc += qsum;

@@ -1,0 +1,25 @@
+set -x
+timeout 400 python -m pytest tests/test_gpu_fecl.py -m gpu -x -q -k "golden or seeded or ragged or work_split or single_class or near_identical or unnormalised" > gpurun_out/pytest_r2r.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_r2r.log | cut -c1-400
+timeout 600 python bench.py --steps 50 --warmup 10 --no-cpu-baseline > gpurun_out/bench_r2r.json 2> gpurun_out/bench_r2r.err; echo "bench rc=$?"
+python - <<PY
+import json
+try:
+    d=json.load(open('gpurun_out/bench_r2r.json'))
+    print('value', d['value']/1e9, 'Gvox/s  ms/step', d['ms_per_step'], 'launches', d['gpu_launches'])
+    for k,v in d['roofline_all'].items(): print(' ', k, round(v['avg_ms']*1e3,1),'us frac', round(v['frac'],3))
+except Exception as e:
+    print('bench parse failed', e); print(open('gpurun_out/bench_r2r.err').read()[-3000:])
+PY
+DYCON_SO_VARIANT=timeline timeout 300 python tools/timeline.py > gpurun_out/timeline_r2r.md 2> gpurun_out/timeline_r2r.err; echo "timeline rc=$?"
+B="python bench.py --steps 3 --warmup 3 --no-graph --no-cpu-baseline --no-e2e"
+ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/launches_r2r.csv $B > gpurun_out/ncu_l_r2r.log 2>&1
+python - <<'PY'
+import csv, collections
+rows = list(csv.reader(l for l in open('gpurun_out/launches_r2r.csv') if l.startswith('"')))
+h = rows[0]; ki = h.index('Kernel Name'); vi = h.index('Metric Value')
+agg = collections.defaultdict(list)
+for r in rows[1:]:
+    try: agg[r[ki][:70]].append(float(r[vi].replace(',', '')))
+    except Exception: pass
+for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])): print(f'{k:72s} n={len(v):3d} avg={sum(v)/len(v)/1e3:8.2f} us')
+PY
