@@ -722,7 +722,7 @@ def run_ours(args):
             main.wait_stream(st_in)
             main.wait_stream(st_out)
 
-        for k in range(max(4, min(args.warmup, 6))):
+        for k in range(max(8, min(args.warmup, 12))):      # (the caching allocator needs a few steps to stop growing)
             e2e_step(k)
         e2e_drain()
         fence()

@@ -38,7 +38,7 @@ def main():
         print("not a timeline build: DYCON_TIMELINE=1 python -m dycon_paper_replication_b200.csrc.build, then run with "
               "DYCON_SO_VARIANT=timeline")
         return
-    names = {0: ("P2 sweep", ["tma:stage", "tma:issued", "mma:bfull", "mma:accfree", "mma:commit", "e0:top", "e0:acc", "e0:math",
+    names = {0: ("tensor-core sweep (similarity sweep in the default fp16 path, loss sweep otherwise)", ["tma:stage", "tma:issued", "mma:bfull", "mma:accfree", "mma:commit", "e0:top", "e0:acc", "e0:math",
                               "e0:bar", "e1:top", "e1:acc", "e1:math", "e1:bar"]),
              1: ("backward", ["tma:stage", "mma1:bfull", "mma1:scfree", "mma1:commit", "mma2:hfull", "mma2:commit", "e0:top",
                               "e0:sc", "e0:math", "e0:hfree", "e0:bar", "e1:top", "e1:sc", "e1:math", "e1:hfree", "e1:bar", "cls"])}
@@ -50,6 +50,16 @@ def main():
             continue
         t0 = nz.min()
         rel = lambda v: "" if v <= 0 else str(int(v - t0))
+        if kern == 1 and not (d[2:4, :62, :5] > 0).any():
+            # the pure-GEMM backward (fecl_tc_bwd_gemm_kernel): producer and MMA issuer only, no pair arithmetic
+            print(f"\n## backward GEMM: cycles since the first stamp (accumulators complete: {rel(d[2, 62, 1])}, kernel tail: {rel(d[2, 63, 0])})\n")
+            print("| 64-column tile | tma: stage free | mma: operands landed | mma: 12 MMAs issued |")
+            print("|---:|---:|---:|---:|")
+            for t in range(62):
+                row = [d[0, t, 0], d[1, t, 0], d[1, t, 2]]
+                if any(v > 0 for v in row):
+                    print(f"| {t} | " + " | ".join(rel(v) for v in row) + " |")
+            continue
         print(f"\n## {title}: cycles since the first stamp (end of loop e0/e1: {rel(d[2, 62, 0])} / {rel(d[3, 62, 0])}, "
               f"df_full e0: {rel(d[2, 62, 1])}, kernel tail: {rel(d[2, 63, 0])})\n")
         print("| t | " + " | ".join(cols) + " |")
