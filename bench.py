@@ -49,6 +49,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replays")
+    ap.add_argument("--overlap", action="store_true",
+                    help="launch the UnCL branch (forward and, through autograd, its backward) on a second stream "
+                         "beside the FeCL branch: a fork / join inside the captured step")
     ap.add_argument("--train-step", action="store_true",
                     help="BASELINE config 3: the full mean-teacher train step with the reference UNet3D as context "
                          "(tools/train_step.py: reference vs drop-in vs fused arms, loss trajectories + step-time breakdown)")
@@ -550,12 +553,26 @@ def run_ours(args):
     set_bytes = sum(x.numel() * 4 for x in (host_sets[0].s_logits, host_sets[0].t_logits, host_sets[0].feat,
                                             host_sets[0].teacher)) + 3 * voxels * 4
 
+    branch = torch.cuda.Stream() if args.overlap else None
+
     def step(k):
         s, t, f, tf, m = sets[k % len(sets)]
         s.grad = None
         f.grad = None
-        loss = U_WEIGHT * (fecl(feat=f, mask=m, teacher_feat=tf, gambling_uncertainty=None, epoch=EPOCH)
-                           + uncl(s, t, BETA))
+        if branch is None:
+            loss = U_WEIGHT * (fecl(feat=f, mask=m, teacher_feat=tf, gambling_uncertainty=None, epoch=EPOCH)
+                               + uncl(s, t, BETA))
+        else:
+            # the two losses share no data: the UnCL kernels run on their own stream (autograd keeps the backward of a
+            # node on the stream of its forward and joins the streams when backward() returns)
+            cur = torch.cuda.current_stream()
+            branch.wait_stream(cur)
+            lf = fecl(feat=f, mask=m, teacher_feat=tf, gambling_uncertainty=None, epoch=EPOCH)
+            with torch.cuda.stream(branch):
+                lu = uncl(s, t, BETA)
+            cur.wait_stream(branch)
+            lu.record_stream(cur)
+            loss = U_WEIGHT * (lf + lu)
         loss.backward()
         return loss
 
@@ -862,7 +879,8 @@ def run_ours(args):
                                                                    if args.global_negatives else ""),
                        "fecl_precision": precision,
                        "l2": f"rotating {args.sets} input sets of {set_bytes / 1e6:.0f} MB each (> 126 MB L2), no flush",
-                       "launch": "CUDA-graph replay of the step (one graph per input set)" if use_graph else "eager",
+                       "launch": ("CUDA-graph replay of the step (one graph per input set)" if use_graph else "eager")
+                                 + (", UnCL branch on a second stream" if args.overlap else ""),
                        "loss_check": final_loss},
             "roofline": roofline, "roofline_all": roof_all,
             "gpu_launches": int(launches), "clocks": clocks}

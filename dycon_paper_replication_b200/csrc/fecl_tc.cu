@@ -44,8 +44,24 @@ __device__ unsigned long long g_timeline[2][4][64][8];      // [kernel: 0 sweep 
     if ((on) && (t) < 64) g_timeline[kern][role][t][ev] = (unsigned long long)clock64(); \
   } while (0)
 __device__ __forceinline__ void g_tl_cls(int t, int cls) { if (t < 64) g_timeline[1][0][t][7] = (unsigned long long)cls; }
+// Spans of EVERY CTA of the four kernels of the default path on the GPU-wide nanosecond timer (%globaltimer): entry,
+// main loop reached, main loop done, exit, SM id, work units -- shows launch skew, programmatic-launch overlap and tails.
+__device__ unsigned long long g_span[4][512][6];            // [0 pack, 1 sweep, 2 row kernel, 3 backward GEMM][CTA][event]
+__device__ __forceinline__ unsigned long long g_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ unsigned int g_smid() { unsigned int r; asm volatile("mov.u32 %0, %%smid;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned int g_cta() { return (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x; }
+#define DYCON_SPAN(kern, on, ev)                                              \
+  do {                                                                        \
+    if ((on) && g_cta() < 512) g_span[kern][g_cta()][ev] = g_now();           \
+  } while (0)
+#define DYCON_SPAN_V(kern, on, ev, val)                                       \
+  do {                                                                        \
+    if ((on) && g_cta() < 512) g_span[kern][g_cta()][ev] = (unsigned long long)(val); \
+  } while (0)
 #else
 #define DYCON_TL(kern, on, role, t, ev) do {} while (0)
+#define DYCON_SPAN(kern, on, ev) do {} while (0)
+#define DYCON_SPAN_V(kern, on, ev, val) do {} while (0)
 __device__ __forceinline__ void g_tl_cls(int, int) {}
 #endif
 
@@ -308,6 +324,8 @@ pack16_kernel(const PackParams p) {
   const int which = blockIdx.z / p.B, b = blockIdx.z - which * p.B;
   const int n0 = blockIdx.x * 64, d0 = blockIdx.y * 64;
   const int tid = threadIdx.x;
+  DYCON_SPAN(0, tid == 0, 0);
+  DYCON_SPAN_V(0, tid == 0, 4, g_smid());
   if (p.pdl) pdl_trigger();     // the first sweep may set up (barriers, TMEM) while this grid drains; it waits before reading
   // (ternaries, not p.x[which]: a dynamic index would copy the parameter arrays to local memory)
   const float* s = (which ? p.src[1] : p.src[0]) + (int64_t)b * (which ? p.sb[1] : p.sb[0]);
@@ -374,6 +392,7 @@ pack16_kernel(const PackParams p) {
       }
     }
   }
+  DYCON_SPAN(0, tid == 0, 3);
 }
 
 // =================================================================================================
@@ -486,6 +505,8 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   //  roles derive from it -- sub-tile numbers, smem / TMEM addresses, descriptors -- lives in uniform registers)
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int KC = p.KC;
+  DYCON_SPAN(1, kMode == 3 && threadIdx.x == 0, 0);
+  DYCON_SPAN_V(1, kMode == 3 && threadIdx.x == 0, 4, g_smid());
   // pair tiles leave through the staging buffers: the stored-pairs loss sweep (X | Gc) and the similarity sweep (S | Gc)
   constexpr bool kSt = kStore || kMode == 3;
   // 32 KB of staging tiles for the TMA stores take the place of one ring stage
@@ -533,6 +554,7 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
   // class bounds come from the pack / rank kernels, which are complete once the predecessor has passed its own
   // wait) and only the epilogue warps wait, right before they first touch the statistics.
   if ((kMode == 0 || kMode == 3) && p.pdl) pdl_wait();
+  DYCON_SPAN(1, kMode == 3 && threadIdx.x == 0, 1);
 
   // ---- which sub-tiles this CTA walks (every agent computes the same map) ----
   RowClass rc{0, 0x7fffffff, 0};
@@ -1188,9 +1210,12 @@ fecl_tc_sweep_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_cons
     }
   }
   DYCON_TL(0, tl_on && warp == 4, 2, 63, 0);
+  DYCON_SPAN(1, kMode == 3 && threadIdx.x == 128, 2);           // (warp 4: its epilogue loop and the grid sum are done)
+  DYCON_SPAN_V(1, kMode == 3 && threadIdx.x == 128, 5, nt);
   tcgen05_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, kSwSlots * kSlotCols);
+  DYCON_SPAN(1, kMode == 3 && threadIdx.x == 0, 3);
 }
 
 // =================================================================================================
@@ -1329,6 +1354,8 @@ fecl_row_pairs_kernel(const RowParams p) {
   const size_t off = (size_t)b * N;
   const float qnan = __int_as_float(0x7fc00000);
   const int r0 = blockIdx.x * p.rows_per_cta;
+  DYCON_SPAN(2, tid == 0, 0);
+  DYCON_SPAN_V(2, tid == 0, 4, g_smid());
   const int r1 = min(r0 + p.rows_per_cta, p.ncol);     // rows up to ncol are read (as X_JI tiles) by the backward
   double red[1] = {0.0};
   auto prefetch = [&](int r) {
@@ -1359,6 +1386,7 @@ fecl_row_pairs_kernel(const RowParams p) {
     }
   }
   if (p.pdl) pdl_wait();                           // row maxima and similarities of the sweep are complete
+  DYCON_SPAN(2, tid == 0, 1);
   if (tid == 0 && p.pdl) pdl_trigger();
   prefetch(r0 + warp);                             // the first row travels while the column statistics are set up
   {
@@ -1499,6 +1527,7 @@ fecl_row_pairs_kernel(const RowParams p) {
     }
   }
 
+  DYCON_SPAN(2, tid == 0, 2);
   // ---- grid sum of the student term; the last block adds the cross sums of the sweep, runs the exchange of a
   //      sharded batch and writes the loss (same protocol as the tail of the loss sweep) ----
   double total_[1];
@@ -1523,6 +1552,7 @@ fecl_row_pairs_kernel(const RowParams p) {
       }
     }
   }
+  DYCON_SPAN(2, tid == 0, 3);
 }
 
 // =================================================================================================
@@ -2099,6 +2129,8 @@ fecl_tc_bwd_gemm_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_c
   const unsigned int* flags = p.gc_flag + ((size_t)b * (p.Npad >> 7) + blockIdx.x) * (p.Npad >> 6) + t0;
   const bool gtl_on = blockIdx.x == 3 && blockIdx.y == 0 && blockIdx.z == 1 && lane == 0;     // (timeline build only)
   (void)gtl_on;
+  DYCON_SPAN(3, threadIdx.x == 0, 0);
+  DYCON_SPAN_V(3, threadIdx.x == 0, 4, g_smid());
 
   if (threadIdx.x == 0) {
     if (smem_u32(smem) & 1023u) __trap();
@@ -2258,8 +2290,10 @@ fecl_tc_bwd_gemm_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_c
     const uint32_t lane_base = (uint32_t)(quarter * 32) << 16;
     mbar_wait(&ms.df_full, 0);
     DYCON_TL(1, gtl_on && warp == 4, 2, 62, 1);
+    DYCON_SPAN(3, threadIdx.x == 128, 1);                        // accumulators complete
     tcgen05_after_sync();
     if (p.pdl) pdl_wait();                          // the zero fill of grad_feat is complete and visible
+    DYCON_SPAN(3, threadIdx.x == 128, 2);
     const float go = __ldg(p.grad_out) / hscale;
     const float gcs = any_gc ? 64.f * hscale * p.lambda_cross / ((float)(*p.cross_cnt) + kTiny) : 0.f;
     const int cgrp = (warp - 4) >> 2;               // 0..3
@@ -2316,6 +2350,14 @@ fecl_tc_bwd_gemm_kernel(const __grid_constant__ CUtensorMap mapF, const __grid_c
   tcgen05_before_sync();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
+  DYCON_SPAN(3, threadIdx.x == 0, 3);
+#ifdef DYCON_TIMELINE
+  if (threadIdx.x == 0 && teacher) {         // work of this CTA: tiles, and how many of them carry a Gc tile
+    int ng = 0;
+    for (int t = 0; t < nt; ++t) ng += __ldg(flags + t) != 0u;
+    DYCON_SPAN_V(3, true, 5, ng * 1000 + nt);
+  }
+#endif
 }
 
 // ---- host side -----------------------------------------------------------------------------------
@@ -2586,7 +2628,11 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
   sp.N = N; sp.Npad = Npad; sp.KC = KC; sp.has_teacher = p.has_teacher;
   // all three sweeps: 256-row tiles when the sample has at least two 128-row blocks, and as many column splits
   // (<= 8, at least one 64-column sub-tile each) as fit one wave of SMs
-  const int rt01 = Npad / 128 >= 2 ? 2 : 1;
+  static const int rt_env = [] {                      // DYCON_FECL_RT=1 | 2 forces the row tiles per CTA (experiments)
+    const char* e = getenv("DYCON_FECL_RT");
+    return e ? atoi(e) : 0;
+  }();
+  const int rt01 = rt_env == 1 ? 1 : Npad / 128 >= 2 ? 2 : 1;
   const int rb_lo = row_lo / (128 * rt01);                                   // row blocks that hold rows of this launch
   const int rb01 = (row_hi + 128 * rt01 - 1) / (128 * rt01) - rb_lo;
   int splits01 = sm_count() / (rb01 * B);
@@ -2850,8 +2896,12 @@ int tc_bwd_impl(const FeclProblem& p, const FeclBwdArgs& a, cudaStream_t st) {
 // copies the timeline of the last launches to the host (timeline build only; returns 0 bytes otherwise)
 size_t fecl_tc_debug_timeline(void* host_out, size_t bytes) {
 #ifdef DYCON_TIMELINE
-  const size_t n = sizeof(unsigned long long) * 2 * 4 * 64 * 8;
+  const size_t n = sizeof(unsigned long long) * 2 * 4 * 64 * 8, n2 = sizeof(unsigned long long) * 4 * 512 * 6;
   if (bytes < n || cudaMemcpyFromSymbol(host_out, g_timeline, n) != cudaSuccess) return 0;
+  if (bytes >= n + n2) {         // the per-CTA spans follow the timeline when the caller made room for them
+    if (cudaMemcpyFromSymbol(static_cast<char*>(host_out) + n, g_span, n2) != cudaSuccess) return 0;
+    return n + n2;
+  }
   return n;
 #else
   (void)host_out; (void)bytes;
