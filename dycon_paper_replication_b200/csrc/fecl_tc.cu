@@ -2700,9 +2700,9 @@ int tc_fwd_impl(const FeclProblem& p, const FeclFwdArgs& a, cudaStream_t st) {
     RowParams rp;
     rp.N = N; rp.Npad = Npad; rp.ncol = (N + 63) / 64 * 64;
     const int chunks = (Npad + 255) / 256;
+    constexpr int kRowWarps = kRowThreads / 32;
     int want = kRowMinBlocks * sm_count() / B;           // CTAs per sample: the resident CTAs of every SM over the batch
     if (want < 1) want = 1;
-    constexpr int kRowWarps = kRowThreads / 32;
     rp.rows_per_cta = ((rp.ncol + want - 1) / want + kRowWarps - 1) / kRowWarps * kRowWarps;
     rp.pdl = no_pdl ? 0 : 1;
     rp.c1 = sp.c1; rp.gamma = p.sc.gamma; rp.kh = p.sc.inv_tau * sp.hscale; rp.inv_rows = (float)p.inv_rows;

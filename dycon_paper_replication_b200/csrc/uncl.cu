@@ -280,8 +280,17 @@ constexpr int kPipeStages = 3;
 constexpr int kPipeChunk = 1024;                 // voxels per chunk = 256 threads x float4
 constexpr size_t kPipeSmemBytes = (size_t)kPipeStages * 4 * kThreads * sizeof(float4);   // 48 KB: four CTAs per SM
 
-__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)), "l"(src)
+// The logits are read exactly once: fetched with an L2 evict-first policy they do not push out what the step still
+// needs from the 126 MB L2 -- FeCL's pair matrices (51 MB, written by the forward, read by the backward GEMM) and the
+// stash of this kernel.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+__device__ __forceinline__ void cp_async16_stream(void* dst, const void* src, uint64_t pol) {
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"((uint32_t)__cvta_generic_to_shared(dst)),
+               "l"(src), "l"(pol)
                : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
@@ -303,6 +312,7 @@ uncl_fwd_c2_pipe_kernel(const float* __restrict__ s, const float* __restrict__ t
     while (p.k >= cps) { p.k -= cps; ++p.b; }
   };
   const int nb = (int)(total_chunks / chunks_per_sample);
+  const uint64_t pol = l2_evict_first_policy();
 
   auto issue = [&](const Pos& p, int st) {                // this thread's four 16-byte copies of chunk p
     if (p.b < nb) {
@@ -311,10 +321,10 @@ uncl_fwd_c2_pipe_kernel(const float* __restrict__ s, const float* __restrict__ t
         const float* s0 = s + (2 * (int64_t)p.b) * V + v;
         const float* t0 = t + (2 * (int64_t)p.b) * V + v;
         float4* dst = ring + (size_t)st * 4 * kThreads + tid;
-        cp_async16(dst, s0);
-        cp_async16(dst + kThreads, s0 + V);
-        cp_async16(dst + 2 * kThreads, t0);
-        cp_async16(dst + 3 * kThreads, t0 + V);
+        cp_async16_stream(dst, s0, pol);
+        cp_async16_stream(dst + kThreads, s0 + V, pol);
+        cp_async16_stream(dst + 2 * kThreads, t0, pol);
+        cp_async16_stream(dst + 3 * kThreads, t0 + V, pol);
       }
     }
     cp_async_commit();                                    // always: keeps the group count uniform
@@ -373,9 +383,9 @@ uncl_bwd_c2_kernel(const float* __restrict__ stash, int64_t B, int64_t V, float 
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < nvec; i += 2 * stride) {   // two loads in flight
       const int64_t i2 = i + stride;
       const bool two = i2 < nvec;
-      const vec_t u = *reinterpret_cast<const vec_t*>(st + i * kVec);
+      const vec_t u = __ldcs(reinterpret_cast<const vec_t*>(st + i * kVec));       // last use of the stash: evict first
       vec_t u2 = u;
-      if (two) u2 = *reinterpret_cast<const vec_t*>(st + i2 * kVec);
+      if (two) u2 = __ldcs(reinterpret_cast<const vec_t*>(st + i2 * kVec));
       vec_t p, n, p2, n2;
 #pragma unroll
       for (int k = 0; k < kVec; ++k) {

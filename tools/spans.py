@@ -90,6 +90,25 @@ def main():
             loop = (m[:, 1] - m[:, 0]) / 1e3
             ro = (m[:, 3] - m[:, 2]) / 1e3
             print(f"| {kv % 1000} | {kv // 1000} | {len(m)} | {np.median(loop):.2f} | {loop.max():.2f} | {np.median(ro):.2f} |")
+    d = sp[2][sp[2][:, 0] > 0]
+    if d.size and "--row-detail" in sys.argv:
+        print("\n## row kernel: loop time (programmatic-launch wait passed -> rows done) by CTAs per SM and by quarter of the grid\n")
+        loop = (d[:, 2] - d[:, 1]) / 1e3
+        per_sm = {}
+        for k in range(len(d)):
+            per_sm.setdefault(int(d[k, 4]), []).append(loop[k])
+        by_n = {}
+        for sm, v in per_sm.items():
+            by_n.setdefault(len(v), []).extend(v)
+        for nn, v in sorted(by_n.items()):
+            print(f"- SMs holding {nn} CTA(s): {len(v) // nn} SMs, loop {min(v):.2f} / {np.median(v):.2f} / {max(v):.2f} us")
+        q = len(d) // 4
+        for k in range(4):
+            v = loop[k * q:(k + 1) * q]
+            print(f"- CTAs {k * q}..{(k + 1) * q - 1}: loop {v.min():.2f} / {np.median(v):.2f} / {v.max():.2f} us")
+        order = np.argsort(loop)
+        print("- slowest CTAs (cta, sm, loop us): " + ", ".join(f"({int(k)}, {int(d[k, 4])}, {loop[k]:.1f})" for k in order[-8:]))
+        print("- fastest CTAs (cta, sm, loop us): " + ", ".join(f"({int(k)}, {int(d[k, 4])}, {loop[k]:.1f})" for k in order[:8]))
     d = sp[1][sp[1][:, 0] > 0]
     if d.size:
         print("\n## similarity sweep: CTA loop time (main loop reached -> done) by sub-tile count\n")
