@@ -320,7 +320,11 @@ template <bool kBf16>
 __global__ void __launch_bounds__(256)
 pack16_kernel(const PackParams p) {
   using T16 = typename Cvt<kBf16>::type;
-  __shared__ float tile[64][65];
+  // [64 d][64 n] floats, the column index XORed with 4 (d / 8): a float4 of four consecutive n stays one aligned 16-byte
+  // store, and the transposed reads -- a lane takes 8 consecutive d of one n, eight lanes cover the 64 d of that n --
+  // spread over all 32 banks (bits 2..4 of the bank come from d / 8, bits 0..1 from n)
+  __shared__ __align__(16) float tile[64 * 64];
+  auto tix = [](int d, int n) { return d * 64 + (n ^ (((d >> 3) & 7) << 2)); };
   const int which = blockIdx.z / p.B, b = blockIdx.z - which * p.B;
   const int n0 = blockIdx.x * 64, d0 = blockIdx.y * 64;
   const int tid = threadIdx.x;
@@ -355,28 +359,31 @@ pack16_kernel(const PackParams p) {
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
         const int idx = tid + 256 * k;
-        float* row = &tile[idx >> 4][(idx & 15) * 4];
-        row[0] = v[k].x; row[1] = v[k].y; row[2] = v[k].z; row[3] = v[k].w;
+        *reinterpret_cast<float4*>(&tile[tix(idx >> 4, (idx & 15) * 4)]) = v[k];
       }
     } else {
       const int tx = tid & 63, ty = tid >> 6;
 #pragma unroll 4
       for (int k = ty; k < 64; k += 4) {
         const int n = n0 + tx, d = d0 + k;
-        tile[k][tx] = (n < p.N && d < p.D) ? __ldg(s + n + (int64_t)d * sd) : 0.f;
+        tile[tix(k, tx)] = (n < p.N && d < p.D) ? __ldg(s + n + (int64_t)d * sd) : 0.f;
       }
     }
     __syncthreads();
     if (p.rank && p.pdl) pdl_wait();       // the loads above overlap the rank kernel; its output is needed from here on
-    const int kx = tid & 31, ry = tid >> 5;
-#pragma unroll 4
-    for (int r = ry; r < 64; r += 8) {
-      const int n = n0 + r;
+    // a thread writes 8 consecutive d of one row n as ONE 16-byte store; the eight lanes of a row fill its 128 bytes
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int u = tid + 256 * k, g = u & 7, r = u >> 3, n = n0 + r;
       if (p.merge ? n < p.N : n < p.Npad) {
         const int nd = (p.rank && n < p.N) ? __ldg(p.rank + (size_t)b * p.N + n) : n;
         const float sc = (rscale && n < p.N) ? __ldg(rscale + (size_t)b * p.N + n) : 1.f;
-        *reinterpret_cast<uint32_t*>(dst + ((size_t)b * (p.merge ? p.N : p.Npad) + nd) * p.Dpad + d0 + 2 * kx) =
-            Cvt<kBf16>::two(tile[2 * kx][r] * sc, tile[2 * kx + 1][r] * sc);
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = tile[tix(8 * g + j, r)] * sc;
+        *reinterpret_cast<uint4*>(dst + ((size_t)b * (p.merge ? p.N : p.Npad) + nd) * p.Dpad + d0 + 8 * g) =
+            make_uint4(Cvt<kBf16>::two(f[0], f[1]), Cvt<kBf16>::two(f[2], f[3]), Cvt<kBf16>::two(f[4], f[5]),
+                       Cvt<kBf16>::two(f[6], f[7]));
       }
     }
   } else {         // any other layout (d contiguous or generic): lanes along d for both
